@@ -1,0 +1,128 @@
+/*
+ * tetra_b200.h -- C ABI of libtetra_b200.so: the Blackwell (sm_100a) implementation of the
+ * TetraEar IQ -> dibit demodulation hot path.
+ *
+ * The reference (syrex1013/TetraEar) has no FFI for this path: the boundary is the Python class
+ * tetraear.signal.processor.SignalProcessor and the hand-off TetraDecoder.decode(symbols)
+ * (SURVEY.md section 8b). Each entry point below states the reference interface it replaces
+ * (file:line, relative to the reference tree). tetraear_b200/processor.py binds them with ctypes;
+ * INTEGRATION.md shows the stub a TetraEar maintainer would add.
+ *
+ * Conventions: every function returns 0 on success or a negative TETRA_E_* code and never throws
+ * or aborts across the ABI; the message is available from tetra_last_error(). Buffers are
+ * caller-owned; the library keeps no reference to them after the call returns. Pointers marked
+ * "host or device" may be either (detected with cudaPointerGetAttributes). A context is
+ * single-caller (the reference uses one SignalProcessor per thread, ui/modern.py:1879); several
+ * contexts may coexist.
+ */
+#ifndef TETRA_B200_H
+#define TETRA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tetra_ctx tetra_ctx;
+
+#define TETRA_OK            0
+#define TETRA_E_INVALID    -1   /* bad argument */
+#define TETRA_E_CUDA       -2   /* CUDA runtime failure (message has the cudaError string) */
+#define TETRA_E_NOMEM      -3
+#define TETRA_E_UNSUPPORTED -4
+
+/* Replaces SignalProcessor.__init__ (signal/processor.py:21-33). device = CUDA ordinal. */
+int tetra_create(tetra_ctx** out, int device, double sample_rate);
+void tetra_destroy(tetra_ctx* ctx);
+/* Last error text of this context (ctx == NULL: last error of tetra_create on this thread). */
+const char* tetra_last_error(const tetra_ctx* ctx);
+/* SignalProcessor.sample_rate is mutated from outside at run time (ui/modern.py:1851-1852). */
+int tetra_set_sample_rate(tetra_ctx* ctx, double sample_rate);
+/* Work is enqueued on this CUDA stream (cudaStream_t as void*; NULL = the context's own stream). */
+int tetra_set_stream(tetra_ctx* ctx, void* cuda_stream);
+/* Block until everything enqueued by this context has finished. */
+int tetra_synchronize(tetra_ctx* ctx);
+
+/* Upper bound on dibits produced for an N-sample block at the context's sample rate
+ * (n_symbols - 1, signal/processor.py:213-215 and :135). */
+int64_t tetra_dibit_capacity(const tetra_ctx* ctx, int64_t n_samples);
+
+/*
+ * Replaces SignalProcessor.process (signal/processor.py:221-273) for a batch of C independent
+ * carriers, plus -- optionally -- the bit expansion and the training-sequence correlation of
+ * TetraDecoder.symbols_to_bits / find_sync (core/decoder.py:140-169, 231-259).
+ *
+ *   iq            [C][pitch] complex64 as interleaved float (re, im); host or device
+ *   n_samples     samples used per carrier (N); pitch >= N is the carrier stride in samples
+ *   freq_offset_hz host [C] or NULL (= all zero); the `freq_offset` argument of process()
+ *   dibits        [C][cap] uint8 values 0..3; host or device
+ *   n_dibits      [C] int32; host or device
+ *   symbols       [C][cap+1] complex64 (interleaved float) soft symbols = SignalProcessor.symbols
+ *                 (processor.py:268); host or device; may be NULL
+ *   best_phase    [C] int32 timing phase picked by extract_symbols (processor.py:189-210); may be NULL
+ *   ts_match      [C][2*cap][2] uint8: number of bits (0..22) agreeing with TS1 / TS2 for the 22-bit
+ *                 window starting at each bit position (decoder.py:237-240); may be NULL
+ * With async != 0 the call only enqueues (device buffers required); use tetra_synchronize().
+ */
+int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int64_t n_samples,
+                        int64_t pitch, const double* freq_offset_hz,
+                        uint8_t* dibits, int64_t cap, int32_t* n_dibits,
+                        float* symbols, int32_t* best_phase, uint8_t* ts_match, int32_t async);
+
+/* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
+int64_t tetra_launch_count(const tetra_ctx* ctx);
+/* Device-time of the most recent fused channelize+demod kernel launch, in ms (CUDA events on the
+ * context's stream); < 0 if none was timed. Enabled by tetra_enable_kernel_timing(ctx, 1). */
+int tetra_enable_kernel_timing(tetra_ctx* ctx, int on);
+double tetra_last_kernel_ms(tetra_ctx* ctx);
+
+/*
+ * Host replay of TetraDecoder.find_sync (core/decoder.py:226-295) over device-computed match
+ * counts for ONE carrier: same visiting order (jump +250 after a hit), same max_corr bookkeeping
+ * over visited positions only, same in-function adaptive retry.
+ *   match [n_windows][2] uint8, threshold as passed by the caller (0.90/0.85/0.80/adaptive)
+ *   positions out [max_positions]; returns the count (>= 0) or a negative error; *max_corr out.
+ */
+int tetra_find_sync(const uint8_t* match, int64_t n_windows, double threshold,
+                    int32_t* positions, int32_t max_positions, double* max_corr);
+/* decoder.py:845-856: the 0.90 / 0.85 / 0.80 / adaptive cascade of TetraDecoder.decode. */
+int tetra_sync_cascade(const uint8_t* match, int64_t n_windows,
+                       int32_t* positions, int32_t max_positions);
+
+/*
+ * Device versions of the reference's public helper methods, complex128 in / complex128 out as in
+ * the reference (host pointers, interleaved double re, im).
+ */
+/* filter_signal (processor.py:51-83): butter(4) zero-phase low-pass. Returns 1 if the filter was
+ * skipped the way the reference skips it (too short / design failure -> input copied). */
+int tetra_filter_signal(tetra_ctx* ctx, const double* in, int64_t n, double bandwidth,
+                        double sample_rate, double* out);
+/* frequency_shift (processor.py:85-100). */
+int tetra_frequency_shift(tetra_ctx* ctx, const double* in, int64_t n, double freq_offset,
+                          double sample_rate, double* out);
+/* extract_symbols (processor.py:168-219): out has room for n elements. */
+int tetra_extract_symbols(tetra_ctx* ctx, const double* in, int64_t n, double sample_rate,
+                          double* out, int64_t* n_out, int32_t* best_phase);
+/* demodulate_dqpsk (processor.py:102-166): out has room for n-1 dibits. */
+int tetra_demodulate_dqpsk(tetra_ctx* ctx, const double* in, int64_t n, uint8_t* out, int64_t* n_out);
+/* resample (processor.py:35-49, scipy.signal.resample FFT method) -- Fourier resampling on device. */
+int tetra_resample(tetra_ctx* ctx, const double* in, int64_t n, int64_t n_out, double* out);
+
+/*
+ * Waterfall rows (ui/modern.py:1921-1934 applied at every hop): Hann window, FFT, fftshift,
+ * 20*log10(|X|/nfft + 1e-20).  iq complex64 host or device, out [rows][nfft] float host or device.
+ * nfft must be a power of two in [64, 8192].
+ */
+int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n_samples, int32_t nfft, int32_t hop,
+                  float* out, int64_t* rows);
+
+/* Filter design used by the generic path (what scipy.signal.butter / cheby1 return to the
+ * reference at processor.py:78 and inside scipy.signal.decimate). Exposed for testing. */
+int tetra_design_butter4(double wn, double* b5, double* a5);
+int tetra_design_cheby1_sos8(double rp_db, double wn, double* sos24);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,217 @@
+"""CPU oracle for the TetraEar IQ -> dibit hot path (TEST INFRASTRUCTURE, not product).
+
+A numpy/scipy restatement of the reference's algorithm, written from the behaviour of
+
+  * tetraear/signal/processor.py:221-273   SignalProcessor.process
+  * tetraear/signal/processor.py:51-83     filter_signal   (butter(4) + filtfilt)
+  * tetraear/signal/processor.py:85-100    frequency_shift (NCO)
+  * tetraear/signal/processor.py:168-219   extract_symbols (block timing pick)
+  * tetraear/signal/processor.py:102-166   demodulate_dqpsk (differential slicer)
+  * tetraear/core/decoder.py:140-169       symbols_to_bits
+  * tetraear/core/decoder.py:171-295       find_sync
+  * tetraear/core/decoder.py:835-857       decode() threshold cascade
+  * tetraear/ui/modern.py:1921-1934        spectrum block
+
+The filter arithmetic of the reference lives in an un-vendored dependency, SciPy
+(requirements.txt:2 `scipy>=1.10.0`, this image: scipy 1.18.1): `scipy.signal.decimate`
+(cheby1(8, 0.05, 0.8/q) SOS, `sosfiltfilt`, `[::q]`), `scipy.signal.butter` + `filtfilt`.
+This module calls the same SciPy entry points (that *is* the reference's algorithm);
+oracle/tetra_oracle.c restates those recursions from scratch in C.
+
+Parity pinning: the reference's own tests hold no numeric vectors for this path
+(SURVEY.md section 8c), so this oracle is pinned against outputs of the reference itself,
+executed in the build container: tests/golden/*.npz, written by oracle/make_golden.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy import signal as _sig
+
+SYMBOL_RATE = 18000
+TARGET_RATE = 240000
+
+# decoder.py:196-199
+TS1 = np.array([1, 1, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 0], dtype=np.int64)
+TS2 = np.array([0, 1, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 1, 1, 0, 0], dtype=np.int64)
+SYNC_LEN = 22
+
+
+def decimation_factor(sample_rate: float) -> int:
+    """processor.py:245-250 -- q = int(fs/240k) when fs > 480 kHz, else 1 (no decimation)."""
+    if sample_rate > TARGET_RATE * 2:
+        q = int(sample_rate / TARGET_RATE)
+        if q > 1:
+            return q
+    return 1
+
+
+def nco(samples: np.ndarray, freq_offset: float, fs: float) -> np.ndarray:
+    """processor.py:97-100."""
+    t = np.arange(len(samples)) / fs
+    shift = np.exp(-1j * 2 * np.pi * freq_offset * t)   # named temporary: keeps numpy on the
+    return samples * shift                              # same (non-aliased) multiply loop
+
+
+def channel_filter(samples: np.ndarray, bandwidth: float, fs: float) -> np.ndarray:
+    """processor.py:66-83 -- butter(4, clamp((bw/2)/(fs/2))) zero-phase."""
+    if len(samples) == 0:
+        return samples
+    wn = min(0.99, max(0.01, (bandwidth / 2) / (fs / 2)))
+    try:
+        b, a = _sig.butter(4, wn, btype="low")
+        return _sig.filtfilt(b, a, samples)
+    except Exception:
+        return samples
+
+
+def timing_pick(samples: np.ndarray, fs: float):
+    """processor.py:179-219 -> (symbols, best_phase, powers[phases tried])."""
+    if len(samples) == 0:
+        return np.array([], dtype=complex), 0, np.zeros(0)
+    sps = int(fs / SYMBOL_RATE)
+    if sps <= 1:
+        return samples, 0, np.zeros(0)
+    step = max(1, sps // 8)
+    best, best_pow, pows = 0, -1.0, []
+    for ph in range(0, sps, step):
+        n = (len(samples) - ph) // sps
+        if n <= 0:
+            pows.append(np.nan)
+            continue
+        p = np.mean(np.abs(samples[ph + sps * np.arange(n)]) ** 2)
+        pows.append(p)
+        if p > best_pow:
+            best_pow, best = p, ph
+    n = (len(samples) - best) // sps
+    return samples[best + sps * np.arange(n)], best, np.array(pows)
+
+
+def slice_dqpsk(symbols: np.ndarray):
+    """processor.py:120-166, vectorised. Returns (dibits uint8, phase_diff float64)."""
+    if len(symbols) < 2:
+        return np.array([], dtype=np.uint8), np.zeros(0)
+    s = np.asarray(symbols)
+    m = np.max(np.abs(s))
+    if m > 0:
+        s = s / m
+    d = s[1:] * np.conj(s[:-1])
+    ph = np.arctan2(np.imag(d), np.real(d))
+    out = np.full(len(ph), 3, dtype=np.uint8)
+    out[ph < 5 * np.pi / 8] = 1
+    out[ph < 3 * np.pi / 8] = 0
+    out[ph < -3 * np.pi / 8] = 2
+    out[ph < -5 * np.pi / 8] = 3
+    return out, ph
+
+
+def process(samples: np.ndarray, freq_offset: float = 0.0, sample_rate: float = 2.4e6):
+    """processor.py:221-273. Returns dict(dibits, symbols, best_phase, powers, phase_diff)."""
+    samples = np.asarray(samples)
+    if len(samples) == 0:
+        return dict(dibits=np.array([], dtype=np.uint8), symbols=np.array([], dtype=complex),
+                    best_phase=0, powers=np.zeros(0), phase_diff=np.zeros(0))
+    rate = float(sample_rate)
+    q = decimation_factor(rate)
+    if q > 1:
+        try:
+            samples = _sig.decimate(samples, q)
+            rate = rate / q
+        except Exception:
+            pass
+    if freq_offset != 0:
+        samples = nco(samples, freq_offset, rate)
+    filt = channel_filter(samples, 25000, rate)
+    syms, best, pows = timing_pick(filt, rate)
+    dib, ph = slice_dqpsk(syms)
+    return dict(dibits=dib, symbols=syms, best_phase=best, powers=pows, phase_diff=ph)
+
+
+def symbols_to_bits(dibits: np.ndarray) -> np.ndarray:
+    """decoder.py:140-169 for the 0..3 case (the only one this path produces): MSB first."""
+    d = np.asarray(dibits).astype(np.int64) & 3
+    bits = np.empty(2 * len(d), dtype=np.int64)
+    bits[0::2] = d >> 1
+    bits[1::2] = d & 1
+    return bits
+
+
+def match_counts(bits: np.ndarray) -> np.ndarray:
+    """Number of agreeing bits vs TS1 and TS2 at every window start -> int[num_windows, 2]
+    (decoder.py:237-240 evaluated at every position)."""
+    bits = np.asarray(bits).astype(np.int64)
+    nw = len(bits) - SYNC_LEN + 1
+    if nw <= 0:
+        return np.zeros((0, 2), dtype=np.int64)
+    win = np.lib.stride_tricks.sliding_window_view(bits, SYNC_LEN)
+    return np.stack([(win == TS1).sum(1), (win == TS2).sum(1)], axis=1)
+
+
+def find_sync(bits: np.ndarray, threshold: float = 0.85):
+    """decoder.py:171-295 -> (positions list[int], max_corr float).
+
+    Same visiting order: on a hit at pos, jump to pos+250; max_corr and the adaptive
+    re-search only see visited positions; TS1 is tested before TS2 and a TS1 hit hides TS2's
+    correlation at that position from max_corr.
+    """
+    bits = np.asarray(bits)
+    if len(bits) < SYNC_LEN:
+        return [], 0.0
+    mc = match_counts(bits)
+    nw = len(mc)
+    pos_list, max_corr, visited = [], 0.0, []
+    i = 0
+    while i < nw:
+        found = False
+        best_here = 0.0
+        for k in range(2):
+            c = mc[i, k] / SYNC_LEN
+            best_here = max(best_here, c)
+            max_corr = max(max_corr, c)
+            if c >= threshold:
+                pos_list.append(i)
+                found = True
+                break
+        if best_here > 0:
+            visited.append((i, best_here))
+        i = i + 250 if found else i + 1
+    if not pos_list and max_corr > 0.75 and max_corr >= (threshold - 0.15):
+        adaptive = max(0.75, max_corr - 0.02)
+        if adaptive < threshold:
+            seen_until = -1  # positions < pos+250 of the last accepted hit are suppressed
+            blocked = np.zeros(nw, dtype=bool)
+            for p, c in visited:
+                if c >= adaptive and not blocked[p]:
+                    pos_list.append(p)
+                    blocked[max(0, p - 250): min(nw, p + 250)] = True
+    return pos_list, float(max_corr)
+
+
+def sync_cascade(bits: np.ndarray):
+    """decoder.py:845-856 -> positions handed to decode_frame."""
+    pos, mx = find_sync(bits, 0.90)
+    if not pos:
+        pos, mx = find_sync(bits, 0.85)
+        if not pos:
+            pos, mx = find_sync(bits, 0.80)
+            if not pos and mx >= 0.75:
+                pos, _ = find_sync(bits, max(0.75, mx - 0.02))
+    return pos
+
+
+def spectrum_db(samples: np.ndarray, n_fft: int = 2048) -> np.ndarray:
+    """modern.py:1924-1934 on the first n_fft samples."""
+    w = np.hanning(n_fft)
+    f = np.fft.fftshift(np.fft.fft(np.asarray(samples[:n_fft]) * w))
+    return 20 * np.log10(np.abs(f) / n_fft + 1e-20)
+
+
+def stft_db(samples: np.ndarray, n_fft: int = 4096, hop: int = 1024) -> np.ndarray:
+    """Config-5 generalisation: the modern.py:1924-1934 block applied at every hop."""
+    x = np.asarray(samples)
+    rows = (len(x) - n_fft) // hop + 1 if len(x) >= n_fft else 0
+    out = np.empty((rows, n_fft))
+    w = np.hanning(n_fft)
+    for r in range(rows):
+        f = np.fft.fftshift(np.fft.fft(x[r * hop: r * hop + n_fft] * w))
+        out[r] = 20 * np.log10(np.abs(f) / n_fft + 1e-20)
+    return out

@@ -1,0 +1,96 @@
+"""CPU: host logic and the C ABI surface (no device work)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+from scipy import signal
+
+from conftest import ROOT, load_golden
+from cases import CASES, SYNC_THRESHOLDS
+from oracle import ref_dsp
+from tetraear_b200 import _lib, sync
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "tetra_b200.h")).read()
+    declared = set(re.findall(r"\b(tetra_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("tetra_ctx")
+    lib = _lib.load()
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    lib = _lib.load()
+    ctx = _lib.c_ctx_p()
+    rc = lib.tetra_create(C.byref(ctx), 0, 2.4e6)
+    assert rc < 0 and b"no CUDA device" in lib.tetra_last_error(None)
+    from tetraear_b200.processor import SignalProcessor
+    with pytest.raises(_lib.TetraError):
+        SignalProcessor(2.4e6)
+
+
+@pytest.mark.parametrize("wn", [12500 / 120000, 0.0104166, 0.02083, 0.01, 0.5, 0.99])
+def test_butter_design_matches_scipy(wn):
+    lib = _lib.load()
+    b, a = np.zeros(5), np.zeros(5)
+    assert lib.tetra_design_butter4(wn, b.ctypes.data, a.ctypes.data) == 0
+    bs, as_ = signal.butter(4, wn)
+    assert np.allclose(b, bs, rtol=1e-12, atol=0) and np.allclose(a, as_, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("q", [2, 4, 7, 8, 10, 13])
+def test_cheby_design_matches_scipy(q):
+    lib = _lib.load()
+    s = np.zeros(24)
+    assert lib.tetra_design_cheby1_sos8(0.05, 0.8 / q, s.ctypes.data) == 0
+    ref = signal.cheby1(8, 0.05, 0.8 / q, output="sos")
+    assert np.allclose(s.reshape(4, 6), ref, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("name", [c[0] for c in CASES if c[2] >= 300])
+def test_find_sync_replay_matches_reference(name):
+    """tetra_find_sync (host replay) on oracle match counts == the reference's find_sync output."""
+    g = load_golden(name)
+    dib = g["dibits"]
+    bits = ref_dsp.symbols_to_bits(dib)
+    assert np.array_equal(sync.symbols_to_bits(dib), bits)
+    mc = ref_dsp.match_counts(bits).astype(np.uint8)
+    for th in SYNC_THRESHOLDS:
+        pos, mx = sync.find_sync(mc, len(dib), th, return_max_corr=True)
+        assert pos == list(g["sync_pos_%03d" % round(th * 100)])
+        assert mx == float(g["sync_max_%03d" % round(th * 100)])
+    assert sync.sync_cascade(mc, len(dib)) == ref_dsp.sync_cascade(bits)
+
+
+def test_find_sync_edge_cases():
+    assert sync.find_sync(np.zeros((0, 2), np.uint8), 0) == []
+    assert sync.find_sync(np.zeros((0, 2), np.uint8), 5, 0.9, True) == ([], 0.0)
+    bits = np.zeros(600, dtype=np.int64)
+    bits[20:42] = ref_dsp.TS1
+    mc = ref_dsp.match_counts(bits).astype(np.uint8)
+    assert sync.find_sync(mc, 300, 0.85, True) == ([20], 1.0)
+    assert sync.burst_slices([20, 300], 300) == [(42, 84, 0)]
+
+
+def test_fir_tables_reproduce_reference_interior():
+    """The generated FIR cascade (tools/design_filters.py) equals decimate+filtfilt away from the edges."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import design_filters as df
+    from tetraear_b200 import synth
+    taps = df.design()
+    hdr = open(os.path.join(ROOT, "tetraear_b200", "csrc", "taps_generated.h")).read()
+    first = float(re.search(r"TB_PROTO_TAPS\[\d+\] = \{\s*([-0-9.e+]+)f", hdr).group(1))
+    assert abs(first - taps["proto"][0]) < 1e-9 * abs(first) + 1e-12, "taps_generated.h is stale"
+    x = synth.carrier_iq(1 << 17, 21, snr_db=20.0)
+    ref = ref_dsp.channel_filter(signal.decimate(x.astype(np.complex128), 10), 25000, 240000.0)
+    y = df.simulate(x, taps, np.float32)
+    err = np.abs(y - ref) / np.abs(ref).max()
+    assert err[160:-160].max() < 2e-6

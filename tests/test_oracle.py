@@ -1,0 +1,51 @@
+"""CPU: the oracle restatement against the golden vectors produced by the reference itself."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_input
+from cases import CASES, SYNC_THRESHOLDS
+from oracle import ref_dsp
+
+
+@pytest.mark.parametrize("name,gen,n,fs,fo", CASES, ids=[c[0] for c in CASES])
+def test_oracle_matches_reference_golden(name, gen, n, fs, fo):
+    g = load_golden(name)
+    x = golden_input(g, **gen)
+    r = ref_dsp.process(x.astype(np.complex128), fo, fs)
+    assert np.array_equal(r["dibits"], g["dibits"])
+    assert r["symbols"].shape == g["symbols"].shape
+    if len(g["symbols"]):
+        assert np.array_equal(r["symbols"], g["symbols"])      # same SciPy calls: bit-identical
+        assert r["best_phase"] == int(g["best_phase"])
+    if len(g["dibits"]):
+        bits = ref_dsp.symbols_to_bits(r["dibits"])
+        assert hashlib.sha256(bits.astype(np.uint8)).hexdigest() == str(g["bits_sha256"])
+        for th in SYNC_THRESHOLDS:
+            pos, mx = ref_dsp.find_sync(bits, th)
+            assert pos == list(g["sync_pos_%03d" % round(th * 100)])
+            assert mx == float(g["sync_max_%03d" % round(th * 100)])
+
+
+def test_find_sync_planted_pattern():
+    # the reference's own unit test plants TS1 at bit 20 (tests/unit/test_tetra_decoder.py:56-66)
+    bits = np.zeros(600, dtype=np.int64)
+    bits[20:42] = ref_dsp.TS1
+    pos, mx = ref_dsp.find_sync(bits, 0.85)
+    assert pos == [20] and mx == 1.0
+    assert ref_dsp.find_sync(np.zeros(10, dtype=np.int64)) == ([], 0.0)
+
+
+def test_slicer_regions_q7():
+    # regions are centred on 0, +pi/2, -pi/2, pi
+    ph = np.array([0.0, np.pi / 2, -np.pi / 2, np.pi, -np.pi + 1e-9, 3 * np.pi / 8 - 1e-9, 3 * np.pi / 8 + 1e-9])
+    s = np.concatenate([[1.0 + 0j], np.exp(1j * np.cumsum(ph))])
+    d, _ = ref_dsp.slice_dqpsk(s)
+    assert list(d) == [0, 1, 2, 3, 3, 0, 1]
+
+
+def test_stft_rows_shape():
+    x = (np.random.default_rng(0).standard_normal(10000) + 0j).astype(np.complex64)
+    assert ref_dsp.stft_db(x, 4096, 1024).shape == (6, 4096)
+    assert ref_dsp.stft_db(x[:100], 4096, 1024).shape == (0, 4096)

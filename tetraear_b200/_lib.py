@@ -1,0 +1,77 @@
+"""ctypes binding of libtetra_b200.so (include/tetra_b200.h). No torch types cross this boundary."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import build as _build
+
+_LIB = None
+
+c_ctx_p = C.c_void_p
+
+_SIGS = {
+    "tetra_create": (C.c_int, [C.POINTER(c_ctx_p), C.c_int, C.c_double]),
+    "tetra_destroy": (None, [c_ctx_p]),
+    "tetra_last_error": (C.c_char_p, [c_ctx_p]),
+    "tetra_set_sample_rate": (C.c_int, [c_ctx_p, C.c_double]),
+    "tetra_set_stream": (C.c_int, [c_ctx_p, C.c_void_p]),
+    "tetra_synchronize": (C.c_int, [c_ctx_p]),
+    "tetra_dibit_capacity": (C.c_int64, [c_ctx_p, C.c_int64]),
+    "tetra_process_batch": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int32]),
+    "tetra_launch_count": (C.c_int64, [c_ctx_p]),
+    "tetra_enable_kernel_timing": (C.c_int, [c_ctx_p, C.c_int]),
+    "tetra_last_kernel_ms": (C.c_double, [c_ctx_p]),
+    "tetra_find_sync": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
+    "tetra_sync_cascade": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
+    "tetra_filter_signal": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
+    "tetra_frequency_shift": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
+    "tetra_extract_symbols": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
+                                        C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "tetra_demodulate_dqpsk": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
+    "tetra_resample": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "tetra_stft_db": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                C.POINTER(C.c_int64)]),
+    "tetra_design_butter4": (C.c_int, [C.c_double, C.c_void_p, C.c_void_p]),
+    "tetra_design_cheby1_sos8": (C.c_int, [C.c_double, C.c_double, C.c_void_p]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if the sources are newer) and type the shared library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        try:
+            path = _build.build()
+        except Exception:
+            if not os.path.exists(path):
+                raise
+    lib = C.CDLL(path)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)      # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+class TetraError(RuntimeError):
+    pass
+
+
+def check(lib, ctx, rc: int, what: str) -> int:
+    if rc < 0:
+        msg = lib.tetra_last_error(ctx)
+        raise TetraError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+    return rc

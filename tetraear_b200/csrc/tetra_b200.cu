@@ -1,0 +1,623 @@
+// libtetra_b200.so -- host side of the C ABI declared in include/tetra_b200.h.
+//
+// Mirrors the control flow of the reference's SignalProcessor.process
+// (tetraear/signal/processor.py:221-273) for a batch of carriers, choosing between
+//   * the fused FIR-cascade kernel (k1_channelize_demod) + exact edge windows, when the block is
+//     long, fs = 2.4 MS/s and freq_offset = 0, and
+//   * the exact-recursion kernel over the whole block otherwise,
+// then the timing pick / slicer kernel and the training-sequence correlator.
+// There is no CPU fallback: without a CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/tetra_b200.h"
+#include "filter_design.h"
+#include "tetra_kernels.cuh"
+#include "tetra_exact.cuh"
+#include "tetra_stft.cuh"
+
+using namespace tetra;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct tetra_ctx {
+    int device = 0;
+    double sample_rate = 2.4e6;
+    cudaStream_t own_stream = nullptr, stream = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    bool timing = false, timed = false;
+    int64_t launches = 0;
+    std::string err;
+    bool tables_uploaded = false;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c;
+    size_t max_scratch_bytes = (size_t)6 << 30;
+};
+
+namespace {
+
+int fail(tetra_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(ctx, e_ == cudaErrorMemoryAllocation ? TETRA_E_NOMEM : TETRA_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); } while (0)
+
+bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+// processor.py:245-250
+int decim_factor(double fs) {
+    if (fs > 240000.0 * 2) { int q = (int)(fs / 240000.0); if (q > 1) return q; }
+    return 1;
+}
+
+struct Plan {
+    int q; bool has_s1, has_s2; int64_t L; double rate; int sps, step; double wn;
+};
+Plan make_plan(double fs, int64_t n) {
+    Plan p;
+    p.q = decim_factor(fs);
+    p.has_s1 = p.q > 1 && n > EX_PAD1;             // sosfiltfilt raises on n <= padlen -> decimation skipped
+    if (!p.has_s1) p.q = 1;
+    p.rate = p.has_s1 ? fs / p.q : fs;
+    p.L = p.has_s1 ? (n + p.q - 1) / p.q : n;
+    double wn = (25000.0 / 2) / (p.rate / 2);      // processor.py:74-75
+    p.wn = std::min(0.99, std::max(0.01, wn));
+    p.has_s2 = p.L > EX_PAD2;                      // filtfilt raises on len <= padlen -> unfiltered
+    p.sps = (int)(p.rate / 18000.0);               // processor.py:183
+    p.step = std::max(1, p.sps / 8);               // processor.py:194
+    return p;
+}
+
+int upload_tables(tetra_ctx* ctx) {
+    if (ctx->tables_uploaded) return 0;
+    float fir[132];
+    memset(fir, 0, sizeof fir);
+    memcpy(fir, TB_FIR120_TAPS, sizeof(float) * (2 * TB_FIR_H + 1));
+    CK(cudaMemcpyToSymbol(c_proto, TB_PROTO_TAPS, sizeof(float) * (2 * TB_PROTO_H + 1)));
+    CK(cudaMemcpyToSymbol(c_hb, TB_HB_TAPS, sizeof(float) * (2 * TB_HB_H + 1)));
+    CK(cudaMemcpyToSymbol(c_fir, fir, sizeof fir));
+    CK(cudaMemcpyToSymbol(c_interp, TB_INTERP_TAPS, sizeof(float) * TB_INT_K));
+    CK(cudaFuncSetAttribute(k1_channelize_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    ctx->tables_uploaded = true;
+    return 0;
+}
+
+void fill_coef(ExactCoef& cf, int q, double wn) {
+    memset(&cf, 0, sizeof cf);
+    if (q > 1) {
+        double sos[24], zi[8];
+        design_cheby1_sos8(0.05, 0.8 / q, sos);
+        sosfilt_zi(sos, 4, zi);
+        memcpy(cf.sos, sos, sizeof sos);
+        memcpy(cf.zi1, zi, sizeof zi);
+    }
+    design_butter4(wn, cf.b, cf.a);
+    lfilter_zi(cf.b, cf.a, 5, cf.zi2);
+}
+
+// window sizes of an exact job (must match k_exact_chain)
+void exact_extents(int mode, int64_t n, int64_t L, int q, int E, bool has_s1, int64_t* w1, int64_t* wz) {
+    int64_t m_lo = 0, m_hi = L;
+    if (mode == EX_LEFT) m_hi = std::min<int64_t>(L, E + EX_T2);
+    else if (mode == EX_RIGHT) m_lo = std::max<int64_t>(0, L - E - 2 * EX_T2);
+    *wz = m_hi - m_lo;
+    if (!has_s1) { *w1 = 1; return; }
+    int64_t tot = n + 2 * EX_PAD1, e_lo = 0, e_hi = tot;
+    if (mode == EX_LEFT) e_hi = std::min<int64_t>(tot, EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
+    else if (mode == EX_RIGHT) e_lo = std::max<int64_t>(0, EX_PAD1 + (int64_t)q * m_lo - EX_T1);
+    *w1 = e_hi - e_lo;
+}
+
+int launch_exact(tetra_ctx* ctx, cudaStream_t st, ExactArgs a, const std::vector<int2>& jobs, int mode_hint) {
+    if (jobs.empty()) return 0;
+    // extents: all jobs of one launch share the worst-case window
+    int64_t w1 = 1, wz = 1;
+    for (int m = 0; m < 3; ++m) {
+        bool used = false;
+        for (auto& j : jobs) if (j.y == m) { used = true; break; }
+        if (!used) continue;
+        int64_t a1, az; exact_extents(m, a.n, a.L, a.q, a.edge, a.has_s1, &a1, &az);
+        w1 = std::max(w1, a1); wz = std::max(wz, az);
+    }
+    (void)mode_hint;
+    const size_t per_job = (size_t)(w1 + wz + wz + 2 * EX_PAD2) * sizeof(double2);
+    size_t chunk = std::max<size_t>(1, ctx->max_scratch_bytes / per_job);
+    chunk = std::min(chunk, jobs.size());
+    CK(ctx->scr1.ensure((size_t)w1 * chunk * sizeof(double2)));
+    CK(ctx->scrz.ensure((size_t)wz * chunk * sizeof(double2)));
+    CK(ctx->scr2.ensure((size_t)(wz + 2 * EX_PAD2) * chunk * sizeof(double2)));
+    CK(ctx->jobs.ensure(jobs.size() * sizeof(int2)));
+    CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    a.scr1 = (double2*)ctx->scr1.p; a.scrz = (double2*)ctx->scrz.p; a.scr2 = (double2*)ctx->scr2.p;
+    for (size_t off = 0; off < jobs.size(); off += chunk) {
+        const int nj = (int)std::min(chunk, jobs.size() - off);
+        a.jobs = (const int2*)ctx->jobs.p + off;
+        a.n_jobs = nj;
+        k_exact_chain<<<(nj + 63) / 64, 64, 0, st>>>(a);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // the job list must outlive the kernels: it lives in ctx->jobs until the next call (same stream order)
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tetra_create(tetra_ctx** out, int device, double sample_rate) {
+    if (!out) return fail(nullptr, TETRA_E_INVALID, "tetra_create: out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, TETRA_E_CUDA, "tetra_create: no CUDA device (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    }
+    if (device < 0 || device >= n_dev) return fail(nullptr, TETRA_E_INVALID, "tetra_create: device %d out of range", device);
+    if (!(sample_rate > 0)) return fail(nullptr, TETRA_E_INVALID, "tetra_create: sample_rate must be > 0");
+    tetra_ctx* ctx = new tetra_ctx();
+    ctx->device = device;
+    ctx->sample_rate = sample_rate;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_t1)) != cudaSuccess) {
+        fail(nullptr, TETRA_E_CUDA, "tetra_create: %s", cudaGetErrorString(e));
+        delete ctx;
+        return TETRA_E_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return TETRA_OK;
+}
+
+void tetra_destroy(tetra_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->side);
+    DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c};
+    for (DevBuf* b : bufs) b->release();
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->side);
+    delete ctx;
+}
+
+const char* tetra_last_error(const tetra_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tetra_set_sample_rate(tetra_ctx* ctx, double sample_rate) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (!(sample_rate > 0)) return fail(ctx, TETRA_E_INVALID, "sample_rate must be > 0");
+    ctx->sample_rate = sample_rate;
+    return TETRA_OK;
+}
+int tetra_set_stream(tetra_ctx* ctx, void* s) {
+    if (!ctx) return TETRA_E_INVALID;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return TETRA_OK;
+}
+int tetra_synchronize(tetra_ctx* ctx) {
+    if (!ctx) return TETRA_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TETRA_OK;
+}
+int64_t tetra_dibit_capacity(const tetra_ctx* ctx, int64_t n) {
+    if (!ctx || n <= 0) return 0;
+    Plan p = make_plan(ctx->sample_rate, n);
+    int64_t ns = p.sps > 1 ? p.L / p.sps : p.L;
+    return ns > 1 ? ns - 1 : 0;
+}
+int64_t tetra_launch_count(const tetra_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int tetra_enable_kernel_timing(tetra_ctx* ctx, int on) { if (!ctx) return TETRA_E_INVALID; ctx->timing = on != 0; return 0; }
+double tetra_last_kernel_ms(tetra_ctx* ctx) {
+    if (!ctx || !ctx->timed) return -1.0;
+    float ms = -1.f;
+    if (cudaEventSynchronize(ctx->ev_t1) != cudaSuccess) return -1.0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) != cudaSuccess) return -1.0;
+    return (double)ms;
+}
+
+int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                        uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                        uint8_t* ts_match, int32_t async) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || N < 0 || (C > 0 && N > 0 && (!iq || pitch < N)) || !n_dibits || (cap > 0 && !dibits) || cap < 0)
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: bad arguments");
+    if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: at most 65535 carriers per call");
+    if (N > ((int64_t)1 << 30)) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: block too long");
+    CK(cudaSetDevice(ctx->device));
+    if (C == 0) return TETRA_OK;
+    cudaStream_t st = ctx->stream;
+    const bool d_in = is_device_ptr(iq), d_dib = is_device_ptr(dibits), d_nd = is_device_ptr(n_dibits);
+    const bool d_sym = is_device_ptr(symbols), d_ph = is_device_ptr(best_phase), d_match = is_device_ptr(ts_match);
+    if (async && !(d_in && (d_dib || !dibits) && d_nd && (d_sym || !symbols) && (d_ph || !best_phase) && (d_match || !ts_match)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: async needs device buffers");
+
+    const Plan pl = make_plan(ctx->sample_rate, N);
+    const int64_t need_cap = tetra_dibit_capacity(ctx, N);
+    if (cap < need_cap) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: cap %lld < required %lld", (long long)cap, (long long)need_cap);
+    if (N == 0 || pl.L <= 0) {      // processor.py:239-241: empty in -> empty out
+        if (d_nd) CK(cudaMemsetAsync(n_dibits, 0, sizeof(int32_t) * C, st)); else memset(n_dibits, 0, sizeof(int32_t) * C);
+        if (best_phase) { if (d_ph) CK(cudaMemsetAsync(best_phase, 0, sizeof(int32_t) * C, st)); else memset(best_phase, 0, sizeof(int32_t) * C); }
+        return TETRA_OK;
+    }
+    if (pl.sps > 1 && (pl.sps + pl.step - 1) / pl.step > FIN_MAXPH)
+        return fail(ctx, TETRA_E_UNSUPPORTED, "timing search with more than %d phases", FIN_MAXPH);
+    int rc = upload_tables(ctx);
+    if (rc) return rc;
+
+    // ---- input on device ----
+    const float2* d_x;
+    int64_t x_pitch = pitch;
+    if (d_in) d_x = (const float2*)iq;
+    else {
+        CK(ctx->in.ensure((size_t)C * N * sizeof(float2)));
+        if (pitch == N) CK(cudaMemcpyAsync(ctx->in.p, iq, (size_t)C * N * sizeof(float2), cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpy2DAsync(ctx->in.p, N * sizeof(float2), iq, pitch * sizeof(float2), N * sizeof(float2), C, cudaMemcpyHostToDevice, st));
+        d_x = (const float2*)ctx->in.p;
+        x_pitch = N;
+    }
+
+    // ---- which carriers take the fused path ----
+    const bool fast_ok = ctx->sample_rate == 2.4e6 && pl.q == 10 && pl.has_s1 && pl.has_s2 && N >= 16384 && pl.sps == K1_NPH;
+    std::vector<int2> edge_jobs, full_jobs;
+    bool any_fo = false;
+    for (int c = 0; c < C; ++c) {
+        const bool zero_fo = !fo_hz || fo_hz[c] == 0.0;
+        if (!zero_fo) any_fo = true;
+        if (fast_ok && zero_fo) { edge_jobs.push_back(make_int2(c, EX_LEFT)); edge_jobs.push_back(make_int2(c, EX_RIGHT)); }
+        else full_jobs.push_back(make_int2(c, EX_FULL));
+    }
+    const bool use_fast = !edge_jobs.empty();
+    if (use_fast && !full_jobs.empty())
+        return fail(ctx, TETRA_E_UNSUPPORTED, "mixing zero and non-zero freq_offset in one batch: split the call");
+    const double* d_fo = nullptr;
+    if (any_fo) {
+        CK(ctx->fo.ensure(sizeof(double) * C));
+        CK(cudaMemcpyAsync(ctx->fo.p, fo_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+        d_fo = (const double*)ctx->fo.p;
+    }
+
+    // ---- buffers ----
+    const int64_t y_pitch = (pl.L + 63) & ~(int64_t)63;
+    CK(ctx->y.ensure((size_t)C * y_pitch * sizeof(float2)));
+    CK(ctx->phase.ensure(sizeof(int32_t) * C));
+    uint8_t* k_dib = d_dib ? dibits : nullptr;
+    int32_t* k_nd = d_nd ? n_dibits : nullptr;
+    float2* k_sym = d_sym ? (float2*)symbols : nullptr;
+    int32_t* k_ph = d_ph ? best_phase : nullptr;
+    uint8_t* k_match = d_match ? ts_match : nullptr;
+    if (!d_dib) { CK(ctx->dib.ensure((size_t)C * cap + 16)); k_dib = (uint8_t*)ctx->dib.p; }
+    if (!d_nd) { CK(ctx->ndib.ensure(sizeof(int32_t) * C)); k_nd = (int32_t*)ctx->ndib.p; }
+    if (symbols && !d_sym) { CK(ctx->sym.ensure((size_t)C * (cap + 1) * sizeof(float2))); k_sym = (float2*)ctx->sym.p; }
+    if (best_phase && !d_ph) k_ph = (int32_t*)ctx->phase.p;
+    if (ts_match && !d_match) { CK(ctx->match.ensure((size_t)C * cap * 4 + 16)); k_match = (uint8_t*)ctx->match.p; }
+
+    ExactArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.x32 = d_x; ea.pitch = x_pitch; ea.n = N; ea.q = pl.q; ea.L = (int32_t)pl.L;
+    ea.has_s1 = pl.has_s1; ea.has_s2 = pl.has_s2;
+    fill_coef(ea.cf, pl.has_s1 ? pl.q : 1, pl.wn);
+    ea.fo = d_fo; ea.fs_dec = pl.rate;
+    ea.y32 = (float2*)ctx->y.p; ea.y_pitch = y_pitch; ea.edge = K1_EDGE;
+
+    FinArgs fa;
+    memset(&fa, 0, sizeof fa);
+    fa.y = (const float2*)ctx->y.p; fa.y_pitch = y_pitch; fa.L = (int32_t)pl.L; fa.sps = pl.sps; fa.step = pl.step;
+    fa.dibits = k_dib; fa.cap = cap; fa.n_dibits = k_nd; fa.symbols = k_sym; fa.best_phase = k_ph;
+    fa.phase_scratch = (int32_t*)ctx->phase.p;
+
+    if (use_fast) {
+        // segments: enough CTAs to fill the machine when there are few carriers
+        int n_seg = 1;
+        const int tiles = (int)((pl.L + K1_W - 1) / K1_W);
+        if (C < 296) n_seg = std::min(tiles, std::max(1, (296 + C - 1) / C));
+        int seg_len = ((tiles + n_seg - 1) / n_seg) * K1_W;
+        n_seg = (int)((pl.L + seg_len - 1) / seg_len);
+        CK(ctx->partial.ensure((size_t)C * n_seg * 16 * sizeof(double)));
+        K1Args ka;
+        ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg;
+        ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.partial = (double*)ctx->partial.p;
+        ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
+        // edge windows run beside the bulk kernel on the side stream
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+        rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        if (rc) return rc;
+        CK(cudaEventRecord(ctx->ev_join, ctx->side));
+        if (ctx->timing) CK(cudaEventRecord(ctx->ev_t0, st));
+        k1_channelize_demod<<<dim3(n_seg, C), K1_THREADS, sizeof(K1Smem), st>>>(ka);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (ctx->timing) { CK(cudaEventRecord(ctx->ev_t1, st)); ctx->timed = true; }
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
+        fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
+    } else {
+        rc = launch_exact(ctx, st, ea, full_jobs, 0);
+        if (rc) return rc;
+        fa.partial = nullptr; fa.n_seg = 0; fa.bulk_lo = 0; fa.bulk_hi = 0;
+    }
+    k_finalize<<<C, FIN_THREADS, 0, st>>>(fa);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (ts_match && cap > 0) {
+        SyncArgs sa; sa.dibits = k_dib; sa.cap = cap; sa.n_dibits = k_nd; sa.match = k_match;
+        const int gx = (int)std::min<int64_t>(64, (2 * cap + 255) / 256);
+        k_sync_match<<<dim3(std::max(gx, 1), C), 256, 0, st>>>(sa);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    // ---- results to host buffers ----
+    if (dibits && !d_dib) CK(cudaMemcpyAsync(dibits, k_dib, (size_t)C * cap, cudaMemcpyDeviceToHost, st));
+    if (!d_nd) CK(cudaMemcpyAsync(n_dibits, k_nd, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+    if (symbols && !d_sym) CK(cudaMemcpyAsync(symbols, k_sym, (size_t)C * (cap + 1) * sizeof(float2), cudaMemcpyDeviceToHost, st));
+    if (best_phase && !d_ph) CK(cudaMemcpyAsync(best_phase, k_ph, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+    if (ts_match && !d_match) CK(cudaMemcpyAsync(ts_match, k_match, (size_t)C * cap * 4, cudaMemcpyDeviceToHost, st));
+    if (!async) CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// find_sync replay (host, integer-exact)
+// ------------------------------------------------------------------------------------------------
+int tetra_find_sync(const uint8_t* match, int64_t nw, double threshold, int32_t* positions, int32_t max_pos, double* max_corr_out) {
+    if (nw < 0 || (nw > 0 && !match) || (max_pos > 0 && !positions)) return TETRA_E_INVALID;
+    int count = 0;
+    double max_corr = 0.0;
+    std::vector<std::pair<int64_t, double>> visited;
+    visited.reserve((size_t)nw);
+    int64_t i = 0;
+    while (i < nw) {
+        bool found = false;
+        double best_here = 0.0;
+        for (int k = 0; k < 2; ++k) {
+            const double corr = (double)match[2 * i + k] / 22.0;
+            best_here = std::max(best_here, corr);
+            max_corr = std::max(max_corr, corr);
+            if (corr >= threshold) {
+                if (count < max_pos) positions[count] = (int32_t)i;
+                ++count; found = true;
+                break;
+            }
+        }
+        if (best_here > 0) visited.emplace_back(i, best_here);
+        i = found ? i + 250 : i + 1;
+    }
+    if (count == 0 && max_corr > 0.75 && max_corr >= (threshold - 0.15)) {
+        const double adaptive = std::max(0.75, max_corr - 0.02);
+        if (adaptive < threshold) {
+            std::vector<char> blocked((size_t)nw, 0);
+            for (auto& pc : visited) {
+                if (pc.second >= adaptive && !blocked[(size_t)pc.first]) {
+                    if (count < max_pos) positions[count] = (int32_t)pc.first;
+                    ++count;
+                    const int64_t lo = std::max<int64_t>(0, pc.first - 250), hi = std::min<int64_t>(nw, pc.first + 250);
+                    for (int64_t t = lo; t < hi; ++t) blocked[(size_t)t] = 1;
+                }
+            }
+        }
+    }
+    if (max_corr_out) *max_corr_out = max_corr;
+    return count;
+}
+
+int tetra_sync_cascade(const uint8_t* match, int64_t nw, int32_t* positions, int32_t max_pos) {
+    double mx = 0.0;
+    int n = tetra_find_sync(match, nw, 0.90, positions, max_pos, &mx);
+    if (n != 0) return n;
+    n = tetra_find_sync(match, nw, 0.85, positions, max_pos, &mx);
+    if (n != 0) return n;
+    n = tetra_find_sync(match, nw, 0.80, positions, max_pos, &mx);
+    if (n != 0) return n;
+    if (mx >= 0.75) n = tetra_find_sync(match, nw, std::max(0.75, mx - 0.02), positions, max_pos, &mx);
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// helper entry points (complex128 host in/out)
+// ------------------------------------------------------------------------------------------------
+static int run_exact_c128(tetra_ctx* ctx, const double* in, int64_t n, bool filter, double wn, double fo, double fs, double* out) {
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tmp_a.ensure((size_t)n * sizeof(double2)));
+    CK(ctx->tmp_b.ensure((size_t)n * sizeof(double2)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, in, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    ExactArgs ea;
+    memset(&ea, 0, sizeof ea);
+    ea.x64 = (const double2*)ctx->tmp_a.p; ea.pitch = n; ea.n = n; ea.q = 1; ea.L = (int32_t)n;
+    ea.has_s1 = 0; ea.has_s2 = filter ? 1 : 0;
+    fill_coef(ea.cf, 1, filter ? wn : 0.5);
+    if (fo != 0.0) {
+        CK(ctx->fo.ensure(sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->fo.p, &fo, sizeof(double), cudaMemcpyHostToDevice, st));
+        ea.fo = (const double*)ctx->fo.p;
+    }
+    ea.fs_dec = fs;
+    ea.y64 = (double2*)ctx->tmp_b.p; ea.y_pitch = n; ea.edge = 0;
+    std::vector<int2> jobs(1, make_int2(0, EX_FULL));
+    int rc = launch_exact(ctx, st, ea, jobs, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->tmp_b.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_filter_signal(tetra_ctx* ctx, const double* in, int64_t n, double bandwidth, double sample_rate, double* out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n < 0 || (n > 0 && (!in || !out)) || !(sample_rate > 0)) return fail(ctx, TETRA_E_INVALID, "tetra_filter_signal: bad arguments");
+    if (n == 0) return TETRA_OK;
+    if (n > ((int64_t)1 << 30)) return fail(ctx, TETRA_E_INVALID, "too long");
+    double wn = (bandwidth / 2) / (sample_rate / 2);
+    wn = std::min(0.99, std::max(0.01, wn));
+    if (!(wn == wn) || n <= EX_PAD2) {            // reference: exception inside filtfilt -> unfiltered (processor.py:81-83)
+        memcpy(out, in, (size_t)n * 2 * sizeof(double));
+        return 1;
+    }
+    return run_exact_c128(ctx, in, n, true, wn, 0.0, sample_rate, out);
+}
+
+int tetra_frequency_shift(tetra_ctx* ctx, const double* in, int64_t n, double fo, double fs, double* out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n < 0 || (n > 0 && (!in || !out)) || !(fs > 0)) return fail(ctx, TETRA_E_INVALID, "tetra_frequency_shift: bad arguments");
+    if (n == 0) return TETRA_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tmp_a.ensure((size_t)n * sizeof(double2)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, in, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    k_nco_c128<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, st>>>((double2*)ctx->tmp_a.p, n, fo, fs);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->tmp_a.p, (size_t)n * sizeof(double2), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_extract_symbols(tetra_ctx* ctx, const double* in, int64_t n, double fs, double* out, int64_t* n_out, int32_t* best_phase) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n < 0 || (n > 0 && (!in || !out)) || !n_out || !(fs > 0)) return fail(ctx, TETRA_E_INVALID, "tetra_extract_symbols: bad arguments");
+    *n_out = 0;
+    if (best_phase) *best_phase = 0;
+    if (n == 0) return TETRA_OK;
+    const int sps = (int)(fs / 18000.0);
+    if (sps <= 1) { memcpy(out, in, (size_t)n * 2 * sizeof(double)); *n_out = n; return TETRA_OK; }
+    const int step = std::max(1, sps / 8);
+    if ((sps + step - 1) / step > FIN_MAXPH) return fail(ctx, TETRA_E_UNSUPPORTED, "too many timing phases");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tmp_a.ensure((size_t)n * sizeof(double2)));
+    CK(ctx->tmp_b.ensure((size_t)(n / sps + 2) * sizeof(double2)));
+    CK(ctx->tmp_c.ensure(2 * sizeof(int64_t)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, in, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    k_extract_c128<<<1, FIN_THREADS, 0, st>>>((const double2*)ctx->tmp_a.p, n, sps, step, (double2*)ctx->tmp_b.p, (int64_t*)ctx->tmp_c.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    int64_t res[2];
+    CK(cudaMemcpyAsync(res, ctx->tmp_c.p, sizeof res, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = res[0];
+    if (best_phase) *best_phase = (int32_t)res[1];
+    if (res[0] > 0) CK(cudaMemcpy(out, ctx->tmp_b.p, (size_t)res[0] * sizeof(double2), cudaMemcpyDeviceToHost));
+    return TETRA_OK;
+}
+
+int tetra_demodulate_dqpsk(tetra_ctx* ctx, const double* in, int64_t n, uint8_t* out, int64_t* n_out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n < 0 || (n > 0 && !in) || !n_out || (n > 1 && !out)) return fail(ctx, TETRA_E_INVALID, "tetra_demodulate_dqpsk: bad arguments");
+    *n_out = 0;
+    if (n < 2) return TETRA_OK;                    // processor.py:120-121
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->tmp_a.ensure((size_t)n * sizeof(double2)));
+    CK(ctx->tmp_b.ensure((size_t)n));
+    CK(ctx->tmp_c.ensure(sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, in, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(ctx->tmp_c.p, 0, sizeof(double), st));
+    const int g = (int)std::min<int64_t>((n + 255) / 256, 2048);
+    k_maxabs_c128<<<g, 256, 0, st>>>((const double2*)ctx->tmp_a.p, n, (unsigned long long*)ctx->tmp_c.p);
+    k_slice_c128<<<g, 256, 0, st>>>((const double2*)ctx->tmp_a.p, n, (const double*)ctx->tmp_c.p, (uint8_t*)ctx->tmp_b.p);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->tmp_b.p, (size_t)(n - 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = n - 1;
+    return TETRA_OK;
+}
+
+int tetra_resample(tetra_ctx* ctx, const double* in, int64_t n, int64_t n_out, double* out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n <= 0 || n_out <= 0 || !in || !out) return fail(ctx, TETRA_E_INVALID, "tetra_resample: bad arguments");
+    if (n > (1 << 22) || n_out > (1 << 22)) return fail(ctx, TETRA_E_UNSUPPORTED, "tetra_resample: at most 2^22 samples");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // Fourier resampling (scipy.signal.resample, complex input): X = DFT(x); keep the lowest
+    // min(n, n_out) bins (split around DC, Nyquist bin handled as SciPy does); y = IDFT * (n_out / n).
+    CK(ctx->tmp_a.ensure((size_t)n * sizeof(double2)));
+    CK(ctx->tmp_b.ensure((size_t)std::max(n, n_out) * sizeof(double2)));
+    CK(ctx->tmp_c.ensure((size_t)n_out * sizeof(double2)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, in, (size_t)n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    int rc = resample_c128(ctx->launches, st, (const double2*)ctx->tmp_a.p, n, (double2*)ctx->tmp_b.p, n_out, (double2*)ctx->tmp_c.p);
+    if (rc) return fail(ctx, TETRA_E_CUDA, "tetra_resample: kernel launch failed");
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->tmp_c.p, (size_t)n_out * sizeof(double2), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n, int32_t nfft, int32_t hop, float* out, int64_t* rows_out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (!rows_out || n < 0 || hop <= 0 || nfft < 64 || nfft > 8192 || (nfft & (nfft - 1)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_stft_db: nfft must be a power of two in [64, 8192], hop > 0");
+    const int64_t rows = n >= nfft ? (n - nfft) / hop + 1 : 0;
+    *rows_out = rows;
+    if (rows == 0) return TETRA_OK;
+    if (!iq || !out) return fail(ctx, TETRA_E_INVALID, "tetra_stft_db: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool d_in = is_device_ptr(iq), d_out = is_device_ptr(out);
+    const float2* dx = (const float2*)iq;
+    float* dout = out;
+    if (!d_in) {
+        CK(ctx->in.ensure((size_t)n * sizeof(float2)));
+        CK(cudaMemcpyAsync(ctx->in.p, iq, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, st));
+        dx = (const float2*)ctx->in.p;
+    }
+    if (!d_out) { CK(ctx->y.ensure((size_t)rows * nfft * sizeof(float))); dout = (float*)ctx->y.p; }
+    int rc = stft_launch(st, dx, n, nfft, hop, rows, dout);
+    ctx->launches++;
+    if (rc) return fail(ctx, TETRA_E_CUDA, "tetra_stft_db: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CK(cudaGetLastError());
+    if (!d_out) CK(cudaMemcpyAsync(out, dout, (size_t)rows * nfft * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_design_butter4(double wn, double* b5, double* a5) {
+    if (!b5 || !a5) return TETRA_E_INVALID;
+    return design_butter4(wn, b5, a5) ? TETRA_OK : TETRA_E_INVALID;
+}
+int tetra_design_cheby1_sos8(double rp, double wn, double* sos24) {
+    if (!sos24) return TETRA_E_INVALID;
+    return design_cheby1_sos8(rp, wn, sos24) ? TETRA_OK : TETRA_E_INVALID;
+}
+
+}  // extern "C"

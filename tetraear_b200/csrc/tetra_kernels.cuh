@@ -1,0 +1,318 @@
+// Device kernels of libtetra_b200 (sm_100a). See DESIGN.md for the data layout and the
+// derivation of every stage; tools/design_filters.py for the FIR tables.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "taps_generated.h"
+
+namespace tetra {
+
+// ----------------------------------------------------------------------------------------------
+// small device helpers
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 ffma2(float2 a, float s, float2 c) {
+    // packed fp32x2 FMA (Blackwell FFMA2): (a.x, a.y) * (s, s) + c
+    float2 b = make_float2(s, s);
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c);
+    unsigned long long rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+    unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+    unsigned long long rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2*>(&rd);
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared through the TMA unit (SASS: UBLKCP), completion on mbarrier.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// K1  channelize_demod_fused  (fast path, fs = 2.4 MS/s, freq_offset = 0)
+// ----------------------------------------------------------------------------------------------
+// One CTA streams one (carrier, segment) through the four FIR stages
+//   A proto /10 -> B half-band /2 -> C fir120 (4 tap quarters) -> D sum + x2 interp + |y|^2 bins
+// with every stage working, in the same iteration, on data produced in earlier iterations, so a
+// single __syncthreads per 6400-sample tile is the only block-wide barrier. IQ tiles arrive by
+// 1-D TMA bulk copies into a 3-deep ring, two tiles ahead of the compute.
+constexpr int K1_TILE = 6400;             // input samples per iteration
+constexpr int K1_HDR = 40;                // samples of the previous tile kept in front of each buffer
+constexpr int K1_W = K1_TILE / 10;        // 640 w (240 kS/s) samples per iteration
+constexpr int K1_U = K1_TILE / 20;        // 320 u/v (120 kS/s) samples per iteration
+constexpr int K1_NBUF = 3;
+constexpr int K1_WRING = 2048, K1_URING = 1024, K1_VRING = 1024;
+constexpr int K1_THREADS = 384;           // warps 0-3: A, 4-7: C, 8-9: B, 10-11: D
+constexpr int K1_DLANES = 64;
+// local (stream-origin relative) index ranges produced in iteration i
+constexpr int K1_A0 = -2;                 // w:  [640 i + A0, +640)
+constexpr int K1_B0 = -326;               // u:  [320 i + B0, +320)
+constexpr int K1_C0 = -710;               // vp: [320 i + C0, +320)
+constexpr int K1_D0 = -1038;              // v:  [320 i + D0, +320)  -> y [640 i + 2 D0, +640)
+constexpr int K1_PREROLL = 640;           // stream origin = n_lo - PREROLL (w samples)
+constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
+constexpr int K1_NPH = 13;
+
+static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 64 && TB_INT_K == 8, "tables changed: re-derive lags");
+// dependency checks (each stage only reads what earlier iterations produced)
+static_assert(2 * (K1_B0 + K1_U - 1) + TB_HB_H <= K1_A0 - 1, "B reads w of a later iteration");
+static_assert((K1_C0 + K1_U - 1) + TB_FIR_H <= K1_B0 - 1, "C reads u of a later iteration");
+static_assert((K1_D0 + K1_U - 1) + TB_INT_K <= K1_C0 - 1, "D reads v of a later iteration");
+static_assert((K1_A0 + K1_W) - (2 * K1_B0 - TB_HB_H) <= K1_WRING, "w ring too small");
+static_assert((K1_B0 + K1_U) - (K1_C0 - TB_FIR_H) <= K1_URING, "u ring too small");
+static_assert((K1_C0 + K1_U) - (K1_D0 - TB_INT_K) <= K1_VRING, "v ring too small");
+
+struct K1Smem {
+    float2 in[K1_NBUF][K1_HDR + K1_TILE];
+    float2 w[K1_WRING];
+    float2 u[K1_URING];
+    float2 vp[4][K1_VRING];
+    double bins[K1_NPH][K1_DLANES];
+    uint64_t full[K1_NBUF];
+};
+
+__constant__ float c_proto[2 * TB_PROTO_H + 1];
+__constant__ float c_hb[2 * TB_HB_H + 1];
+__constant__ float c_fir[2 * TB_FIR_H + 1 + 3];   // padded to 132 = 4 x 33
+__constant__ float c_interp[TB_INT_K];
+
+struct K1Args {
+    const float2* x;        // [C][pitch]
+    int64_t pitch;
+    int64_t n;              // samples per carrier
+    int32_t L;              // ceil(n/10)
+    int32_t seg_len;        // y samples per segment (multiple of 640)
+    int32_t n_seg;
+    float2* y;              // [C][y_pitch]
+    int64_t y_pitch;
+    double* partial;        // [C][n_seg][16]
+    int32_t aligned;        // 1: x base/pitch allow 16-byte bulk copies
+};
+
+// fill one input buffer body with tile k of the stream (global x index gx0 .. gx0+6400)
+__device__ __forceinline__ void k1_issue_tile(K1Smem& s, const K1Args& a, const float2* xc, int64_t gx0, int k,
+                                              int lane, bool full_warp) {
+    float2* dst = &s.in[k % K1_NBUF][K1_HDR];
+    uint64_t* bar = &s.full[k % K1_NBUF];
+    const bool inside = (gx0 >= 0) && (gx0 + K1_TILE <= a.n);
+    if (inside && a.aligned) {
+        if (lane == 0) {
+            mbar_expect_tx(bar, K1_TILE * 8);
+            tma_load_1d(dst, xc + gx0, K1_TILE * 8, bar);
+        }
+    } else {
+        // block-edge tile: bounds-checked copy with zero fill (zero extension of the block)
+        if (full_warp) {
+            for (int t = lane; t < K1_TILE; t += 32) {
+                int64_t g = gx0 + t;
+                dst[t] = (g >= 0 && g < a.n) ? __ldg(xc + g) : make_float2(0.f, 0.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Args a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int seg = blockIdx.x, car = blockIdx.y;
+    const int n_lo = seg * a.seg_len;
+    const int n_hi = min(n_lo + a.seg_len, a.L);
+    const int O = n_lo - K1_PREROLL;                      // stream origin in w samples (even)
+    const float2* xc = a.x + (int64_t)car * a.pitch;
+    const int64_t gx_origin = (int64_t)O * 10;
+    // iterations: last y local index needed is (n_hi-1-O); D_i ends at 640 i + 2 D0 + 639
+    const int n_iter = (n_hi - 1 - O - 2 * K1_D0 - (K1_W - 1) + K1_W - 1) / K1_W + 1;
+    // tiles that can contain input: local sample index < 10*(n_hi + 200 - O), global < n
+    int n_load = n_iter;
+    // valid y range written by this CTA (edges belong to the exact kernel)
+    const int y_lo = max(n_lo, K1_EDGE), y_hi = min(n_hi, a.L - K1_EDGE);
+
+    // ---- prologue: zero rings/bins/headers, init barriers, start the first two tiles ----
+    for (int i = tid; i < K1_WRING; i += K1_THREADS) s.w[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_URING; i += K1_THREADS) s.u[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < 4 * K1_VRING; i += K1_THREADS) (&s.vp[0][0])[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_NPH * K1_DLANES; i += K1_THREADS) (&s.bins[0][0])[i] = 0.0;
+    for (int i = tid; i < K1_NBUF * K1_HDR; i += K1_THREADS) s.in[i / K1_HDR][i % K1_HDR] = make_float2(0.f, 0.f);
+    if (tid == 0) {
+        for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        k1_issue_tile(s, a, xc, gx_origin, 0, lane, true);
+        if (n_load > 1) k1_issue_tile(s, a, xc, gx_origin + K1_TILE, 1, lane, true);
+    }
+
+    // per-role constants
+    float ctap[33];                                        // role C: this warp's tap quarter
+    if (warp >= 4 && warp < 8) {
+        const int q = warp - 4;
+#pragma unroll
+        for (int k = 0; k < 33; ++k) ctap[k] = c_fir[32 * q + k];   // quarter q uses taps [32q, 32q+32) (+1 for q=3)
+    }
+
+    for (int i = 0; i < n_iter; ++i) {
+        // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
+        if (warp == 0 && i + 2 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i + 2) * K1_TILE, i + 2, lane, true);
+
+        if (warp < 4) {
+            // ---------------- role A: proto, 5 outputs per lane ----------------
+            const int L5 = tid;                            // 0..127
+            mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
+            const float2* buf = &s.in[i % K1_NBUF][0];
+            const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
+            float2 acc[5];
+#pragma unroll
+            for (int g = 0; g < 5; ++g) acc[g] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t2 = 0; t2 < 41; ++t2) {
+                const float4 v = p4[t2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = 2 * t2 + h;
+                    const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) {
+                        const int d = t - 10 * g;
+                        if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                    }
+                }
+            }
+            const int wbase = K1_W * i + K1_A0 + 5 * L5;
+#pragma unroll
+            for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
+            // tail of this tile -> header of the next buffer
+            if (L5 < K1_HDR) s.in[(i + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
+        } else if (warp < 8) {
+            // ---------------- role C: fir120 quarter, 10 outputs per lane ----------------
+            const int q = warp - 4;
+            const int nu0 = K1_U * i + K1_C0 + 10 * lane;   // first output (local u index), even
+            const int s0 = nu0 - TB_FIR_H + 32 * q;         // first input sample, even
+            float2 acc[10];
+#pragma unroll
+            for (int r = 0; r < 10; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t2 = 0; t2 < 21; ++t2) {
+                const float4 v = *reinterpret_cast<const float4*>(&s.u[(s0 + 2 * t2) & (K1_URING - 1)]);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int t = 2 * t2 + h;
+                    const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) {
+                        const int k = t - r;               // tap index within the quarter
+                        if (k >= 0 && k < 32) acc[r] = ffma2(xv, ctap[k], acc[r]);
+                    }
+                }
+            }
+            if (q == 3) {                                   // 129th tap (k = 32 of the last quarter)
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {
+                    const float2 xv = s.u[(s0 + 32 + r) & (K1_URING - 1)];
+                    acc[r] = ffma2(xv, ctap[32], acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 10; ++r) s.vp[q][(nu0 + r) & (K1_VRING - 1)] = acc[r];
+        } else if (warp < 10) {
+            // ---------------- role B: half-band /2, 5 outputs per lane ----------------
+            const int lb = tid - 256;                       // 0..63
+            const int nu0 = K1_U * i + K1_B0 + 5 * lb;
+            float2 acc[5];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) acc[r] = make_float2(0.f, 0.f);
+            const int w0 = 2 * nu0 - TB_HB_H;               // first w sample needed
+#pragma unroll
+            for (int t = 0; t < 2 * 4 + 2 * TB_HB_H + 1; ++t) {
+                const float2 xv = s.w[(w0 + t) & (K1_WRING - 1)];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) {
+                    const int d = t - 2 * r;                // tap index 0..22 (centre 11)
+                    if (d >= 0 && d <= 2 * TB_HB_H && (d == TB_HB_H || ((d - TB_HB_H) & 1)))
+                        acc[r] = ffma2(xv, c_hb[d], acc[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
+        } else {
+            // ---------------- role D: sum quarters, x2 interpolation, store, power bins ----------------
+            const int ld = tid - 320;                       // 0..63
+            const int nu0 = K1_U * i + K1_D0 + 5 * ld;      // local v index of first output pair
+            float2 v[5 + 2 * TB_INT_K - 1];                 // v[nu0-7 .. nu0+4+8]
+#pragma unroll
+            for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) {
+                const int idx = (nu0 - (TB_INT_K - 1) + t) & (K1_VRING - 1);
+                v[t] = fadd2(fadd2(s.vp[0][idx], s.vp[1][idx]), fadd2(s.vp[2][idx], s.vp[3][idx]));
+            }
+            float2 yv[10];
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+                yv[2 * r] = v[r + TB_INT_K - 1];
+                float2 o = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < TB_INT_K; ++k)
+                    o = ffma2(fadd2(v[r + TB_INT_K - 1 - k], v[r + TB_INT_K + k]), c_interp[k], o);
+                yv[2 * r + 1] = o;
+            }
+            const int n0 = O + 2 * nu0;                     // global y index of yv[0]
+            float2* yc = a.y + (int64_t)car * a.y_pitch;
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const int n = n0 + r;
+                if (n >= y_lo && n < y_hi) {
+                    yc[n] = yv[r];
+                    const int ph = n % K1_NPH;
+                    s.bins[ph][ld] += (double)yv[r].x * (double)yv[r].x + (double)yv[r].y * (double)yv[r].y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: reduce the 64 private bin columns ----
+    if (tid < K1_NPH) {
+        double t = 0.0;
+        for (int j = 0; j < K1_DLANES; ++j) t += s.bins[tid][j];
+        a.partial[((int64_t)car * a.n_seg + seg) * 16 + tid] = t;
+    }
+}
+
+}  // namespace tetra

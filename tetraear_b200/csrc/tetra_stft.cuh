@@ -1,0 +1,261 @@
+// K3 waterfall STFT + the small complex128 helper kernels behind the public helper entry points.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tetra {
+
+// ----------------------------------------------------------------------------------------------
+// K3  stft_power_db : ui/modern.py:1921-1934 applied at every hop.
+//   row r: X = FFT(hann(nfft) * x[r*hop : r*hop+nfft]);  out[r][(k + nfft/2) % nfft] = 20 log10(|X[k]|/nfft + 1e-20)
+// One persistent CTA per SM builds the Hann window and the twiddle table once in shared memory
+// (fp64 sincospi, rounded to fp32) and then transforms rows with an in-smem radix-2 Stockham FFT.
+// ----------------------------------------------------------------------------------------------
+constexpr int STFT_THREADS = 512;
+
+template <int NFFT>
+__global__ void __launch_bounds__(STFT_THREADS) k_stft_db(const float2* __restrict__ x, int64_t n, int hop, int64_t rows,
+                                                            float* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    float2* buf0 = reinterpret_cast<float2*>(sm_raw);
+    float2* buf1 = buf0 + NFFT;
+    float2* tw = buf1 + NFFT;                    // NFFT/2 twiddles exp(-2 pi i t / NFFT)
+    float* win = reinterpret_cast<float*>(tw + NFFT / 2);
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NFFT / 2; t += STFT_THREADS) {
+        double s, c;
+        sincospi(-2.0 * (double)t / (double)NFFT, &s, &c);
+        tw[t] = make_float2((float)c, (float)s);
+    }
+    for (int t = tid; t < NFFT; t += STFT_THREADS)   // np.hanning: symmetric, 0.5 - 0.5 cos(2 pi n / (N-1))
+        win[t] = (float)(0.5 - 0.5 * cospi(2.0 * (double)t / (double)(NFFT - 1)));
+    __syncthreads();
+    const float inv_n = 1.0f / (float)NFFT;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float2* xr = x + r * hop;
+        for (int t = tid; t < NFFT; t += STFT_THREADS) {
+            const float2 v = __ldg(xr + t);
+            const float w = win[t];
+            buf0[t] = make_float2(v.x * w, v.y * w);
+        }
+        __syncthreads();
+        float2* src = buf0;
+        float2* dst = buf1;
+#pragma unroll 1
+        for (int ns = 1; ns < NFFT; ns <<= 1) {
+            const int tw_stride = NFFT / (2 * ns);
+            for (int j = tid; j < NFFT / 2; j += STFT_THREADS) {
+                const int k = j & (ns - 1);
+                const float2 w = tw[k * tw_stride];
+                const float2 a = src[j];
+                const float2 b = src[j + NFFT / 2];
+                const float2 bw = make_float2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+                const int j0 = ((j - k) << 1) + k;
+                dst[j0] = make_float2(a.x + bw.x, a.y + bw.y);
+                dst[j0 + ns] = make_float2(a.x - bw.x, a.y - bw.y);
+            }
+            __syncthreads();
+            float2* t = src; src = dst; dst = t;
+        }
+        float* orow = out + r * NFFT;
+        for (int k = tid; k < NFFT; k += STFT_THREADS) {
+            const float2 v = src[(k + NFFT / 2) & (NFFT - 1)];   // fftshift
+            const float mag = sqrtf(v.x * v.x + v.y * v.y) * inv_n + 1e-20f;
+            orow[k] = 20.0f * log10f(mag);
+        }
+        __syncthreads();
+    }
+}
+
+template <int NFFT>
+static int stft_launch_t(cudaStream_t st, const float2* x, int64_t n, int hop, int64_t rows, float* out) {
+    const size_t smem = (size_t)NFFT * 8 * 2 + (size_t)NFFT / 2 * 8 + (size_t)NFFT * 4;
+    if (cudaFuncSetAttribute(k_stft_db<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)sms * per_sm);
+    k_stft_db<NFFT><<<grid, STFT_THREADS, smem, st>>>(x, n, hop, rows, out);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+static int stft_launch(cudaStream_t st, const float2* x, int64_t n, int nfft, int hop, int64_t rows, float* out) {
+    switch (nfft) {
+        case 64: return stft_launch_t<64>(st, x, n, hop, rows, out);
+        case 128: return stft_launch_t<128>(st, x, n, hop, rows, out);
+        case 256: return stft_launch_t<256>(st, x, n, hop, rows, out);
+        case 512: return stft_launch_t<512>(st, x, n, hop, rows, out);
+        case 1024: return stft_launch_t<1024>(st, x, n, hop, rows, out);
+        case 2048: return stft_launch_t<2048>(st, x, n, hop, rows, out);
+        case 4096: return stft_launch_t<4096>(st, x, n, hop, rows, out);
+        case 8192: return stft_launch_t<8192>(st, x, n, hop, rows, out);
+    }
+    return -1;
+}
+
+// ----------------------------------------------------------------------------------------------
+// complex128 helpers
+// ----------------------------------------------------------------------------------------------
+// frequency_shift (processor.py:97-100): x[n] * exp(-1j * 2 pi f * (n / fs))
+__global__ void k_nco_c128(double2* x, int64_t n, double fo, double fs) {
+    const double w = (2.0 * M_PI) * fo;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = (double)i / fs;
+        double s, c;
+        sincos(-(w * t), &s, &c);
+        const double2 v = x[i];
+        x[i] = make_double2(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+// extract_symbols (processor.py:179-219) on complex128: res[0] = n_symbols, res[1] = best phase
+__global__ void __launch_bounds__(256) k_extract_c128(const double2* x, int64_t n, int sps, int step, double2* out, int64_t* res) {
+    __shared__ double red[8];
+    __shared__ int s_best;
+    const int tid = threadIdx.x;
+    int best = 0;
+    double best_pow = -1.0;
+    for (int ph = 0; ph < sps; ph += step) {
+        const int64_t cnt = (n - ph) / sps;
+        if (cnt <= 0) continue;
+        double acc = 0.0;
+        for (int64_t k = tid; k < cnt; k += 256) {
+            const double2 v = x[ph + k * sps];
+            acc += v.x * v.x + v.y * v.y;
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < 8; ++w) s += red[w];
+            const double mean = s / (double)cnt;
+            if (mean > best_pow) { best_pow = mean; best = ph; }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) s_best = best;
+    __syncthreads();
+    best = s_best;
+    const int64_t cnt = (n - best) / sps > 0 ? (n - best) / sps : 0;
+    for (int64_t k = tid; k < cnt; k += 256) out[k] = x[best + k * sps];
+    if (tid == 0) { res[0] = cnt; res[1] = best; }
+}
+
+// max |x| (processor.py:124-125); doubles >= 0 order like their bit patterns
+__global__ void k_maxabs_c128(const double2* x, int64_t n, unsigned long long* out) {
+    double m = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = fmax(m, hypot(x[i].x, x[i].y));
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// demodulate_dqpsk (processor.py:127-163)
+__global__ void k_slice_c128(const double2* x, int64_t n, const double* maxabs, uint8_t* out) {
+    const double mx = *maxabs;
+    const double T3 = 3.0 * M_PI / 8.0, T5 = 5.0 * M_PI / 8.0;
+    for (int64_t i = 1 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 s1 = x[i], s0 = x[i - 1];
+        if (mx > 0) { s1.x /= mx; s1.y /= mx; s0.x /= mx; s0.y /= mx; }
+        const double re = s1.x * s0.x + s1.y * s0.y;
+        const double im = s1.y * s0.x - s1.x * s0.y;
+        const double ph = atan2(im, re);
+        uint8_t d;
+        if (ph < -T5) d = 3; else if (ph < -T3) d = 2; else if (ph < T3) d = 0; else if (ph < T5) d = 1; else d = 3;
+        out[i - 1] = d;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fourier resampling (scipy.signal.resample, two-sided FFT branch for complex input):
+//   Y[:m2] = X[:m2]; Y[m2-m:] = X[m2-m:]; even m: down -> Y[m/2] += X[n-m/2]; up -> split the bin.
+//   y = IDFT_num(Y) * (num / n)
+// evaluated as two direct DFT sums over the <= m+1 kept bins with exact integer phase reduction.
+// ----------------------------------------------------------------------------------------------
+__global__ void k_phase_table(double2* tab, int64_t n, double sign) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s, c;
+        sincospi(sign * 2.0 * (double)i / (double)n, &s, &c);
+        tab[i] = make_double2(c, s);
+    }
+}
+// one block per kept bin b (0 <= b < nb): bin index kx(b) in X; Ykeep[b] = sum_j x[j] tab[(j*kx) % n]
+__global__ void __launch_bounds__(256) k_dft_bins(const double2* x, int64_t n, const double2* tab, int64_t m2, int64_t m,
+                                                  int64_t nb, double2* ykeep) {
+    __shared__ double2 red[8];
+    for (int64_t b = blockIdx.x; b < nb; b += gridDim.x) {
+        int64_t kx;
+        if (b < m2) kx = b; else if (b < m) kx = n - (m - b); else kx = n - m / 2;   // b == m: the extra -m/2 bin
+        double ar = 0, ai = 0;
+        for (int64_t j = threadIdx.x; j < n; j += 256) {
+            const double2 w = tab[(j * kx) % n];
+            const double2 v = x[j];
+            ar += v.x * w.x - v.y * w.y;
+            ai += v.x * w.y + v.y * w.x;
+        }
+        for (int o = 16; o; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_double2(ar, ai);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sr = 0, si = 0;
+            for (int w = 0; w < 8; ++w) { sr += red[w].x; si += red[w].y; }
+            ykeep[b] = make_double2(sr, si);
+        }
+        __syncthreads();
+    }
+}
+// y[t] = (1/n) sum_b Yb * exp(+2 pi i ky(b) t / num)
+__global__ void __launch_bounds__(256) k_idft_bins(const double2* ykeep, int64_t n, int64_t num, const double2* tab_out,
+                                                   int64_t m2, int64_t m, int mode /*0 same,1 down,2 up*/, double2* y) {
+    __shared__ double2 red[8];
+    const bool even = (m % 2) == 0;
+    for (int64_t t = blockIdx.x; t < num; t += gridDim.x) {
+        double ar = 0, ai = 0;
+        for (int64_t b = threadIdx.x; b < m; b += 256) {
+            int64_t ky = b < m2 ? b : num - (m - b);
+            double2 v = ykeep[b];
+            if (even && b == m / 2) {
+                if (mode == 1) { v.x += ykeep[m].x; v.y += ykeep[m].y; }
+                else if (mode == 2) { v.x *= 0.5; v.y *= 0.5; }
+            }
+            const double2 w = tab_out[(ky * t) % num];
+            ar += v.x * w.x - v.y * w.y;
+            ai += v.x * w.y + v.y * w.x;
+            if (even && b == m / 2 && mode == 2) {           // mirrored half of the split bin
+                const double2 w2 = tab_out[((num - m / 2) * t) % num];
+                ar += v.x * w2.x - v.y * w2.y;
+                ai += v.x * w2.y + v.y * w2.x;
+            }
+        }
+        for (int o = 16; o; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = make_double2(ar, ai);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sr = 0, si = 0;
+            for (int w = 0; w < 8; ++w) { sr += red[w].x; si += red[w].y; }
+            y[t] = make_double2(sr / (double)n, si / (double)n);
+        }
+        __syncthreads();
+    }
+}
+
+// scratch: tabs holds max(n, num) phase entries (reused for both directions), y receives num outputs
+static int resample_c128(int64_t& launches, cudaStream_t st, const double2* x, int64_t n, double2* tabs, int64_t num, double2* y) {
+    const int64_t m = std::min(n, num), m2 = m / 2 + 1;
+    const bool even = (m % 2) == 0;
+    const int mode = num < n ? 1 : (n < num ? 2 : 0);
+    const int64_t nb = m + ((even && mode == 1) ? 1 : 0);
+    double2* ykeep = nullptr;
+    if (cudaMallocAsync((void**)&ykeep, (size_t)(m + 1) * sizeof(double2), st) != cudaSuccess) return -1;
+    k_phase_table<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, st>>>(tabs, n, -1.0);
+    k_dft_bins<<<(int)std::min<int64_t>(nb, 65535), 256, 0, st>>>(x, n, tabs, m2, m, nb, ykeep);
+    k_phase_table<<<(int)std::min<int64_t>((num + 255) / 256, 1024), 256, 0, st>>>(tabs, num, 1.0);
+    k_idft_bins<<<(int)std::min<int64_t>(num, 65535), 256, 0, st>>>(ykeep, n, num, tabs, m2, m, mode, y);
+    launches += 4;
+    cudaFreeAsync(ykeep, st);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace tetra

@@ -1,0 +1,230 @@
+"""Host-side mirror of the reference's ``tetraear.signal.processor.SignalProcessor``.
+
+Same class name, constructor, attributes and method surface as the reference
+(tetraear/signal/processor.py:18-273), so that ``TetraDecoder`` and the capture loops
+(ui/modern.py:1879, 2022; continuous_capture.py:50-56) run unchanged. Every method calls the
+sm_100a kernels through the C ABI of ``libtetra_b200.so`` (include/tetra_b200.h) with ctypes;
+there is no NumPy/SciPy implementation behind it and no CPU fallback: without the library or a
+CUDA device the constructor raises.
+
+Error behaviour follows the reference: empty input gives empty output (processor.py:239-241,
+120-121, 179-180, 66-67); a failure inside the DSP is logged on the reference's logger name and
+``process`` returns empty arrays instead of raising (processor.py:81-83, 256-257).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from . import _lib
+
+logger = logging.getLogger("tetraear.signal.processor")
+
+
+def _as_c64(samples) -> np.ndarray:
+    a = np.asarray(samples)
+    if a.dtype != np.complex64:
+        a = a.astype(np.complex64)
+    return np.ascontiguousarray(a)
+
+
+def _as_c128(samples) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(samples), dtype=np.complex128)
+
+
+class SignalProcessor:
+    """Processes raw IQ samples for TETRA demodulation on a B200 (drop-in for the reference class)."""
+
+    def __init__(self, sample_rate=2.4e6, device: int = 0):
+        self._lib = _lib.load()
+        self._ctx = _lib.c_ctx_p()
+        rc = self._lib.tetra_create(C.byref(self._ctx), int(device), float(sample_rate))
+        if rc != 0:
+            msg = self._lib.tetra_last_error(None)
+            raise _lib.TetraError(f"tetra_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.sample_rate = sample_rate
+        self.symbol_rate = 18000                                  # processor.py:30
+        self.samples_per_symbol = int(sample_rate / self.symbol_rate)   # processor.py:31
+        self.symbols = None                                       # processor.py:33
+        self.best_phase = None
+        self.device = int(device)
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.tetra_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        return _lib.check(self._lib, self._ctx, rc, what)
+
+    def _sync_rate(self):
+        # sample_rate is a plain attribute mutated from outside (ui/modern.py:1851-1852)
+        self._check(self._lib.tetra_set_sample_rate(self._ctx, float(self.sample_rate)), "set_sample_rate")
+
+    # -- reference helper methods -----------------------------------------------------------
+    def resample(self, samples, target_rate):
+        """processor.py:35-49 (scipy.signal.resample, FFT method) -- Fourier resampling on device."""
+        x = _as_c128(samples)
+        num = int(len(x) * target_rate / self.sample_rate)
+        if len(x) == 0 or num <= 0:
+            return np.zeros(max(num, 0), dtype=np.complex128)
+        out = np.empty(num, dtype=np.complex128)
+        self._check(self._lib.tetra_resample(self._ctx, x.ctypes.data, len(x), num, out.ctypes.data), "resample")
+        return out
+
+    def filter_signal(self, samples, bandwidth=25000, sample_rate=None):
+        """processor.py:51-83: Butterworth order-4 low-pass, zero phase."""
+        if len(samples) == 0:
+            return samples
+        fs = sample_rate if sample_rate is not None else self.sample_rate
+        x = _as_c128(samples)
+        out = np.empty_like(x)
+        try:
+            self._check(self._lib.tetra_filter_signal(self._ctx, x.ctypes.data, len(x), float(bandwidth), float(fs),
+                                                      out.ctypes.data), "filter_signal")
+        except _lib.TetraError as e:
+            logger.warning(f"Filter design failed, using unfiltered samples: {e}")
+            return samples
+        return out
+
+    def frequency_shift(self, samples, freq_offset, sample_rate=None):
+        """processor.py:85-100: multiply by exp(-j 2 pi f n / fs)."""
+        fs = sample_rate if sample_rate is not None else self.sample_rate
+        x = _as_c128(samples)
+        out = np.empty_like(x)
+        if len(x):
+            self._check(self._lib.tetra_frequency_shift(self._ctx, x.ctypes.data, len(x), float(freq_offset),
+                                                        float(fs), out.ctypes.data), "frequency_shift")
+        return out
+
+    def demodulate_dqpsk(self, samples):
+        """processor.py:102-166: differential phase slicer -> uint8 in 0..3."""
+        if len(samples) < 2:
+            return np.array([], dtype=np.uint8)
+        x = _as_c128(samples)
+        out = np.empty(len(x) - 1, dtype=np.uint8)
+        n_out = C.c_int64(0)
+        self._check(self._lib.tetra_demodulate_dqpsk(self._ctx, x.ctypes.data, len(x), out.ctypes.data,
+                                                     C.byref(n_out)), "demodulate_dqpsk")
+        return out[: n_out.value]
+
+    def extract_symbols(self, samples, sample_rate=None):
+        """processor.py:168-219: block timing pick + symbol-rate gather."""
+        if len(samples) == 0:
+            return np.array([], dtype=complex)
+        fs = sample_rate if sample_rate is not None else self.sample_rate
+        x = _as_c128(samples)
+        out = np.empty(len(x), dtype=np.complex128)
+        n_out, ph = C.c_int64(0), C.c_int32(0)
+        self._check(self._lib.tetra_extract_symbols(self._ctx, x.ctypes.data, len(x), float(fs), out.ctypes.data,
+                                                    C.byref(n_out), C.byref(ph)), "extract_symbols")
+        self.best_phase = int(ph.value)
+        return out[: n_out.value].copy()
+
+    # -- the hot path -----------------------------------------------------------------------
+    def process(self, samples, freq_offset=0):
+        """processor.py:221-273 -> uint8 dibits; side effect ``self.symbols`` (processor.py:268)."""
+        if len(samples) == 0:
+            self.symbols = np.array([], dtype=complex)
+            return np.array([], dtype=np.uint8)
+        try:
+            res = self.process_batch(_as_c64(samples)[None, :], [float(freq_offset)], want_symbols=True)
+        except _lib.TetraError as e:
+            logger.warning(f"GPU demodulation failed: {e}")
+            self.symbols = np.array([], dtype=complex)
+            return np.array([], dtype=np.uint8)
+        n = int(res["n_dibits"][0])
+        n_sym = n + 1 if n > 0 else int(res["n_symbols"][0])
+        self.symbols = res["symbols"][0, :n_sym].astype(np.complex128)
+        self.best_phase = int(res["best_phase"][0])
+        return res["dibits"][0, :n].copy()
+
+    def process_batch(self, iq, freq_offsets=None, want_symbols=True, want_match=False):
+        """Batched ``process``: iq complex64 [C, N] (numpy), freq_offsets [C] or None.
+
+        Returns dict(dibits uint8 [C, cap], n_dibits int32 [C], n_symbols int32 [C], best_phase int32 [C],
+        symbols complex64 [C, cap+1] (if want_symbols), ts_match uint8 [C, 2*cap, 2] (if want_match)).
+        """
+        self._sync_rate()
+        iq = np.ascontiguousarray(iq, dtype=np.complex64)
+        if iq.ndim != 2:
+            raise ValueError("iq must be [carriers, samples]")
+        n_car, n = iq.shape
+        cap = int(self._lib.tetra_dibit_capacity(self._ctx, n))
+        dib = np.zeros((n_car, max(cap, 1)), dtype=np.uint8)
+        nd = np.zeros(n_car, dtype=np.int32)
+        ph = np.zeros(n_car, dtype=np.int32)
+        sym = np.zeros((n_car, cap + 1), dtype=np.complex64) if want_symbols else None
+        mt = np.zeros((n_car, 2 * max(cap, 1), 2), dtype=np.uint8) if want_match else None
+        fo = None
+        if freq_offsets is not None:
+            fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
+            if fo.shape != (n_car,):
+                raise ValueError("freq_offsets must have one entry per carrier")
+        self._check(self._lib.tetra_process_batch(
+            self._ctx, iq.ctypes.data, n_car, n, n, fo.ctypes.data if fo is not None else None,
+            dib.ctypes.data, cap, nd.ctypes.data, sym.ctypes.data if sym is not None else None, ph.ctypes.data,
+            mt.ctypes.data if mt is not None else None, 0), "process_batch")
+        n_sym = np.where(nd > 0, nd + 1, 0).astype(np.int32)
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=n_sym, best_phase=ph)
+        if sym is not None:
+            out["symbols"] = sym
+        if mt is not None:
+            out["ts_match"] = mt[:, : 2 * cap]
+        return out
+
+    # -- device-resident batch (bench / multi-GPU): pointers are raw CUDA addresses ----------
+    def process_batch_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int,
+                             cap: int, n_dibits_ptr: int, symbols_ptr: int = 0, best_phase_ptr: int = 0,
+                             ts_match_ptr: int = 0, stream: int = 0, freq_offsets=None):
+        """Enqueue on `stream` (a cudaStream_t as int) with all buffers already in HBM; asynchronous."""
+        self._sync_rate()
+        self._check(self._lib.tetra_set_stream(self._ctx, stream or None), "set_stream")
+        fo = None
+        if freq_offsets is not None:
+            fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
+        self._check(self._lib.tetra_process_batch(
+            self._ctx, iq_ptr, n_carriers, n_samples, pitch, fo.ctypes.data if fo is not None else None,
+            dibits_ptr, cap, n_dibits_ptr, symbols_ptr or None, best_phase_ptr or None, ts_match_ptr or None, 1),
+            "process_batch(device)")
+
+    def dibit_capacity(self, n_samples: int) -> int:
+        self._sync_rate()
+        return int(self._lib.tetra_dibit_capacity(self._ctx, int(n_samples)))
+
+    def stft_db(self, iq, n_fft=4096, hop=1024):
+        """Waterfall rows: ui/modern.py:1921-1934 applied at every hop -> float32 [rows, n_fft]."""
+        x = _as_c64(iq)
+        rows = C.c_int64(0)
+        n_rows = (len(x) - n_fft) // hop + 1 if len(x) >= n_fft else 0
+        out = np.empty((max(n_rows, 0), n_fft), dtype=np.float32)
+        self._check(self._lib.tetra_stft_db(self._ctx, x.ctypes.data, len(x), int(n_fft), int(hop),
+                                            out.ctypes.data, C.byref(rows)), "stft_db")
+        return out[: rows.value]
+
+    def spectrum(self, samples, n_fft=2048, center_frequency=0.0):
+        """The spectrum block of CaptureThread.run (ui/modern.py:1921-1937): (freqs, power_dB)."""
+        p = self.stft_db(np.asarray(samples)[:n_fft], n_fft, n_fft)
+        freqs = np.fft.fftshift(np.fft.fftfreq(n_fft, 1 / self.sample_rate)) + center_frequency
+        return freqs, p[0].astype(np.float64)
+
+    def enable_kernel_timing(self, on=True):
+        self._lib.tetra_enable_kernel_timing(self._ctx, 1 if on else 0)
+
+    def last_kernel_ms(self) -> float:
+        return float(self._lib.tetra_last_kernel_ms(self._ctx))
+
+    def launch_count(self) -> int:
+        return int(self._lib.tetra_launch_count(self._ctx))
+
+    def synchronize(self):
+        self._check(self._lib.tetra_synchronize(self._ctx), "synchronize")
