@@ -29,6 +29,7 @@ N_SAMPLES = 1 << 20
 TOTAL_CARRIERS = 4096
 BYTES_PER_SAMPLE = 8.10      # 8 B read + (1 B dibit + 8 B soft symbol + ~4 B match) per 130 samples
 METRIC = "IQ MS/s demodulated"
+WORKLOAD = "configs[3]: %d carriers x 2^20 complex64 samples @2.4 MS/s, sharded %d per GPU"
 
 
 def measured_peak():
@@ -99,42 +100,74 @@ def _cpu_worker(args):
     return time.perf_counter() - t0
 
 
-def cpu_rate(carriers_per_core=2, cores=None):
-    """MS/s of the oracle port with one process per host core, each on its own carriers."""
+def cpu_rate(carriers_per_core=2, cores=None, pool=None):
+    """MS/s of the oracle port with one process per host core, each on its own carrier stream."""
     import multiprocessing as mp
     cores = cores or len(os.sched_getaffinity(0))
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
+    own = pool is None
+    if own:
+        pool = mp.get_context("spawn").Pool(cores)
         pool.map(_cpu_worker, [(i, 0) for i in range(cores)])              # import + generate, untimed
+    try:
         t0 = time.perf_counter()
         pool.map(_cpu_worker, [(i, carriers_per_core) for i in range(cores)])
         dt = time.perf_counter() - t0
+    finally:
+        if own:
+            pool.close(); pool.join()
     total = cores * carriers_per_core * N_SAMPLES
     return total / dt / 1e6, cores, dt
 
 
+def cpu_baseline_sample(target_s=12.0):
+    """One bounded sample (about target_s seconds of wall time on all host cores) of the same workload."""
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.get_context("spawn").Pool(cores)
+    try:
+        pool.map(_cpu_worker, [(i, 0) for i in range(cores)])
+        _, _, dt1 = cpu_rate(1, cores, pool)                                # calibration pass
+        reps = int(max(2, min(256, round(target_s / max(dt1, 1e-3)))))
+        v, _, dt = cpu_rate(reps, cores, pool)
+    finally:
+        pool.close(); pool.join()
+    return v, cores, dt, reps
+
+
 def run_reference(a):
+    """--impl reference: the reference's CPU algorithm (oracle port: the same SciPy calls the reference makes,
+    plus symbols_to_bits and the TS1/TS2 match counts) on every host core; a step = a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals = []
-    for _ in range(a.warmup if a.warmup < 2 else 1):
-        cpu_rate(1)
-    steps = max(1, min(a.steps, 5))
-    cores = None
-    t_all = time.perf_counter()
-    for _ in range(steps):
-        v, cores, dt = cpu_rate(2)
-        vals.append(v)
-    wall = time.perf_counter() - t_all
-    v = float(np.mean(vals))
-    sample = f"{steps} steps x {cores} processes x 2 carriers x 2^20 samples (process + symbols_to_bits + TS match counts)"
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.get_context("spawn").Pool(cores)
+    budget_s = 150.0
+    try:
+        pool.map(_cpu_worker, [(i, 0) for i in range(cores)])
+        _, _, dt1 = cpu_rate(1, cores, pool)
+        steps = max(1, a.steps)
+        warm = max(0, a.warmup)
+        reps = int(max(1, min(64, (budget_s / (steps + warm)) / max(dt1, 1e-3))))
+        for _ in range(warm):
+            cpu_rate(reps, cores, pool)
+        vals, t_all = [], time.perf_counter()
+        for _ in range(steps):
+            v, _, _ = cpu_rate(reps, cores, pool)
+            vals.append(v)
+        wall = time.perf_counter() - t_all
+    finally:
+        pool.close(); pool.join()
+    v = cores * reps * steps * N_SAMPLES / wall / 1e6
+    sample = (f"{steps} steps x {cores} processes x {reps} carrier-blocks x 2^20 samples "
+              f"(process + symbols_to_bits + TS1/TS2 match counts), {wall:.1f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": a.gpus, "steps": steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "strong",
+        "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "4096 carriers x 2^20 complex samples @2.4 MS/s (bounded sample of it on the host)",
-                   "n_samples": N_SAMPLES},
+        "config": {"workload": WORKLOAD % (a.carriers, a.carriers // max(1, a.gpus)) + " (bounded sample of it on the host cores)",
+                   "n_samples": N_SAMPLES, "carriers": a.carriers},
         "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -193,49 +226,48 @@ def run_ours(a):
     if world > 1:
         all_dib = torch.zeros((total, cap), dtype=torch.uint8, device=dev)
         all_nd = torch.zeros(total, dtype=torch.int32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
+    # every kernel of the step, the NCCL gather and the timing events share ONE explicit stream
+    work = torch.cuda.Stream(device=dev)
     sp.enable_kernel_timing(True)
 
     def step():
         sp.process_batch_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
-                                sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=stream)
+                                sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream)
         if world > 1:
             dist.all_gather_into_tensor(all_dib, dib)
             dist.all_gather_into_tensor(all_nd, nd)
 
-    for _ in range(a.warmup):
-        step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.3)
-    l0 = sp.launch_count()
-    k_ms = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(a.steps):
-        step()
-        k_ms.append(None)
-    ev1.record()
-    torch.cuda.synchronize()
+    with torch.cuda.stream(work):
+        for _ in range(a.warmup):
+            step()
+        torch.cuda.synchronize()
+        sp.kernel_time_ms()                                  # drop the warm-up launches from the record
+        if world > 1:
+            dist.barrier()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.5)
+        l0 = sp.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(work)
+        for _ in range(a.steps):
+            step()
+        ev1.record(work)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
     launches = sp.launch_count() - l0
-    # dominant kernel, timed alone with CUDA events on the launching stream (separate, untimed-region passes)
-    for i in range(min(a.steps, 5)):
-        sp.process_batch_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
-                                sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=stream)
-        torch.cuda.synchronize()
-        k_ms[i] = sp.last_kernel_ms()
-    k_ms = [k for k in k_ms if k is not None and k > 0]
+    k_total_ms, k_n = sp.kernel_time_ms()                    # the fused kernel's launches INSIDE the timed region
+    if rank == 0:
+        time.sleep(0.3)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.barrier()
     ms_total = float(t.item())
     ms_step = ms_total / a.steps
     value = total * N_SAMPLES / (ms_step * 1e-3) / 1e6
@@ -252,53 +284,59 @@ def run_ours(a):
             ok &= n_i == len(r["dibits"]) and bool(np.array_equal(dib[i, :n_i].cpu().numpy(), r["dibits"]))
             s = torch.view_as_complex(sym[i, : n_i + 1]).cpu().numpy()
             ok &= bool(np.abs(s - r["symbols"]).max() / np.abs(r["symbols"]).max() < 1e-5)
+            bits = ref_dsp.symbols_to_bits(r["dibits"])
+            ok &= bool(np.array_equal(mt[i, : 2 * n_i - 21].cpu().numpy(), ref_dsp.match_counts(bits)))
         parity = bool(ok)
 
-    # ---- e2e: host buffers through the public API, H2D + D2H inside the timed region ----
-    e2e = None
-    if rank == 0 or world > 1:
-        ce = min(a.e2e_carriers, n_local)
-        hx = torch.view_as_complex(x[:ce]).cpu().pin_memory()
-        hx_np = hx.numpy()
-        sp._lib.tetra_set_stream(sp._ctx, None)
-        r0 = sp.process_batch(hx_np, None, want_symbols=False, want_match=False)     # warm-up (allocations)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        reps = 3
-        for _ in range(reps):
-            r0 = sp.process_batch(hx_np, None, want_symbols=False, want_match=False)
-        dt = (time.perf_counter() - t0) / reps
-        te = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        dt = float(te.item())
-        e2e = {"value": world * ce * N_SAMPLES / dt / 1e6, "unit": "MS/s",
-               "h2d_bytes_per_step": int(ce * N_SAMPLES * 8), "d2h_bytes_per_step": int(ce * (cap + 8)),
-               "carriers_per_rank": ce, "note": "pinned host IQ -> tetra_process_batch -> host dibits; PCIe-bound"}
+    # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region ----
+    ce = min(a.e2e_carriers, n_local)
+    hx = torch.view_as_complex(x[:ce]).cpu().pin_memory()
+    hx_np = hx.numpy()
+    sp._lib.tetra_set_stream(sp._ctx, None)
+    sp.process_batch(hx_np, None, want_symbols=False, want_match=False)          # warm-up (allocations)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        r0 = sp.process_batch(hx_np, None, want_symbols=False, want_match=False)
+    dt = (time.perf_counter() - t0) / reps
+    te = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    dt = float(te.item())
+    e2e = {"value": world * ce * N_SAMPLES / dt / 1e6, "unit": "MS/s",
+           "h2d_bytes_per_step": int(ce * N_SAMPLES * 8), "d2h_bytes_per_step": int(ce * (cap + 8)),
+           "carriers_per_rank": ce, "timed": "host wall clock around SignalProcessor.process_batch, max over ranks",
+           "note": "pinned host IQ -> tetra_process_batch -> host dibits; PCIe-bound"}
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        k_avg = float(np.mean(k_ms)) if k_ms else None
+        k_avg = (k_total_ms / k_n) if k_n else None
         achieved = (BYTES_PER_SAMPLE * n_local * N_SAMPLES / (k_avg * 1e-3) / 1e9) if k_avg else None
-        cpu_v, cpu_cores, cpu_dt = (None, None, None)
+        cpu = None
         if world == 1 and not a.no_cpu:
-            cpu_v, cpu_cores, cpu_dt = cpu_rate(2)
+            cpu_v, cpu_cores, cpu_dt, cpu_reps = cpu_baseline_sample()
+            cpu = {"value": cpu_v, "unit": "MS/s", "cores": cpu_cores, "kind": "port",
+                   "sample": "%d processes x %d carrier-blocks x 2^20 samples (process + symbols_to_bits + TS match counts), %.1f s"
+                             % (cpu_cores, cpu_reps, cpu_dt)}
         out = {
             "metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "carriers_per_s": value / 2.4,
-            "config": {"workload": "configs[3]: %d carriers x 2^20 complex64 samples @2.4 MS/s, sharded %d per GPU" % (total, n_local),
+            "config": {"workload": WORKLOAD % (total, n_local),
                        "n_samples": N_SAMPLES, "carriers": total, "freq_offset": 0,
                        "l2": "inputs (%.1f GiB per GPU) far larger than L2; no flush needed" % (n_local * N_SAMPLES * 8 / 2**30),
                        "outputs": "dibits + soft symbols + best phase + TS1/TS2 match counts"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "k1_channelize_demod", "kernel_ms": k_avg, "peak_source": peak_src,
-                         "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE},
-            "cpu_baseline": ({"value": cpu_v, "unit": "MS/s", "cores": cpu_cores, "kind": "port",
-                              "sample": "%d processes x 2 carriers x 2^20 samples, %.1f s" % (cpu_cores, cpu_dt)}
-                             if cpu_v else None),
+                         "frac": (achieved / peak) if achieved else None, "traffic": a.traffic,
+                         "kernel": "k1_channelize_demod", "kernel_ms": k_avg, "kernel_launches_timed": k_n,
+                         "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
+                         "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
+                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES},
+            "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity,
         }
         print(json.dumps(out))
@@ -316,6 +354,8 @@ def main():
     ap.add_argument("--carriers", type=int, default=TOTAL_CARRIERS)
     ap.add_argument("--e2e-carriers", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per launch of the fused kernel from an ncu --set full capture (profiles/), if known")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)

@@ -39,7 +39,8 @@ void tetra_destroy(tetra_ctx* ctx);
 const char* tetra_last_error(const tetra_ctx* ctx);
 /* SignalProcessor.sample_rate is mutated from outside at run time (ui/modern.py:1851-1852). */
 int tetra_set_sample_rate(tetra_ctx* ctx, double sample_rate);
-/* Work is enqueued on this CUDA stream (cudaStream_t as void*; NULL = the context's own stream). */
+/* Work is enqueued on this CUDA stream (cudaStream_t as void*; NULL = the context's own
+ * non-blocking stream; pass cudaStreamLegacy (0x1) for the legacy default stream). */
 int tetra_set_stream(tetra_ctx* ctx, void* cuda_stream);
 /* Block until everything enqueued by this context has finished. */
 int tetra_synchronize(tetra_ctx* ctx);
@@ -72,10 +73,12 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int
 
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t tetra_launch_count(const tetra_ctx* ctx);
-/* Device-time of the most recent fused channelize+demod kernel launch, in ms (CUDA events on the
- * context's stream); < 0 if none was timed. Enabled by tetra_enable_kernel_timing(ctx, 1). */
+/* With timing enabled every fused channelize+demod kernel launch is bracketed by a CUDA-event pair
+ * on the stream it is launched on. tetra_kernel_time_ms waits for them, returns the summed device
+ * time in ms of the launches recorded since the last query (< 0 if none), stores their number in
+ * *n_launches and resets the record. */
 int tetra_enable_kernel_timing(tetra_ctx* ctx, int on);
-double tetra_last_kernel_ms(tetra_ctx* ctx);
+double tetra_kernel_time_ms(tetra_ctx* ctx, int32_t* n_launches);
 
 /*
  * Host replay of TetraDecoder.find_sync (core/decoder.py:226-295) over device-computed match

@@ -49,8 +49,11 @@ struct tetra_ctx {
     int device = 0;
     double sample_rate = 2.4e6;
     cudaStream_t own_stream = nullptr, stream = nullptr, side = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
-    bool timing = false, timed = false;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // per-launch CUDA-event pairs around the fused kernel (bench.py's roofline leg)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    size_t ev_used = 0;
+    bool timing = false;
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
@@ -196,8 +199,7 @@ int tetra_create(tetra_ctx** out, int device, double sample_rate) {
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess ||
-        (e = cudaEventCreate(&ctx->ev_t0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev_t1)) != cudaSuccess) {
+        (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
         fail(nullptr, TETRA_E_CUDA, "tetra_create: %s", cudaGetErrorString(e));
         delete ctx;
         return TETRA_E_CUDA;
@@ -216,7 +218,7 @@ void tetra_destroy(tetra_ctx* ctx) {
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
-    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->side);
     delete ctx;
 }
@@ -247,13 +249,25 @@ int64_t tetra_dibit_capacity(const tetra_ctx* ctx, int64_t n) {
     return ns > 1 ? ns - 1 : 0;
 }
 int64_t tetra_launch_count(const tetra_ctx* ctx) { return ctx ? ctx->launches : 0; }
-int tetra_enable_kernel_timing(tetra_ctx* ctx, int on) { if (!ctx) return TETRA_E_INVALID; ctx->timing = on != 0; return 0; }
-double tetra_last_kernel_ms(tetra_ctx* ctx) {
-    if (!ctx || !ctx->timed) return -1.0;
-    float ms = -1.f;
-    if (cudaEventSynchronize(ctx->ev_t1) != cudaSuccess) return -1.0;
-    if (cudaEventElapsedTime(&ms, ctx->ev_t0, ctx->ev_t1) != cudaSuccess) return -1.0;
-    return (double)ms;
+int tetra_enable_kernel_timing(tetra_ctx* ctx, int on) {
+    if (!ctx) return TETRA_E_INVALID;
+    ctx->timing = on != 0;
+    ctx->ev_used = 0;
+    return 0;
+}
+double tetra_kernel_time_ms(tetra_ctx* ctx, int32_t* n_launches) {
+    if (n_launches) *n_launches = 0;
+    if (!ctx || ctx->ev_used == 0) return -1.0;
+    double total = 0.0;
+    for (size_t i = 0; i < ctx->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(ctx->ev_pool[i].second) != cudaSuccess) return -1.0;
+        if (cudaEventElapsedTime(&ms, ctx->ev_pool[i].first, ctx->ev_pool[i].second) != cudaSuccess) return -1.0;
+        total += ms;
+    }
+    if (n_launches) *n_launches = (int32_t)ctx->ev_used;
+    ctx->ev_used = 0;
+    return total;
 }
 
 int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
@@ -304,9 +318,11 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     for (int c = 0; c < C; ++c) {
         const bool zero_fo = !fo_hz || fo_hz[c] == 0.0;
         if (!zero_fo) any_fo = true;
-        if (fast_ok && zero_fo) { edge_jobs.push_back(make_int2(c, EX_LEFT)); edge_jobs.push_back(make_int2(c, EX_RIGHT)); }
+        if (fast_ok && zero_fo) edge_jobs.push_back(make_int2(c, EX_LEFT));
         else full_jobs.push_back(make_int2(c, EX_FULL));
     }
+    // LEFT jobs first, then RIGHT: the two window shapes differ in length, keep warps homogeneous
+    for (size_t k = 0, n_left = edge_jobs.size(); k < n_left; ++k) edge_jobs.push_back(make_int2(edge_jobs[k].x, EX_RIGHT));
     const bool use_fast = !edge_jobs.empty();
     if (use_fast && !full_jobs.empty())
         return fail(ctx, TETRA_E_UNSUPPORTED, "mixing zero and non-zero freq_offset in one batch: split the call");
@@ -364,11 +380,21 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
-        if (ctx->timing) CK(cudaEventRecord(ctx->ev_t0, st));
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        if (ctx->timing && ctx->ev_used < 4096) {
+            if (ctx->ev_used == ctx->ev_pool.size()) {
+                cudaEvent_t a = nullptr, b = nullptr;
+                CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+                ctx->ev_pool.emplace_back(a, b);
+            }
+            t0 = ctx->ev_pool[ctx->ev_used].first; t1 = ctx->ev_pool[ctx->ev_used].second;
+            ctx->ev_used++;
+            CK(cudaEventRecord(t0, st));
+        }
         k1_channelize_demod<<<dim3(n_seg, C), K1_THREADS, sizeof(K1Smem), st>>>(ka);
         ctx->launches++;
         CK(cudaGetLastError());
-        if (ctx->timing) { CK(cudaEventRecord(ctx->ev_t1, st)); ctx->timed = true; }
+        if (t1) CK(cudaEventRecord(t1, st));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;

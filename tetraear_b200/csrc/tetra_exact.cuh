@@ -14,6 +14,7 @@ constexpr int EX_PAD1 = 27;   // sosfiltfilt: 3 * (2*n_sections + 1), n_sections
 constexpr int EX_PAD2 = 15;   // filtfilt: 3 * max(len(a), len(b)) = 3 * 5
 constexpr int EX_T1 = 1280;   // warm-up of an approximate start/end, stage 1 (pole radius 0.9821 -> 8e-11)
 constexpr int EX_T2 = 160;    // same for stage 2 (pole radius 0.8837 -> 3e-9)
+constexpr int EX_U = 8;       // recursion steps per load group
 
 enum { EX_FULL = 0, EX_LEFT = 1, EX_RIGHT = 2 };
 
@@ -145,18 +146,38 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
         int64_t e_lo = 0, e_hi = tot;
         if (mode == EX_LEFT) e_hi = min(tot, (int64_t)EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
         else if (mode == EX_RIGHT) e_lo = max((int64_t)0, (int64_t)EX_PAD1 + (int64_t)q * m_lo - EX_T1);
+        // Both passes run in groups of EX_U steps: the group's loads are issued together ahead of
+        // the (serially dependent) recursion steps, so memory latency is paid once per group.
         SosState st;
         sos_init(st, a.cf, ex_oddext(xat, n, EX_PAD1, e_lo));
-        for (int64_t e = e_lo; e < e_hi; ++e)
-            a.scr1[(e - e_lo) * nj + j] = sos_step(st, a.cf, ex_oddext(xat, n, EX_PAD1, e));
+        for (int64_t e = e_lo; e < e_hi; e += EX_U) {
+            double2 in[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) in[u] = ex_oddext(xat, n, EX_PAD1, min(e + u, e_hi - 1));
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                const double2 v = sos_step(st, a.cf, in[u]);
+                if (e + u < e_hi) a.scr1[(e + u - e_lo) * nj + j] = v;
+            }
+        }
         sos_init(st, a.cf, a.scr1[(e_hi - 1 - e_lo) * nj + j]);
-        const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);
-        for (int64_t e = e_hi - 1; e >= e_stop; --e) {
-            const double2 v = sos_step(st, a.cf, a.scr1[(e - e_lo) * nj + j]);
-            const int64_t i = e - EX_PAD1;
-            if (i >= 0 && i < n && (i % q) == 0) {
-                const int m = (int)(i / q);
-                if (m >= m_lo && m < m_hi) a.scrz[(int64_t)(m - m_lo) * nj + j] = nco(v, m);
+        const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);   // >= EX_PAD1: i below is >= 0
+        int64_t i = e_hi - 1 - EX_PAD1;                  // input index of the step being produced
+        int m = (int)(i / q), r = (int)(i % q);          // i = q*m + r, kept incrementally
+        for (int64_t e = e_hi - 1; e >= e_stop; e -= EX_U) {
+            double2 in[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) in[u] = a.scr1[(max(e - u, e_stop) - e_lo) * nj + j];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                if (e - u >= e_stop) {
+                    const double2 v = sos_step(st, a.cf, in[u]);
+                    if (r == 0) {
+                        if (i < n && m >= m_lo && m < m_hi) a.scrz[(int64_t)(m - m_lo) * nj + j] = nco(v, m);
+                        r = q; --m;
+                    }
+                    --r; --i;
+                }
             }
         }
     } else {
@@ -178,13 +199,30 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
         auto z2 = [&](int64_t e) { return ex_oddext(zat, (int64_t)L, EX_PAD2, e); };
         BaState st;
         ba_init(st, a.cf, z2(e_lo));
-        for (int64_t e = e_lo; e < e_hi; ++e) a.scr2[(e - e_lo) * nj + j] = ba_step(st, a.cf, z2(e));
+        for (int64_t e = e_lo; e < e_hi; e += EX_U) {
+            double2 in[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) in[u] = z2(min(e + u, e_hi - 1));
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                const double2 v = ba_step(st, a.cf, in[u]);
+                if (e + u < e_hi) a.scr2[(e + u - e_lo) * nj + j] = v;
+            }
+        }
         ba_init(st, a.cf, a.scr2[(e_hi - 1 - e_lo) * nj + j]);
         const int64_t e_stop = (int64_t)EX_PAD2 + o_lo;
-        for (int64_t e = e_hi - 1; e >= e_stop; --e) {
-            const double2 v = ba_step(st, a.cf, a.scr2[(e - e_lo) * nj + j]);
-            const int64_t m = e - EX_PAD2;
-            if (m >= o_lo && m < o_hi) put((int)m, v);
+        for (int64_t e = e_hi - 1; e >= e_stop; e -= EX_U) {
+            double2 in[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) in[u] = a.scr2[(max(e - u, e_stop) - e_lo) * nj + j];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                if (e - u >= e_stop) {
+                    const double2 v = ba_step(st, a.cf, in[u]);
+                    const int64_t m = e - u - EX_PAD2;
+                    if (m >= o_lo && m < o_hi) put((int)m, v);
+                }
+            }
         }
     } else {
         for (int m = o_lo; m < o_hi; ++m) put(m, zat(m));

@@ -185,10 +185,13 @@ class SignalProcessor:
     # -- device-resident batch (bench / multi-GPU): pointers are raw CUDA addresses ----------
     def process_batch_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int,
                              cap: int, n_dibits_ptr: int, symbols_ptr: int = 0, best_phase_ptr: int = 0,
-                             ts_match_ptr: int = 0, stream: int = 0, freq_offsets=None):
-        """Enqueue on `stream` (a cudaStream_t as int) with all buffers already in HBM; asynchronous."""
+                             ts_match_ptr: int = 0, stream=None, freq_offsets=None):
+        """Enqueue on `stream` (a cudaStream_t as int; 0 = the legacy default stream, None = the
+        context's own stream) with all buffers already in HBM; asynchronous."""
         self._sync_rate()
-        self._check(self._lib.tetra_set_stream(self._ctx, stream or None), "set_stream")
+        if stream is not None and int(stream) == 0:
+            stream = 1                                    # cudaStreamLegacy
+        self._check(self._lib.tetra_set_stream(self._ctx, stream), "set_stream")
         fo = None
         if freq_offsets is not None:
             fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
@@ -220,8 +223,11 @@ class SignalProcessor:
     def enable_kernel_timing(self, on=True):
         self._lib.tetra_enable_kernel_timing(self._ctx, 1 if on else 0)
 
-    def last_kernel_ms(self) -> float:
-        return float(self._lib.tetra_last_kernel_ms(self._ctx))
+    def kernel_time_ms(self):
+        """(summed device ms, launches) of the fused kernel since the last query (CUDA events on its stream)."""
+        n = C.c_int32(0)
+        ms = float(self._lib.tetra_kernel_time_ms(self._ctx, C.byref(n)))
+        return ms, int(n.value)
 
     def launch_count(self) -> int:
         return int(self._lib.tetra_launch_count(self._ctx))
