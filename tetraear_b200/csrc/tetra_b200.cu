@@ -105,9 +105,9 @@ Plan make_plan(double fs, int64_t n) {
 
 int upload_tables(tetra_ctx* ctx) {
     if (ctx->tables_uploaded) return 0;
-    float fir[132];
+    float fir[128];
     memset(fir, 0, sizeof fir);
-    memcpy(fir, TB_FIR120_TAPS, sizeof(float) * (2 * TB_FIR_H + 1));
+    memcpy(fir + 1, TB_FIR120_TAPS, sizeof(float) * (2 * TB_FIR_H + 1));   // 127 taps behind one zero
     CK(cudaMemcpyToSymbol(c_proto, TB_PROTO_TAPS, sizeof(float) * (2 * TB_PROTO_H + 1)));
     CK(cudaMemcpyToSymbol(c_hb, TB_HB_TAPS, sizeof(float) * (2 * TB_HB_H + 1)));
     CK(cudaMemcpyToSymbol(c_fir, fir, sizeof fir));

@@ -146,37 +146,71 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
         int64_t e_lo = 0, e_hi = tot;
         if (mode == EX_LEFT) e_hi = min(tot, (int64_t)EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
         else if (mode == EX_RIGHT) e_lo = max((int64_t)0, (int64_t)EX_PAD1 + (int64_t)q * m_lo - EX_T1);
-        // Both passes run in groups of EX_U steps: the group's loads are issued together ahead of
-        // the (serially dependent) recursion steps, so memory latency is paid once per group.
-        SosState st;
-        sos_init(st, a.cf, ex_oddext(xat, n, EX_PAD1, e_lo));
-        for (int64_t e = e_lo; e < e_hi; e += EX_U) {
-            double2 in[EX_U];
+        // Both passes run in groups of EX_U steps with the NEXT group's loads in flight while the
+        // current group's (serially dependent) recursion steps execute.
+        double2* __restrict__ scr1 = a.scr1;
+        double2* __restrict__ scrz = a.scrz;
+        auto ld_fwd = [&](double2* g, int64_t e) {
+            if (e >= EX_PAD1 && e + EX_U <= EX_PAD1 + n) {            // group entirely inside the block
 #pragma unroll
-            for (int u = 0; u < EX_U; ++u) in[u] = ex_oddext(xat, n, EX_PAD1, min(e + u, e_hi - 1));
+                for (int u = 0; u < EX_U; ++u) g[u] = xat(e - EX_PAD1 + u);
+            } else {
+#pragma unroll
+                for (int u = 0; u < EX_U; ++u) g[u] = ex_oddext(xat, n, EX_PAD1, min(e + u, e_hi - 1));
+            }
+        };
+        auto st_fwd = [&](SosState& st, const double2* g, int64_t e) {
 #pragma unroll
             for (int u = 0; u < EX_U; ++u) {
-                const double2 v = sos_step(st, a.cf, in[u]);
-                if (e + u < e_hi) a.scr1[(e + u - e_lo) * nj + j] = v;
+                const double2 v = sos_step(st, a.cf, g[u]);
+                if (e + u < e_hi) scr1[(e + u - e_lo) * nj + j] = v;
+            }
+        };
+        SosState st;
+        sos_init(st, a.cf, ex_oddext(xat, n, EX_PAD1, e_lo));
+        {
+            double2 ga[EX_U], gb[EX_U];
+            ld_fwd(ga, e_lo);
+            for (int64_t e = e_lo; e < e_hi; e += 2 * EX_U) {
+                if (e + EX_U < e_hi) ld_fwd(gb, e + EX_U);
+                st_fwd(st, ga, e);
+                if (e + EX_U < e_hi) {
+                    if (e + 2 * EX_U < e_hi) ld_fwd(ga, e + 2 * EX_U);
+                    st_fwd(st, gb, e + EX_U);
+                }
             }
         }
-        sos_init(st, a.cf, a.scr1[(e_hi - 1 - e_lo) * nj + j]);
+        __threadfence_block();
+        sos_init(st, a.cf, scr1[(e_hi - 1 - e_lo) * nj + j]);
         const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);   // >= EX_PAD1: i below is >= 0
         int64_t i = e_hi - 1 - EX_PAD1;                  // input index of the step being produced
         int m = (int)(i / q), r = (int)(i % q);          // i = q*m + r, kept incrementally
-        for (int64_t e = e_hi - 1; e >= e_stop; e -= EX_U) {
-            double2 in[EX_U];
+        auto ld_bwd = [&](double2* g, int64_t e) {
 #pragma unroll
-            for (int u = 0; u < EX_U; ++u) in[u] = a.scr1[(max(e - u, e_stop) - e_lo) * nj + j];
+            for (int u = 0; u < EX_U; ++u) g[u] = scr1[(max(e - u, e_stop) - e_lo) * nj + j];
+        };
+        auto st_bwd = [&](const double2* g, int64_t e) {
 #pragma unroll
             for (int u = 0; u < EX_U; ++u) {
                 if (e - u >= e_stop) {
-                    const double2 v = sos_step(st, a.cf, in[u]);
+                    const double2 v = sos_step(st, a.cf, g[u]);
                     if (r == 0) {
-                        if (i < n && m >= m_lo && m < m_hi) a.scrz[(int64_t)(m - m_lo) * nj + j] = nco(v, m);
+                        if (i < n && m >= m_lo && m < m_hi) scrz[(int64_t)(m - m_lo) * nj + j] = nco(v, m);
                         r = q; --m;
                     }
                     --r; --i;
+                }
+            }
+        };
+        {
+            double2 ga[EX_U], gb[EX_U];
+            ld_bwd(ga, e_hi - 1);
+            for (int64_t e = e_hi - 1; e >= e_stop; e -= 2 * EX_U) {
+                if (e - EX_U >= e_stop) ld_bwd(gb, e - EX_U);
+                st_bwd(ga, e);
+                if (e - EX_U >= e_stop) {
+                    if (e - 2 * EX_U >= e_stop) ld_bwd(ga, e - 2 * EX_U);
+                    st_bwd(gb, e - EX_U);
                 }
             }
         }

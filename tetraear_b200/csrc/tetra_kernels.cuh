@@ -65,48 +65,58 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // K1  channelize_demod_fused  (fast path, fs = 2.4 MS/s, freq_offset = 0)
 // ----------------------------------------------------------------------------------------------
 // One CTA streams one (carrier, segment) through the four FIR stages
-//   A proto /10 -> B half-band /2 -> C fir120 (4 tap quarters) -> D sum + x2 interp + |y|^2 bins
+//   A proto /10 -> B half-band /2 -> C fir120 (129 taps) -> D x2 interp + store + |y|^2 phase sums
 // with every stage working, in the same iteration, on data produced in earlier iterations, so a
 // single __syncthreads per 6400-sample tile is the only block-wide barrier. IQ tiles arrive by
 // 1-D TMA bulk copies into a 3-deep ring, two tiles ahead of the compute.
+//
+// Stage C keeps its accumulators in registers across four iterations: each of its four warps owns
+// every fourth group of 320 outputs and adds one quarter of the 129 taps per iteration (oldest
+// inputs first), so no partial sums ever go through shared memory.
 constexpr int K1_TILE = 6400;             // input samples per iteration
 constexpr int K1_HDR = 40;                // samples of the previous tile kept in front of each buffer
 constexpr int K1_W = K1_TILE / 10;        // 640 w (240 kS/s) samples per iteration
 constexpr int K1_U = K1_TILE / 20;        // 320 u/v (120 kS/s) samples per iteration
 constexpr int K1_NBUF = 3;
-constexpr int K1_WRING = 2048, K1_URING = 1024, K1_VRING = 1024;
+constexpr int K1_WRING = 2048, K1_URING = 2048, K1_VRING = 1024;
 constexpr int K1_THREADS = 384;           // warps 0-3: A, 4-7: C, 8-9: B, 10-11: D
 constexpr int K1_DLANES = 64;
+constexpr int K1_CQ = 4;                  // tap quarters = iterations a C group stays in registers
 // local (stream-origin relative) index ranges produced in iteration i
-constexpr int K1_A0 = -2;                 // w:  [640 i + A0, +640)
-constexpr int K1_B0 = -326;               // u:  [320 i + B0, +320)
-constexpr int K1_C0 = -710;               // vp: [320 i + C0, +320)
-constexpr int K1_D0 = -1038;              // v:  [320 i + D0, +320)  -> y [640 i + 2 D0, +640)
+constexpr int K1_A0 = -2;                 // w: [640 i + A0, +640)
+constexpr int K1_B0 = -326;               // u: [320 i + B0, +320)
+constexpr int K1_C0 = -614;               // v group g: [320 g + C0, +320), finished in iteration g + 3
+constexpr int K1_D0 = -1902;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
 constexpr int K1_PREROLL = 640;           // stream origin = n_lo - PREROLL (w samples)
 constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
 constexpr int K1_NPH = 13;
 
-static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 64 && TB_INT_K == 8, "tables changed: re-derive lags");
+static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K == 8, "tables changed: re-derive lags");
 // dependency checks (each stage only reads what earlier iterations produced)
 static_assert(2 * (K1_B0 + K1_U - 1) + TB_HB_H <= K1_A0 - 1, "B reads w of a later iteration");
-static_assert((K1_C0 + K1_U - 1) + TB_FIR_H <= K1_B0 - 1, "C reads u of a later iteration");
-static_assert((K1_D0 + K1_U - 1) + TB_INT_K <= K1_C0 - 1, "D reads v of a later iteration");
+// quarter q of group g runs in iteration g + q and reads u up to 320 g + C0 + 319 - 64 + 32 q + 31 (+1 for the 129th tap)
+static_assert((K1_C0 + K1_U - 1) - 64 + 31 <= K1_B0 - 1, "C quarter 0 reads u of a later iteration");
+static_assert((K1_C0 + K1_U - 1) - 64 + 32 * 3 + 31 <= 2 * K1_U + K1_B0 + K1_U - 1, "C quarter 3 reads u of a later iteration");
+// D in iteration i reads v up to 320 i + D0 + 319 + 8; finished groups then: g <= i - 4
+static_assert((K1_D0 + K1_U - 1) + TB_INT_K <= -K1_CQ * K1_U + K1_C0 + K1_U - 1, "D reads v of an unfinished group");
 static_assert((K1_A0 + K1_W) - (2 * K1_B0 - TB_HB_H) <= K1_WRING, "w ring too small");
-static_assert((K1_B0 + K1_U) - (K1_C0 - TB_FIR_H) <= K1_URING, "u ring too small");
-static_assert((K1_C0 + K1_U) - (K1_D0 - TB_INT_K) <= K1_VRING, "v ring too small");
+static_assert((3 * K1_U + K1_B0 + K1_U) - (K1_C0 - 64 + 32 * 3) <= K1_URING, "u ring too small");
+static_assert((-3 * K1_U + K1_C0 + K1_U) - (K1_D0 - TB_INT_K) <= K1_VRING, "v ring too small");
+static_assert((K1_C0 % 2) == 0 && (K1_D0 % 2) == 0 && (K1_PREROLL % 2) == 0, "16-byte aligned ring reads need even offsets");
+static_assert((2 * K1_D0) % 2 == 0, "y pairs must start on even samples");
 
 struct K1Smem {
     float2 in[K1_NBUF][K1_HDR + K1_TILE];
     float2 w[K1_WRING];
     float2 u[K1_URING];
-    float2 vp[4][K1_VRING];
+    float2 v[K1_VRING];
     double bins[K1_NPH][K1_DLANES];
     uint64_t full[K1_NBUF];
 };
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
 __constant__ float c_hb[2 * TB_HB_H + 1];
-__constant__ float c_fir[2 * TB_FIR_H + 1 + 3];   // padded to 132 = 4 x 33
+__constant__ float c_fir[128];                    // c_fir[0] = 0, c_fir[1 + k] = fir120 tap k (127 taps): v[n] = sum_k c_fir[k] u[n - 64 + k]
 __constant__ float c_interp[TB_INT_K];
 
 struct K1Args {
@@ -123,8 +133,7 @@ struct K1Args {
 };
 
 // fill one input buffer body with tile k of the stream (global x index gx0 .. gx0+6400)
-__device__ __forceinline__ void k1_issue_tile(K1Smem& s, const K1Args& a, const float2* xc, int64_t gx0, int k,
-                                              int lane, bool full_warp) {
+__device__ __forceinline__ void k1_issue_tile(K1Smem& s, const K1Args& a, const float2* xc, int64_t gx0, int k, int lane) {
     float2* dst = &s.in[k % K1_NBUF][K1_HDR];
     uint64_t* bar = &s.full[k % K1_NBUF];
     const bool inside = (gx0 >= 0) && (gx0 + K1_TILE <= a.n);
@@ -134,17 +143,38 @@ __device__ __forceinline__ void k1_issue_tile(K1Smem& s, const K1Args& a, const 
             tma_load_1d(dst, xc + gx0, K1_TILE * 8, bar);
         }
     } else {
-        // block-edge tile: bounds-checked copy with zero fill (zero extension of the block)
-        if (full_warp) {
-            for (int t = lane; t < K1_TILE; t += 32) {
-                int64_t g = gx0 + t;
-                dst[t] = (g >= 0 && g < a.n) ? __ldg(xc + g) : make_float2(0.f, 0.f);
+        // block-edge tile: bounds-checked copy with zero fill. Samples outside the block never reach
+        // an output this kernel keeps (those are K1_EDGE away from the ends), so the fill value is free.
+        for (int t = lane; t < K1_TILE; t += 32) {
+            int64_t g = gx0 + t;
+            dst[t] = (g >= 0 && g < a.n) ? __ldg(xc + g) : make_float2(0.f, 0.f);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+    }
+}
+
+// one quarter (taps 32 q .. 32 q + 31 of the 128-entry table c_fir) of ten consecutive fir120 outputs;
+// q is warp-uniform, so the taps arrive through uniform constant loads and there is one copy of this code
+__device__ __forceinline__ void k1_fir_quarter(const float2* __restrict__ u, int s0, const float* __restrict__ taps,
+                                               float2 (&acc)[10]) {
+#pragma unroll
+    for (int t2 = 0; t2 < 21; ++t2) {
+        const float4 v = *reinterpret_cast<const float4*>(&u[(s0 + 2 * t2) & (K1_URING - 1)]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * t2 + h;
+            const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const int k = t - r;               // tap index within the quarter
+                if (k >= 0 && k < 32) acc[r] = ffma2(xv, taps[k], acc[r]);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar);
         }
     }
 }
+
+__device__ __forceinline__ void k1_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -159,15 +189,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     const int64_t gx_origin = (int64_t)O * 10;
     // iterations: last y local index needed is (n_hi-1-O); D_i ends at 640 i + 2 D0 + 639
     const int n_iter = (n_hi - 1 - O - 2 * K1_D0 - (K1_W - 1) + K1_W - 1) / K1_W + 1;
-    // tiles that can contain input: local sample index < 10*(n_hi + 200 - O), global < n
-    int n_load = n_iter;
+    // tiles that hold samples of the block: [i_first, n_load); the others are never loaded nor filtered
+    const int i_first = gx_origin >= 0 ? 0 : (int)((-gx_origin) / K1_TILE);
+    const int n_load = (int)min((int64_t)n_iter, (a.n - gx_origin + K1_TILE - 1) / K1_TILE);
     // valid y range written by this CTA (edges belong to the exact kernel)
     const int y_lo = max(n_lo, K1_EDGE), y_hi = min(n_hi, a.L - K1_EDGE);
 
     // ---- prologue: zero rings/bins/headers, init barriers, start the first two tiles ----
     for (int i = tid; i < K1_WRING; i += K1_THREADS) s.w[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_URING; i += K1_THREADS) s.u[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < 4 * K1_VRING; i += K1_THREADS) (&s.vp[0][0])[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_VRING; i += K1_THREADS) s.v[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_NPH * K1_DLANES; i += K1_THREADS) (&s.bins[0][0])[i] = 0.0;
     for (int i = tid; i < K1_NBUF * K1_HDR; i += K1_THREADS) s.in[i / K1_HDR][i % K1_HDR] = make_float2(0.f, 0.f);
     if (tid == 0) {
@@ -176,85 +207,76 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
+    // tile k lives in buffer (k - i_first) % NBUF and completes phase (k - i_first) / NBUF of its barrier
     if (warp == 0) {
-        k1_issue_tile(s, a, xc, gx_origin, 0, lane, true);
-        if (n_load > 1) k1_issue_tile(s, a, xc, gx_origin + K1_TILE, 1, lane, true);
+        if (i_first < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)i_first * K1_TILE, 0, lane);
+        if (i_first + 1 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i_first + 1) * K1_TILE, 1, lane);
     }
 
-    // per-role constants
-    float ctap[33];                                        // role C: this warp's tap quarter
-    if (warp >= 4 && warp < 8) {
-        const int q = warp - 4;
+    // Each role runs its own loop (own loop-carried registers); all of them meet once per iteration at
+    // barrier 0 (bar.sync with the full CTA thread count is well defined from divergent code paths).
+    if (warp < 4) {
+        // ---------------- role A: proto, 5 outputs per lane ----------------
+        for (int i = 0; i < n_iter; ++i) {
+            if (i >= i_first && i < n_load) {
+                const int k = i - i_first;
+                // producer: tile k+2 goes into the buffer tile k-1 just left (its tail is already copied)
+                if (warp == 0 && i + 2 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i + 2) * K1_TILE, k + 2, lane);
+                const int L5 = tid;                            // 0..127
+                mbar_wait(&s.full[k % K1_NBUF], (uint32_t)((k / K1_NBUF) & 1));
+                const float2* buf = &s.in[k % K1_NBUF][0];
+                const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
+                float2 acc[5];
 #pragma unroll
-        for (int k = 0; k < 33; ++k) ctap[k] = c_fir[32 * q + k];   // quarter q uses taps [32q, 32q+32) (+1 for q=3)
-    }
-
-    for (int i = 0; i < n_iter; ++i) {
-        // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
-        if (warp == 0 && i + 2 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i + 2) * K1_TILE, i + 2, lane, true);
-
-        if (warp < 4) {
-            // ---------------- role A: proto, 5 outputs per lane ----------------
-            const int L5 = tid;                            // 0..127
-            mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
-            const float2* buf = &s.in[i % K1_NBUF][0];
-            const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
-            float2 acc[5];
+                for (int g = 0; g < 5; ++g) acc[g] = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int g = 0; g < 5; ++g) acc[g] = make_float2(0.f, 0.f);
+                for (int t2 = 0; t2 < 41; ++t2) {
+                    const float4 v = p4[t2];
 #pragma unroll
-            for (int t2 = 0; t2 < 41; ++t2) {
-                const float4 v = p4[t2];
+                    for (int h = 0; h < 2; ++h) {
+                        const int t = 2 * t2 + h;
+                        const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int t = 2 * t2 + h;
-                    const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-#pragma unroll
-                    for (int g = 0; g < 5; ++g) {
-                        const int d = t - 10 * g;
-                        if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                        for (int g = 0; g < 5; ++g) {
+                            const int d = t - 10 * g;
+                            if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                        }
                     }
                 }
+                const int wbase = K1_W * i + K1_A0 + 5 * L5;
+#pragma unroll
+                for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
+                // tail of this tile -> header of the next buffer
+                if (L5 < K1_HDR) s.in[(k + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
             }
-            const int wbase = K1_W * i + K1_A0 + 5 * L5;
+            k1_bar_sync();
+        }
+    } else if (warp < 8) {
+        // ---------------- role C: fir120, 10 outputs per lane, one tap quarter per iteration ----------------
+        float2 cacc[10];                                    // outputs of the group in flight
 #pragma unroll
-            for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
-            // tail of this tile -> header of the next buffer
-            if (L5 < K1_HDR) s.in[(i + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
-        } else if (warp < 8) {
-            // ---------------- role C: fir120 quarter, 10 outputs per lane ----------------
-            const int q = warp - 4;
-            const int nu0 = K1_U * i + K1_C0 + 10 * lane;   // first output (local u index), even
-            const int s0 = nu0 - TB_FIR_H + 32 * q;         // first input sample, even
-            float2 acc[10];
+        for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
+        for (int i = 0; i < n_iter; ++i) {
+            const int q = (i - (warp - 4)) & 3;             // this warp's group is g = i - q
+            const int nu0 = K1_U * (i - q) + K1_C0 + 10 * lane;   // first output (local v index), even
+            const int s0 = nu0 - 64 + 32 * q;               // first input sample of this quarter, even
+            if (q == 0) {
 #pragma unroll
-            for (int r = 0; r < 10; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int t2 = 0; t2 < 21; ++t2) {
-                const float4 v = *reinterpret_cast<const float4*>(&s.u[(s0 + 2 * t2) & (K1_URING - 1)]);
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int t = 2 * t2 + h;
-                    const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-#pragma unroll
-                    for (int r = 0; r < 10; ++r) {
-                        const int k = t - r;               // tap index within the quarter
-                        if (k >= 0 && k < 32) acc[r] = ffma2(xv, ctap[k], acc[r]);
-                    }
-                }
+                for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
             }
-            if (q == 3) {                                   // 129th tap (k = 32 of the last quarter)
+            k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
+            if (q == 3) {
 #pragma unroll
-                for (int r = 0; r < 10; ++r) {
-                    const float2 xv = s.u[(s0 + 32 + r) & (K1_URING - 1)];
-                    acc[r] = ffma2(xv, ctap[32], acc[r]);
-                }
+                for (int r = 0; r < 10; r += 2)
+                    *reinterpret_cast<float4*>(&s.v[(nu0 + r) & (K1_VRING - 1)]) =
+                        make_float4(cacc[r].x, cacc[r].y, cacc[r + 1].x, cacc[r + 1].y);
             }
-#pragma unroll
-            for (int r = 0; r < 10; ++r) s.vp[q][(nu0 + r) & (K1_VRING - 1)] = acc[r];
-        } else if (warp < 10) {
-            // ---------------- role B: half-band /2, 5 outputs per lane ----------------
-            const int lb = tid - 256;                       // 0..63
+            k1_bar_sync();
+        }
+    } else if (warp < 10) {
+        // ---------------- role B: half-band /2, 5 outputs per lane ----------------
+        const int lb = tid - 256;                           // 0..63
+        for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
             float2 acc[5];
 #pragma unroll
@@ -272,42 +294,67 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
 #pragma unroll
             for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
-        } else {
-            // ---------------- role D: sum quarters, x2 interpolation, store, power bins ----------------
-            const int ld = tid - 320;                       // 0..63
+            k1_bar_sync();
+        }
+    } else {
+        // ---------------- role D: x2 interpolation, store, power sums per timing phase ----------------
+        const int ld = tid - 320;                           // 0..63
+        float2* yc = a.y + (int64_t)car * a.y_pitch;
+        double pacc[K1_NPH];                                // |y|^2 sums, pacc[j] <-> phase (n0 + j) % 13
+#pragma unroll
+        for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
+        for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_D0 + 5 * ld;      // local v index of first output pair
-            float2 v[5 + 2 * TB_INT_K - 1];                 // v[nu0-7 .. nu0+4+8]
+            const int n0 = O + 2 * nu0;                     // global y index of the first output (even)
+            if (n0 + 10 > y_lo && n0 < y_hi) {
+                float2 v[5 + 2 * TB_INT_K - 1];             // v[nu0-7 .. nu0+4+8]
 #pragma unroll
-            for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) {
-                const int idx = (nu0 - (TB_INT_K - 1) + t) & (K1_VRING - 1);
-                v[t] = fadd2(fadd2(s.vp[0][idx], s.vp[1][idx]), fadd2(s.vp[2][idx], s.vp[3][idx]));
-            }
-            float2 yv[10];
+                for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) v[t] = s.v[(nu0 - (TB_INT_K - 1) + t) & (K1_VRING - 1)];
+                float2 yv[10];
 #pragma unroll
-            for (int r = 0; r < 5; ++r) {
-                yv[2 * r] = v[r + TB_INT_K - 1];
-                float2 o = make_float2(0.f, 0.f);
+                for (int r = 0; r < 5; ++r) {
+                    yv[2 * r] = v[r + TB_INT_K - 1];
+                    float2 o = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int k = 0; k < TB_INT_K; ++k)
-                    o = ffma2(fadd2(v[r + TB_INT_K - 1 - k], v[r + TB_INT_K + k]), c_interp[k], o);
-                yv[2 * r + 1] = o;
-            }
-            const int n0 = O + 2 * nu0;                     // global y index of yv[0]
-            float2* yc = a.y + (int64_t)car * a.y_pitch;
+                    for (int k = 0; k < TB_INT_K; ++k)
+                        o = ffma2(fadd2(v[r + TB_INT_K - 1 - k], v[r + TB_INT_K + k]), c_interp[k], o);
+                    yv[2 * r + 1] = o;
+                }
+                if (n0 >= y_lo && n0 + 10 <= y_hi) {        // the common case: all ten inside
 #pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                const int n = n0 + r;
-                if (n >= y_lo && n < y_hi) {
-                    yc[n] = yv[r];
-                    const int ph = n % K1_NPH;
-                    s.bins[ph][ld] += (double)yv[r].x * (double)yv[r].x + (double)yv[r].y * (double)yv[r].y;
+                    for (int r = 0; r < 10; r += 2) {
+                        *reinterpret_cast<float4*>(yc + n0 + r) = make_float4(yv[r].x, yv[r].y, yv[r + 1].x, yv[r + 1].y);
+                        // |y|^2 in fp32 (y itself is fp32), accumulated in fp64; slot r <-> phase (n0 + r) % 13
+                        pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
+                        pacc[r + 1] += (double)fmaf(yv[r + 1].x, yv[r + 1].x, yv[r + 1].y * yv[r + 1].y);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) {
+                        const int n = n0 + r;
+                        if (n >= y_lo && n < y_hi) {
+                            yc[n] = yv[r];
+                            pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
+                        }
+                    }
                 }
             }
+            // next iteration n0 advances by 640 = 3 (mod 13): rotate so that slot j keeps meaning phase (n0 + j) % 13
+            {
+                const double t0 = pacc[0], t1 = pacc[1], t2 = pacc[2];
+#pragma unroll
+                for (int j = 0; j < K1_NPH - 3; ++j) pacc[j] = pacc[j + 3];
+                pacc[10] = t0; pacc[11] = t1; pacc[12] = t2;
+            }
+            k1_bar_sync();
         }
-        __syncthreads();
+        // after n_iter rotations slot j means phase (n0 + j) % 13 with n0 taken for iteration n_iter
+        const int n0e = O + 2 * (K1_U * n_iter + K1_D0 + 5 * ld);
+        const int base = ((n0e % K1_NPH) + K1_NPH) % K1_NPH;
+#pragma unroll
+        for (int j = 0; j < K1_NPH; ++j) s.bins[(base + j) % K1_NPH][ld] = pacc[j];
     }
-
-    // ---- epilogue: reduce the 64 private bin columns ----
+    __syncthreads();
     if (tid < K1_NPH) {
         double t = 0.0;
         for (int j = 0; j < K1_DLANES; ++j) t += s.bins[tid][j];

@@ -31,7 +31,7 @@ B_BUT, A_BUT = signal.butter(4, (25000 / 2) / (FS1 / 2), btype="low")
 PROTO_H = 20      # proto taps -20..20 (41)
 HB_K = 6          # hb: true half-band, centre 0.5 + HB_K odd taps each side (length 4*HB_K-1)
 HB_H = 2 * HB_K - 1
-FIR_H = 64        # fir120 taps -64..64 at 120k (129)
+FIR_H = 63        # fir120 taps -63..63 at 120k (127; the kernel pads to 128 = 4 quarters of 32)
 INT_K = 8         # interp: 2*INT_K taps at half-sample offsets
 
 
