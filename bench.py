@@ -262,6 +262,7 @@ def run_ours(a):
     ms_total = ev0.elapsed_time(ev1)
     launches = sp.launch_count() - l0
     k_total_ms, k_n = sp.kernel_time_ms()                    # the fused kernel's launches INSIDE the timed region
+    phases = sp.last_phase_ms()                              # timeline of the last timed step
     if rank == 0:
         time.sleep(0.3)
     clocks = sampler.stop() if rank == 0 else None
@@ -335,7 +336,8 @@ def run_ours(a):
                          "kernel": "k1_channelize_demod", "kernel_ms": k_avg, "kernel_launches_timed": k_n,
                          "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
-                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES},
+                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES,
+                         "last_step_timeline_ms": {"fused_kernel_and_edge_join": phases[0], "finalize_and_sync": phases[2]}},
             "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity,
         }

@@ -79,6 +79,10 @@ int64_t tetra_launch_count(const tetra_ctx* ctx);
  * *n_launches and resets the record. */
 int tetra_enable_kernel_timing(tetra_ctx* ctx, int on);
 double tetra_kernel_time_ms(tetra_ctx* ctx, int32_t* n_launches);
+/* Timeline of the most recent timed fast-path call, device ms between consecutive marks on the
+ * context's stream: out3[0] call start -> fused kernel done and edge windows joined,
+ * out3[1] (idle), out3[2] timing pick + slicer + TS correlator. */
+int tetra_last_phase_ms(tetra_ctx* ctx, double* out3);
 
 /*
  * Host replay of TetraDecoder.find_sync (core/decoder.py:226-295) over device-computed match

@@ -24,6 +24,7 @@ _SIGS = {
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),
     "tetra_enable_kernel_timing": (C.c_int, [c_ctx_p, C.c_int]),
     "tetra_kernel_time_ms": (C.c_double, [c_ctx_p, C.POINTER(C.c_int32)]),
+    "tetra_last_phase_ms": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tetra_find_sync": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "tetra_sync_cascade": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]),
     "tetra_filter_signal": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),

@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -54,6 +55,8 @@ struct tetra_ctx {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
     bool timing = false;
+    cudaEvent_t ph_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // call start, edges joined, finalize done (debug timeline)
+    bool ph_valid = false;
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
@@ -176,6 +179,33 @@ int launch_exact(tetra_ctx* ctx, cudaStream_t st, ExactArgs a, const std::vector
     return 0;
 }
 
+// LEFT / RIGHT edge windows of the fast path: 8 lanes per job (k_exact_edges)
+int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std::vector<int2>& jobs) {
+    if (jobs.empty()) return 0;
+    int64_t w1 = 1, wz = 1;
+    for (int m = EX_LEFT; m <= EX_RIGHT; ++m) {
+        int64_t a1, az; exact_extents(m, ea.n, ea.L, ea.q, ea.edge, true, &a1, &az);
+        w1 = std::max(w1, a1); wz = std::max(wz, az);
+    }
+    const size_t nj = jobs.size();
+    CK(ctx->scr1.ensure((size_t)w1 * nj * sizeof(double2)));
+    CK(ctx->scrz.ensure((size_t)wz * nj * sizeof(double2)));
+    CK(ctx->scr2.ensure((size_t)(wz + 2 * EX_PAD2) * nj * sizeof(double2)));
+    CK(ctx->jobs.ensure(nj * sizeof(int2)));
+    CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
+    EdgeArgs g;
+    g.x = ea.x32; g.pitch = ea.pitch; g.n = ea.n; g.q = ea.q; g.L = ea.L; g.edge = ea.edge; g.cf = ea.cf;
+    g.y = ea.y32; g.y_pitch = ea.y_pitch; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
+    g.scr1 = (double2*)ctx->scr1.p; g.scrz = (double2*)ctx->scrz.p; g.scr2 = (double2*)ctx->scr2.p;
+    g.w1 = w1; g.wz = wz;
+    const int jobs_per_block = EXL_THREADS / EXL_TEAM;
+    k_exact_edges<<<(int)((nj + jobs_per_block - 1) / jobs_per_block), EXL_THREADS, 0, st>>>(g);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+
 }  // namespace
 
 extern "C" {
@@ -197,7 +227,7 @@ int tetra_create(tetra_ctx** out, int device, double sample_rate) {
     ctx->sample_rate = sample_rate;
     if ((e = cudaSetDevice(device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithPriority(&ctx->side, cudaStreamNonBlocking, -1)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming)) != cudaSuccess ||
         (e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming)) != cudaSuccess) {
         fail(nullptr, TETRA_E_CUDA, "tetra_create: %s", cudaGetErrorString(e));
@@ -219,6 +249,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (int k = 0; k < 4; ++k) if (ctx->ph_ev[k]) cudaEventDestroy(ctx->ph_ev[k]);
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->side);
     delete ctx;
 }
@@ -268,6 +299,18 @@ double tetra_kernel_time_ms(tetra_ctx* ctx, int32_t* n_launches) {
     if (n_launches) *n_launches = (int32_t)ctx->ev_used;
     ctx->ev_used = 0;
     return total;
+}
+
+int tetra_last_phase_ms(tetra_ctx* ctx, double* out3) {
+    if (!ctx || !out3) return TETRA_E_INVALID;
+    if (!ctx->ph_valid) return fail(ctx, TETRA_E_INVALID, "no timed fast-path call yet");
+    CK(cudaEventSynchronize(ctx->ph_ev[3]));
+    for (int k = 0; k < 3; ++k) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ph_ev[k], ctx->ph_ev[k + 1]));
+        out3[k] = ms;
+    }
+    return TETRA_OK;
 }
 
 int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
@@ -375,9 +418,16 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
         // edge windows run beside the bulk kernel on the side stream
+        if (ctx->timing) {
+            if (!ctx->ph_ev[0]) for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&ctx->ph_ev[k]));
+            CK(cudaEventRecord(ctx->ph_ev[0], st));
+        }
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        // 8 lanes per job (short critical path) unless TETRA_EDGE_MODE=2 asks for the thread-per-job kernel
+        static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
+        if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
         cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -396,6 +446,7 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
     } else {
@@ -403,16 +454,20 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         if (rc) return rc;
         fa.partial = nullptr; fa.n_seg = 0; fa.bulk_lo = 0; fa.bulk_hi = 0;
     }
+    if (ctx->timing && use_fast && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[2], st));
+    const bool fused_match = ts_match && cap > 0 && cap <= FIN_DIB_SMEM;
+    fa.match = fused_match ? k_match : nullptr;
     k_finalize<<<C, FIN_THREADS, 0, st>>>(fa);
     ctx->launches++;
     CK(cudaGetLastError());
-    if (ts_match && cap > 0) {
+    if (ts_match && cap > 0 && !fused_match) {
         SyncArgs sa; sa.dibits = k_dib; sa.cap = cap; sa.n_dibits = k_nd; sa.match = k_match;
         const int gx = (int)std::min<int64_t>(64, (2 * cap + 255) / 256);
         k_sync_match<<<dim3(std::max(gx, 1), C), 256, 0, st>>>(sa);
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    if (ctx->timing && use_fast && ctx->ph_ev[0]) { CK(cudaEventRecord(ctx->ph_ev[3], st)); ctx->ph_valid = true; }
     // ---- results to host buffers ----
     if (dibits && !d_dib) CK(cudaMemcpyAsync(dibits, k_dib, (size_t)C * cap, cudaMemcpyDeviceToHost, st));
     if (!d_nd) CK(cudaMemcpyAsync(n_dibits, k_nd, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));

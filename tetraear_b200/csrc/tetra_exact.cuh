@@ -12,7 +12,7 @@ namespace tetra {
 
 constexpr int EX_PAD1 = 27;   // sosfiltfilt: 3 * (2*n_sections + 1), n_sections = 4
 constexpr int EX_PAD2 = 15;   // filtfilt: 3 * max(len(a), len(b)) = 3 * 5
-constexpr int EX_T1 = 1280;   // warm-up of an approximate start/end, stage 1 (pole radius 0.9821 -> 8e-11)
+constexpr int EX_T1 = 1024;   // warm-up of an approximate start/end, stage 1 (pole radius 0.9821 -> 9e-9)
 constexpr int EX_T2 = 160;    // same for stage 2 (pole radius 0.8837 -> 3e-9)
 constexpr int EX_U = 8;       // recursion steps per load group
 
@@ -264,10 +264,221 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// k_exact_edges: the same recursions for the LEFT / RIGHT edge windows of the fast path, spread over
+// 8 lanes per job: lane (k, c) owns biquad section k of the Chebyshev cascade for component c
+// (re / im are independent real filters). The sections form a systolic chain: lane k works on
+// sample s - 2k at step s and receives section k-1's output by warp shuffle two steps after it
+// was produced, so the only serial dependency per step is one section's own z0 -> y recurrence
+// (2 DFMA) instead of the whole 4-section cascade plus a global-memory round trip.
+// Scratch is job-major: the 8 lanes of a job read and write 64 contiguous bytes.
+// ----------------------------------------------------------------------------------------------
+constexpr int EXL_TEAM = 8;
+constexpr int EXL_THREADS = 128;          // 16 jobs per block
+constexpr int EXL_BLK = 32;               // steps per unrolled block (one block of input prefetched ahead)
+
+struct EdgeArgs {
+    const float2* x;         // [C][pitch] complex64
+    int64_t pitch, n;
+    int32_t q, L, edge;
+    ExactCoef cf;
+    float2* y;               // [C][y_pitch]
+    int64_t y_pitch;
+    const int2* jobs;        // (carrier, mode), mode in {EX_LEFT, EX_RIGHT}
+    int32_t n_jobs;
+    double2* scr1;           // [n_jobs][w1] forward stage-1 output
+    double2* scrz;           // [n_jobs][wz] stage-1 result
+    double2* scr2;           // [n_jobs][wz + 2 PAD2] forward stage-2 output
+    int64_t w1, wz;
+};
+
+__global__ void __launch_bounds__(EXL_THREADS, 5) k_exact_edges(const EdgeArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int t = lane & (EXL_TEAM - 1), team_base = lane & ~(EXL_TEAM - 1);
+    const int k = t >> 1, c = t & 1;                     // section, component
+    int j = (blockIdx.x * EXL_THREADS + threadIdx.x) / EXL_TEAM;
+    const bool live = j < a.n_jobs;                      // dead teams follow along (shuffles) but never store
+    if (!live) j = a.n_jobs - 1;
+    const int car = a.jobs[j].x, mode = a.jobs[j].y;
+    const float* xc = reinterpret_cast<const float*>(a.x + (int64_t)car * a.pitch);
+    const int L = a.L, E = a.edge, q = a.q;
+    const int64_t n = a.n;
+    int m_lo = 0, m_hi = L, o_lo = 0, o_hi = L;
+    if (mode == EX_LEFT) { o_hi = min(L, E); m_hi = min(L, E + EX_T2); }
+    else { o_lo = max(0, L - E); m_lo = max(0, L - E - 2 * EX_T2); }
+    const int64_t tot = n + 2 * EX_PAD1;
+    int64_t e_lo = 0, e_hi = tot;
+    if (mode == EX_LEFT) e_hi = min(tot, (int64_t)EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
+    else e_lo = max((int64_t)0, (int64_t)EX_PAD1 + (int64_t)q * m_lo - EX_T1);
+    const int nf = (int)(e_hi - e_lo);
+    double* s1 = reinterpret_cast<double*>(a.scr1 + (int64_t)j * a.w1);      // [nf][2]
+    double* sz = reinterpret_cast<double*>(a.scrz + (int64_t)j * a.wz);      // [m_hi - m_lo][2]
+    double* s2 = reinterpret_cast<double*>(a.scr2 + (int64_t)j * (a.wz + 2 * EX_PAD2));
+
+    // component cc of the odd-extended input at extended index e (scipy odd_ext, evaluated in double)
+    auto xext = [&](int64_t e, int cc) -> double {
+        const int64_t i = e - EX_PAD1;
+        if (i < 0) return 2.0 * (double)__ldg(xc + cc) - (double)__ldg(xc + 2 * (-i) + cc);
+        if (i >= n) return 2.0 * (double)__ldg(xc + 2 * (n - 1) + cc) - (double)__ldg(xc + 2 * (2 * (n - 1) - i) + cc);
+        return (double)__ldg(xc + 2 * i + cc);
+    };
+    const double b0 = a.cf.sos[k][0], b1 = a.cf.sos[k][1], b2 = a.cf.sos[k][2], a1 = a.cf.sos[k][4], a2 = a.cf.sos[k][5];
+    const double zi0 = a.cf.zi1[k][0], zi1 = a.cf.zi1[k][1];
+    const int src_prev = lane - 2;                       // lane holding section k-1 of the same component
+
+    // Both passes advance in blocks of EXL_BLK steps, fully unrolled and branch-free. The 8 lanes of a job act as
+    // loaders: lane t keeps component (t & 1) of sample 4 g + (t >> 1), g = 0..EXL_BLK/4-1, of the block, fetched RAW
+    // one block ahead (`fetch`) and turned into the filter input only when the block starts (`cook`), so no
+    // instruction waits on a load it has just issued. Section-0 lanes pull their sample by shuffle one step early.
+    double y_last, in_next, hx_next, z0, z1;
+    auto run_pass = [&](int n_steps, double zinit0, double zinit1, auto&& fetch, auto&& cook, auto&& emit) {
+        double hc[EXL_BLK / 4];
+        decltype(fetch(0, 0)) hn[EXL_BLK / 4];
+#pragma unroll
+        for (int g = 0; g < EXL_BLK / 4; ++g) hn[g] = fetch(4 * g + (t >> 1), t & 1);
+#pragma unroll
+        for (int g = 0; g < EXL_BLK / 4; ++g) hc[g] = cook(hn[g], 4 * g + (t >> 1), t & 1);
+        y_last = 0.0; in_next = 0.0; z0 = zinit0; z1 = zinit1;
+        hx_next = __shfl_sync(0xffffffffu, hc[0], team_base + c);          // sample 0
+        // the four jobs of a warp may have windows of different length: every lane runs the longest
+        // one (the shuffles below need the whole warp); steps beyond a job's own range are predicated off
+        int n_loop = n_steps;
+#pragma unroll
+        for (int o = 16; o >= EXL_TEAM; o >>= 1) n_loop = max(n_loop, __shfl_xor_sync(0xffffffffu, n_loop, o));
+        for (int sb = 0; sb < n_loop + 6; sb += EXL_BLK) {
+#pragma unroll
+            for (int g = 0; g < EXL_BLK / 4; ++g) hn[g] = fetch(sb + EXL_BLK + 4 * g + (t >> 1), t & 1);
+#pragma unroll
+            for (int u = 0; u < EXL_BLK; ++u) {
+                const int s = sb + u;
+                const double in_cur = in_next;
+                in_next = __shfl_sync(0xffffffffu, y_last, src_prev);      // consumed at step s + 1
+                const double hx_cur = hx_next;
+                if (u + 1 < EXL_BLK) {
+                    hx_next = __shfl_sync(0xffffffffu, hc[(u + 1) >> 2], team_base + 2 * ((u + 1) & 3) + c);
+                } else {                                                   // sample s + 1 opens the next block
+#pragma unroll
+                    for (int g = 0; g < EXL_BLK / 4; ++g) hc[g] = cook(hn[g], sb + EXL_BLK + 4 * g + (t >> 1), t & 1);
+                    hx_next = __shfl_sync(0xffffffffu, hc[0], team_base + c);
+                }
+                const int idx = s - 2 * k;                                 // sample this section works on
+                const double X = k == 0 ? hx_cur : in_cur;
+                // a section starts from its steady state when its first sample arrives; what it does before
+                // (idx < 0) or after its range never reaches a kept output
+                const double s0 = idx == 0 ? zinit0 : z0, s1v = idx == 0 ? zinit1 : z1;
+                const double tz = b1 * X + s1v;                            // off the recurrence
+                const double yv = b0 * X + s0;
+                z0 = tz - a1 * yv;
+                z1 = b2 * X - a2 * yv;
+                y_last = yv;
+                emit(idx, yv, k == 3 && (unsigned)idx < (unsigned)n_steps);
+            }
+        }
+    };
+
+    // ---------------- stage 1, forward: f = sosfilt(ext[e_lo .. e_hi)) ----------------
+    {
+        const double x0 = xext(e_lo, c);
+        const double edge_lo = (double)__ldg(xc + (t & 1)), edge_hi = (double)__ldg(xc + 2 * (n - 1) + (t & 1));
+        // sample np of the pass <-> extended index e = e_lo + np <-> input index i = e - PAD1, reflected at the ends
+        run_pass(nf, zi0 * x0, zi1 * x0,
+                 [&](int np, int cc) -> float {
+                     const int64_t i = e_lo + min(np, nf - 1) - EX_PAD1;
+                     const int64_t ir = i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
+                     return __ldg(xc + 2 * ir + cc);
+                 },
+                 [&](float raw, int np, int cc) -> double {
+                     const int64_t i = e_lo + min(np, nf - 1) - EX_PAD1;
+                     return i < 0 ? 2.0 * edge_lo - (double)raw : (i >= n ? 2.0 * edge_hi - (double)raw : (double)raw);
+                 },
+                 [&](int idx, double yv, bool on) { if (on && live) s1[2 * (int64_t)idx + c] = yv; });
+    }
+    __syncwarp();
+    // ---------------- stage 1, backward over the forward output, keep every q-th ----------------
+    {
+        const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);
+        const int nb = (int)(e_hi - e_stop);             // steps n' = 0 .. nb-1 <-> e = e_hi - 1 - n'
+        const double x0 = s1[2 * (int64_t)(nf - 1) + c];
+        // decimation bookkeeping (used by the last section only): i = e - PAD1 = q m + r
+        const int64_t i0 = e_hi - 1 - EX_PAD1;
+        int m = (int)(i0 / q), r = (int)(i0 % q);
+        run_pass(nb, zi0 * x0, zi1 * x0,
+                 [&](int np, int cc) -> double { return s1[2 * (int64_t)(nf - 1 - min(np, nb - 1)) + cc]; },
+                 [&](double raw, int, int) -> double { return raw; },
+                 [&](int idx, double yv, bool on) {
+                     const bool hit = on && r == 0;
+                     if (hit && live && (int64_t)q * m < n && m >= m_lo && m < m_hi) sz[2 * (int64_t)(m - m_lo) + c] = yv;
+                     m -= hit ? 1 : 0;
+                     r = hit ? q - 1 : r - (on ? 1 : 0);
+                 });
+    }
+    __syncwarp();
+    // ---------------- stage 2: filtfilt(b, a) on z, two lanes (re, im) per job ----------------
+    if (k == 0) {
+        auto zat = [&](int64_t mm) { return sz[2 * (mm - m_lo) + c]; };
+        auto z2 = [&](int64_t e) -> double {             // odd extension around the true block ends
+            const int64_t i = e - EX_PAD2;
+            if (i < 0) return 2.0 * zat(0) - zat(-i);
+            if (i >= L) return 2.0 * zat(L - 1) - zat(2 * ((int64_t)L - 1) - i);
+            return zat(i);
+        };
+        const int64_t tot2 = (int64_t)L + 2 * EX_PAD2;
+        int64_t f_lo = 0, f_hi = tot2;
+        if (mode == EX_LEFT) f_hi = min(tot2, (int64_t)EX_PAD2 + m_hi);
+        else f_lo = (int64_t)EX_PAD2 + m_lo;
+        const double* cb = a.cf.b; const double* ca = a.cf.a;
+        double z[4] = {0.0, 0.0, 0.0, 0.0};
+        auto step = [&](double X) {
+            const double yv = cb[0] * X + z[0];
+            z[0] = cb[1] * X - ca[1] * yv + z[1];
+            z[1] = cb[2] * X - ca[2] * yv + z[2];
+            z[2] = cb[3] * X - ca[3] * yv + z[3];
+            z[3] = cb[4] * X - ca[4] * yv;
+            return yv;
+        };
+        {
+            const double x0 = z2(f_lo);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = a.cf.zi2[u] * x0;
+        }
+        for (int64_t e = f_lo; e < f_hi; e += EX_U) {
+            double g[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) g[u] = z2(min(e + u, f_hi - 1));
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                const double yv = step(g[u]);
+                if (e + u < f_hi && live) s2[2 * (e + u - f_lo) + c] = yv;
+            }
+        }
+        {
+            const double x0 = s2[2 * (f_hi - 1 - f_lo) + c];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) z[u] = a.cf.zi2[u] * x0;
+        }
+        const int64_t f_stop = (int64_t)EX_PAD2 + o_lo;
+        float* yc = reinterpret_cast<float*>(a.y + (int64_t)car * a.y_pitch);
+        for (int64_t e = f_hi - 1; e >= f_stop; e -= EX_U) {
+            double g[EX_U];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) g[u] = s2[2 * (max(e - u, f_stop) - f_lo) + c];
+#pragma unroll
+            for (int u = 0; u < EX_U; ++u) {
+                if (e - u >= f_stop) {
+                    const double yv = step(g[u]);
+                    const int64_t mm = e - u - EX_PAD2;
+                    if (live && mm >= o_lo && mm < o_hi) yc[2 * mm + c] = (float)yv;
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // K_finalize: timing pick (processor.py:189-215) + soft symbols + differential slicer (:129-163)
 // ----------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 constexpr int FIN_MAXPH = 32;
+constexpr int FIN_B = 8;                  // symbols per thread and batch in k_finalize
 
 struct FinArgs {
     const float2* y;         // [C][y_pitch] filtered samples at the decimated rate
@@ -283,47 +494,76 @@ struct FinArgs {
     float2* symbols;         // [C][cap+1] or null
     int32_t* best_phase;     // [C] or null
     int32_t* phase_scratch;  // [C] always written (used by later kernels)
+    uint8_t* match;          // [C][2*cap][2] or null: TS1/TS2 agreement counts, fused when cap <= FIN_DIB_SMEM
 };
 
+constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22 (decoder.py:196-197)
+constexpr uint32_t TS2_BITS = 0x1E90DCu;   // 0111101001000011011100                      (decoder.py:198-199)
+constexpr int FIN_DIB_SMEM = 12288;         // dibits of one carrier kept in shared memory for the fused correlator
+
+// processor.py:152-161 on the differential product d = s1 * conj(s0) without the arctangent:
+//   ph < -5pi/8 -> 3, < -3pi/8 -> 2, < 3pi/8 -> 0, < 5pi/8 -> 1, else 3,   ph = atan2(im, re) in (-pi, pi].
+// With k = tan(3pi/8) the four rays are im = +-k re (re > 0: +-3pi/8) and im = -+k re (re < 0: +-5pi/8).
+__device__ __forceinline__ uint8_t slice_dqpsk(double re, double im) {
+    const double k = 2.414213562373095048801688724209698;   // 1 + sqrt(2)
+    const double kr = k * re;
+    if (re > 0.0) {
+        if (im < -kr) return 2;              // ph < -3pi/8 (and > -pi/2)
+        return im < kr ? 0 : 1;              // [-3pi/8, 3pi/8) -> 0, [3pi/8, pi/2) -> 1
+    }
+    // re <= 0: ph in [pi/2, pi] (im >= 0) or [-pi, -pi/2] (im < 0); -kr >= 0
+    if (im > 0.0 || (im == 0.0 && re == 0.0)) {
+        if (re == 0.0 && im == 0.0) return 0;   // atan2(0, 0) = 0
+        return im > -kr ? 1 : 3;             // ph < 5pi/8  <=>  im > k |re|
+    }
+    if (im == 0.0) return 3;                 // ph = pi
+    return im <= kr ? 2 : 3;                 // ph >= -5pi/8  <=>  -im >= k |re|  <=>  im <= k re
+}
+
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
-    __shared__ double red[FIN_MAXPH][FIN_THREADS / 32];
+    __shared__ double red[FIN_THREADS];
     __shared__ int s_best;
+    __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
+    __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
     const int car = blockIdx.x, tid = threadIdx.x;
-    const float2* y = a.y + (int64_t)car * a.y_pitch;
+    const float2* __restrict__ y = a.y + (int64_t)car * a.y_pitch;
     const int L = a.L, sps = a.sps, step = a.step;
-    const int nph = (sps + step - 1) / step;            // phases tried: 0, step, 2 step, ...
+    const int nph = (sps + step - 1) / step;            // phases tried: 0, step, 2 step, ... (<= FIN_MAXPH)
     int best = 0;
     if (sps > 1) {
-        // power sums over n = ph + sps*k, k < (L - ph) / sps  <=>  n + sps <= L
-        double acc[FIN_MAXPH];
-#pragma unroll
-        for (int p = 0; p < FIN_MAXPH; ++p) acc[p] = 0.0;
-        const int n_end = L - sps;                       // last admissible n (inclusive)
-        for (int n = tid; n <= n_end; n += FIN_THREADS) {
-            if (n >= a.bulk_lo && n < a.bulk_hi) continue;
-            const int ph = n % sps;
-            if (ph % step) continue;
-            const float2 v = y[n];
-            const double pw = (double)v.x * (double)v.x + (double)v.y * (double)v.y;
-            const int slot = ph / step;
-#pragma unroll
-            for (int p = 0; p < FIN_MAXPH; ++p) if (p == slot) acc[p] += pw;
+        // Power sum of phase ph over n = ph + sps*k, k < cnt = (L - ph) / sps. Thread (g, p) = (tid / nph, tid % nph)
+        // owns the symbols k = g (mod G) of phase p; samples inside [bulk_lo, bulk_hi) were already summed by the
+        // fused kernel and are skipped.
+        const int G = FIN_THREADS / nph;
+        const int g = tid / nph, p = tid % nph;
+        const bool has_bulk = a.bulk_lo < a.bulk_hi;
+        double acc = 0.0;
+        if (g < G) {
+            const int ph = p * step;
+            const int cnt = (L - ph) / sps;
+            // k < k_lo_end: below the bulk; k >= k_hi_beg: above it
+            const int k_lo_end = has_bulk ? min(cnt, max(0, (a.bulk_lo - ph + sps - 1) / sps)) : cnt;
+            const int k_hi_beg = has_bulk ? max(k_lo_end, (a.bulk_hi - ph + sps - 1) / sps) : cnt;
+            for (int k = g; k < k_lo_end; k += G) {
+                const float2 v = y[ph + sps * k];
+                acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            }
+            for (int k = k_hi_beg + g; k < cnt; k += G) {
+                const float2 v = y[ph + sps * k];
+                acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            }
         }
-        for (int p = 0; p < nph; ++p) {
-            double v = acc[p];
-            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if ((tid & 31) == 0) red[p][tid >> 5] = v;
-        }
+        red[tid] = acc;
         __syncthreads();
         if (tid == 0) {
             double best_pow = -1.0;
-            for (int p = 0; p < nph; ++p) {
-                const int ph = p * step;
+            for (int pp = 0; pp < nph; ++pp) {
+                const int ph = pp * step;
                 const int cnt = (L - ph) / sps;
                 if (cnt <= 0) continue;
                 double sum = 0.0;
-                for (int w = 0; w < FIN_THREADS / 32; ++w) sum += red[p][w];
-                if (a.partial && a.bulk_lo < a.bulk_hi)
+                for (int gg = 0; gg < G; ++gg) sum += red[gg * nph + pp];
+                if (a.partial && has_bulk)
                     for (int sg = 0; sg < a.n_seg; ++sg) sum += a.partial[((int64_t)car * a.n_seg + sg) * 16 + ph];
                 const double mean = sum / (double)cnt;
                 if (mean > best_pow) { best_pow = mean; best = ph; }
@@ -335,27 +575,70 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     }
     const int stride = sps > 1 ? sps : 1;
     const int n_sym = sps > 1 ? max(0, (L - best) / sps) : L;
+    const int nd = n_sym > 1 ? n_sym - 1 : 0;
     if (tid == 0) {
-        a.n_dibits[car] = n_sym > 1 ? n_sym - 1 : 0;
+        a.n_dibits[car] = nd;
         if (a.best_phase) a.best_phase[car] = best;
         a.phase_scratch[car] = best;
     }
     uint8_t* dib = a.dibits + (int64_t)car * a.cap;
     float2* sym = a.symbols ? a.symbols + (int64_t)car * (a.cap + 1) : nullptr;
-    const double T3 = 3.0 * M_PI / 8.0, T5 = 5.0 * M_PI / 8.0;
-    for (int k = tid; k < n_sym; k += FIN_THREADS) {
-        const float2 s1 = y[best + (int64_t)stride * k];
-        if (sym) sym[k] = s1;
-        if (k >= 1) {
-            const float2 s0 = y[best + (int64_t)stride * (k - 1)];
-            // diff = s1 * conj(s0)
-            const double re = (double)s1.x * s0.x + (double)s1.y * s0.y;
-            const double im = (double)s1.y * s0.x - (double)s1.x * s0.y;
-            const double ph = atan2(im, re);
-            uint8_t d;
-            if (ph < -T5) d = 3; else if (ph < -T3) d = 2; else if (ph < T3) d = 0; else if (ph < T5) d = 1; else d = 3;
-            dib[k - 1] = d;
+    const bool fuse = a.match != nullptr && nd <= FIN_DIB_SMEM;
+    // symbols k = tid + 256 j, FIN_B of them per batch with all loads of a batch issued before any use
+    const float2* ys = y + best;
+    for (int k0 = tid; k0 < n_sym; k0 += FIN_B * FIN_THREADS) {
+        float2 s1[FIN_B], s0[FIN_B];
+#pragma unroll
+        for (int j = 0; j < FIN_B; ++j) {
+            const int k = min(k0 + j * FIN_THREADS, n_sym - 1);
+            s1[j] = ys[(int64_t)stride * k];
+            s0[j] = ys[(int64_t)stride * max(k - 1, 0)];
         }
+#pragma unroll
+        for (int j = 0; j < FIN_B; ++j) {
+            const int k = k0 + j * FIN_THREADS;
+            if (k < n_sym) {
+                if (sym) sym[k] = s1[j];
+                if (k >= 1) {
+                    // diff = s1 * conj(s0); the products of two floats are exact in double
+                    const double re = (double)s1[j].x * s0[j].x + (double)s1[j].y * s0[j].y;
+                    const double im = (double)s1[j].y * s0[j].x - (double)s1[j].x * s0[j].y;
+                    const uint8_t d = slice_dqpsk(re, im);
+                    dib[k - 1] = d;
+                    if (fuse) s_dib[k - 1] = d;
+                }
+            }
+        }
+    }
+    if (!fuse) return;
+    // ---- fused frame-sync correlator (decoder.py:140-169 bit expansion, :237-240 agreement counts) ----
+    __syncthreads();
+    const int n_words = (nd + 15) / 16 + 1;             // 16 dibits = 32 bits per word, first bit = MSB; one zero word behind
+    for (int j = tid; j < n_words; j += FIN_THREADS) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int idx = 16 * j + m;
+            w = (w << 2) | (idx < nd ? (uint32_t)(s_dib[idx] & 3u) : 0u);
+        }
+        s_bits[j] = w;
+    }
+    __syncthreads();
+    const int nw = 2 * nd - 22 + 1;                     // window starts (decoder.py:232)
+    uint8_t* out = a.match + (int64_t)car * a.cap * 4;
+    for (int p = tid; 2 * p < nw; p += FIN_THREADS) {   // windows 2p and 2p+1 share their words
+        const int i = 2 * p;
+        const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
+        const int sh = i & 31;                          // even, <= 30: 23 bits starting at sh fit in 64
+        const uint32_t w0 = (uint32_t)(two >> (64 - 22 - sh)) & 0x3FFFFFu;
+        const uint32_t w1 = (uint32_t)(two >> (64 - 23 - sh)) & 0x3FFFFFu;
+        uchar4 o;
+        o.x = (uint8_t)(22 - __popc(w0 ^ TS1_BITS));
+        o.y = (uint8_t)(22 - __popc(w0 ^ TS2_BITS));
+        o.z = (uint8_t)(22 - __popc(w1 ^ TS1_BITS));
+        o.w = (uint8_t)(22 - __popc(w1 ^ TS2_BITS));
+        if (i + 1 < nw) *reinterpret_cast<uchar4*>(out + 2 * (int64_t)i) = o;
+        else { out[2 * (int64_t)i] = o.x; out[2 * (int64_t)i + 1] = o.y; }
     }
 }
 
@@ -363,9 +646,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
 // K_sync: dibits -> bits (decoder.py:140-169) and 22-bit TS1/TS2 agreement at every bit offset
 // (decoder.py:237-240). One thread per window start.
 // ----------------------------------------------------------------------------------------------
-constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22
-constexpr uint32_t TS2_BITS = 0x1E90DCu;   // 0111101001000011011100
-
 struct SyncArgs {
     const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
     uint8_t* match;          // [C][2*cap][2]

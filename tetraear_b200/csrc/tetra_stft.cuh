@@ -155,15 +155,12 @@ __global__ void k_maxabs_c128(const double2* x, int64_t n, unsigned long long* o
 // demodulate_dqpsk (processor.py:127-163)
 __global__ void k_slice_c128(const double2* x, int64_t n, const double* maxabs, uint8_t* out) {
     const double mx = *maxabs;
-    const double T3 = 3.0 * M_PI / 8.0, T5 = 5.0 * M_PI / 8.0;
     for (int64_t i = 1 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double2 s1 = x[i], s0 = x[i - 1];
         if (mx > 0) { s1.x /= mx; s1.y /= mx; s0.x /= mx; s0.y /= mx; }
         const double re = s1.x * s0.x + s1.y * s0.y;
         const double im = s1.y * s0.x - s1.x * s0.y;
-        const double ph = atan2(im, re);
-        uint8_t d;
-        if (ph < -T5) d = 3; else if (ph < -T3) d = 2; else if (ph < T3) d = 0; else if (ph < T5) d = 1; else d = 3;
+        const uint8_t d = slice_dqpsk(re, im);
         out[i - 1] = d;
     }
 }

@@ -229,6 +229,12 @@ class SignalProcessor:
         ms = float(self._lib.tetra_kernel_time_ms(self._ctx, C.byref(n)))
         return ms, int(n.value)
 
+    def last_phase_ms(self):
+        """Device ms of the last timed fast-path call: [fused kernel + edge join, gap, finalize]."""
+        out = np.zeros(3, dtype=np.float64)
+        self._check(self._lib.tetra_last_phase_ms(self._ctx, out.ctypes.data), "last_phase_ms")
+        return out.tolist()
+
     def launch_count(self) -> int:
         return int(self._lib.tetra_launch_count(self._ctx))
 
