@@ -179,7 +179,7 @@ int launch_exact(tetra_ctx* ctx, cudaStream_t st, ExactArgs a, const std::vector
     return 0;
 }
 
-// LEFT / RIGHT edge windows of the fast path: 8 lanes per job (k_exact_edges)
+// LEFT / RIGHT edge windows of the fast path: one thread per job, time-skewed biquad sections (k_exact_edges)
 int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std::vector<int2>& jobs) {
     if (jobs.empty()) return 0;
     int64_t w1 = 1, wz = 1;
@@ -198,8 +198,7 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
     g.y = ea.y32; g.y_pitch = ea.y_pitch; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
     g.scr1 = (double2*)ctx->scr1.p; g.scrz = (double2*)ctx->scrz.p; g.scr2 = (double2*)ctx->scr2.p;
     g.w1 = w1; g.wz = wz;
-    const int jobs_per_block = EXL_THREADS / EXL_TEAM;
-    k_exact_edges<<<(int)((nj + jobs_per_block - 1) / jobs_per_block), EXL_THREADS, 0, st>>>(g);
+    k_exact_edges<<<(int)((nj + EXT_THREADS - 1) / EXT_THREADS), EXT_THREADS, 0, st>>>(g);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -424,7 +423,7 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         }
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        // 8 lanes per job (short critical path) unless TETRA_EDGE_MODE=2 asks for the thread-per-job kernel
+        // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
         static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
         if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
         else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);

@@ -264,17 +264,17 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
 }
 
 // ----------------------------------------------------------------------------------------------
-// k_exact_edges: the same recursions for the LEFT / RIGHT edge windows of the fast path, spread over
-// 8 lanes per job: lane (k, c) owns biquad section k of the Chebyshev cascade for component c
-// (re / im are independent real filters). The sections form a systolic chain: lane k works on
-// sample s - 2k at step s and receives section k-1's output by warp shuffle two steps after it
-// was produced, so the only serial dependency per step is one section's own z0 -> y recurrence
-// (2 DFMA) instead of the whole 4-section cascade plus a global-memory round trip.
-// Scratch is job-major: the 8 lanes of a job read and write 64 contiguous bytes.
+// k_exact_edges: the same recursions for the LEFT / RIGHT edge windows of the fast path, one
+// thread per job, with the four biquad sections of the Chebyshev cascade SKEWED in time: at step
+// s section k works on sample s - k and takes section k-1's output of the previous step from a
+// register. The 4 sections x (re, im) of a step are then independent of each other, so the
+// serial dependency per step is one section's own z0 -> y recurrence (2 DFMA) with 40 DFMA of
+// independent work to fill the pipe, instead of a chain through the whole cascade.
+// Input / scratch are read one block of steps ahead into registers. Scratch is job-major.
 // ----------------------------------------------------------------------------------------------
-constexpr int EXL_TEAM = 8;
-constexpr int EXL_THREADS = 128;          // 16 jobs per block
-constexpr int EXL_BLK = 32;               // steps per unrolled block (one block of input prefetched ahead)
+constexpr int EXT_THREADS = 64;
+constexpr int EXT_FB = 16;                // forward steps per prefetched block (float2 each)
+constexpr int EXT_BB = 8;                 // backward steps per prefetched block (double2 each)
 
 struct EdgeArgs {
     const float2* x;         // [C][pitch] complex64
@@ -291,15 +291,51 @@ struct EdgeArgs {
     int64_t w1, wz;
 };
 
-__global__ void __launch_bounds__(EXL_THREADS, 5) k_exact_edges(const EdgeArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int t = lane & (EXL_TEAM - 1), team_base = lane & ~(EXL_TEAM - 1);
-    const int k = t >> 1, c = t & 1;                     // section, component
-    int j = (blockIdx.x * EXL_THREADS + threadIdx.x) / EXL_TEAM;
-    const bool live = j < a.n_jobs;                      // dead teams follow along (shuffles) but never store
-    if (!live) j = a.n_jobs - 1;
+struct SkewState {
+    double z0[4][2], z1[4][2];            // biquad states [section][re, im]
+    double yl[4][2];                      // each section's output of the previous step
+};
+
+// section k on input (xr, xi); scipy _sosfilt order of operations
+__device__ __forceinline__ void skew_section(const ExactCoef& c, SkewState& st, int k, double xr, double xi) {
+    const double b0 = c.sos[k][0], b1 = c.sos[k][1], b2 = c.sos[k][2], a1 = c.sos[k][4], a2 = c.sos[k][5];
+    const double yr = b0 * xr + st.z0[k][0], yi = b0 * xi + st.z0[k][1];
+    st.z0[k][0] = (b1 * xr + st.z1[k][0]) - a1 * yr;
+    st.z0[k][1] = (b1 * xi + st.z1[k][1]) - a1 * yi;
+    st.z1[k][0] = b2 * xr - a2 * yr;
+    st.z1[k][1] = b2 * xi - a2 * yi;
+    st.yl[k][0] = yr; st.yl[k][1] = yi;
+}
+// all four sections active: descending k so that yl[k-1] still holds the previous step's output
+__device__ __forceinline__ void skew_step_all(const ExactCoef& c, SkewState& st, double xr, double xi) {
+    skew_section(c, st, 3, st.yl[2][0], st.yl[2][1]);
+    skew_section(c, st, 2, st.yl[1][0], st.yl[1][1]);
+    skew_section(c, st, 1, st.yl[0][0], st.yl[0][1]);
+    skew_section(c, st, 0, xr, xi);
+}
+// sections k_lo..k_hi only (pipeline fill / drain)
+__device__ __forceinline__ void skew_step_some(const ExactCoef& c, SkewState& st, double xr, double xi, int k_lo, int k_hi) {
+#pragma unroll
+    for (int k = 3; k >= 0; --k) {
+        if (k < k_lo || k > k_hi) continue;
+        if (k == 0) skew_section(c, st, 0, xr, xi);
+        else skew_section(c, st, k, st.yl[k - 1][0], st.yl[k - 1][1]);
+    }
+}
+__device__ __forceinline__ void skew_init(const ExactCoef& c, SkewState& st, double2 x0) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        st.z0[k][0] = c.zi1[k][0] * x0.x; st.z0[k][1] = c.zi1[k][0] * x0.y;
+        st.z1[k][0] = c.zi1[k][1] * x0.x; st.z1[k][1] = c.zi1[k][1] * x0.y;
+        st.yl[k][0] = st.yl[k][1] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(EXT_THREADS) k_exact_edges(const EdgeArgs a) {
+    const int j = blockIdx.x * EXT_THREADS + threadIdx.x;
+    if (j >= a.n_jobs) return;
     const int car = a.jobs[j].x, mode = a.jobs[j].y;
-    const float* xc = reinterpret_cast<const float*>(a.x + (int64_t)car * a.pitch);
+    const float2* __restrict__ xc = a.x + (int64_t)car * a.pitch;
     const int L = a.L, E = a.edge, q = a.q;
     const int64_t n = a.n;
     int m_lo = 0, m_hi = L, o_lo = 0, o_hi = L;
@@ -310,163 +346,127 @@ __global__ void __launch_bounds__(EXL_THREADS, 5) k_exact_edges(const EdgeArgs a
     if (mode == EX_LEFT) e_hi = min(tot, (int64_t)EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
     else e_lo = max((int64_t)0, (int64_t)EX_PAD1 + (int64_t)q * m_lo - EX_T1);
     const int nf = (int)(e_hi - e_lo);
-    double* s1 = reinterpret_cast<double*>(a.scr1 + (int64_t)j * a.w1);      // [nf][2]
-    double* sz = reinterpret_cast<double*>(a.scrz + (int64_t)j * a.wz);      // [m_hi - m_lo][2]
-    double* s2 = reinterpret_cast<double*>(a.scr2 + (int64_t)j * (a.wz + 2 * EX_PAD2));
+    double2* __restrict__ s1 = a.scr1 + (int64_t)j * a.w1;      // [nf]
+    double2* __restrict__ sz = a.scrz + (int64_t)j * a.wz;      // [m_hi - m_lo]
+    double2* __restrict__ s2 = a.scr2 + (int64_t)j * (a.wz + 2 * EX_PAD2);
 
-    // component cc of the odd-extended input at extended index e (scipy odd_ext, evaluated in double)
-    auto xext = [&](int64_t e, int cc) -> double {
-        const int64_t i = e - EX_PAD1;
-        if (i < 0) return 2.0 * (double)__ldg(xc + cc) - (double)__ldg(xc + 2 * (-i) + cc);
-        if (i >= n) return 2.0 * (double)__ldg(xc + 2 * (n - 1) + cc) - (double)__ldg(xc + 2 * (2 * (n - 1) - i) + cc);
-        return (double)__ldg(xc + 2 * i + cc);
-    };
-    const double b0 = a.cf.sos[k][0], b1 = a.cf.sos[k][1], b2 = a.cf.sos[k][2], a1 = a.cf.sos[k][4], a2 = a.cf.sos[k][5];
-    const double zi0 = a.cf.zi1[k][0], zi1 = a.cf.zi1[k][1];
-    const int src_prev = lane - 2;                       // lane holding section k-1 of the same component
+    auto xat = [&](int64_t i) { const float2 v = __ldg(xc + i); return make_double2((double)v.x, (double)v.y); };
+    SkewState st;
 
-    // Both passes advance in blocks of EXL_BLK steps, fully unrolled and branch-free. The 8 lanes of a job act as
-    // loaders: lane t keeps component (t & 1) of sample 4 g + (t >> 1), g = 0..EXL_BLK/4-1, of the block, fetched RAW
-    // one block ahead (`fetch`) and turned into the filter input only when the block starts (`cook`), so no
-    // instruction waits on a load it has just issued. Section-0 lanes pull their sample by shuffle one step early.
-    double y_last, in_next, hx_next, z0, z1;
-    auto run_pass = [&](int n_steps, double zinit0, double zinit1, auto&& fetch, auto&& cook, auto&& emit) {
-        double hc[EXL_BLK / 4];
-        decltype(fetch(0, 0)) hn[EXL_BLK / 4];
+    // ---------------- stage 1, forward: f = sosfilt(ext[e_lo .. e_hi)), sample s <-> e = e_lo + s ----------------
+    {
+        skew_init(a.cf, st, ex_oddext(xat, n, EX_PAD1, e_lo));
+        auto slow = [&](int s) {                          // any step: pads, pipeline fill and drain
+            const int k_lo = max(0, s - nf + 1), k_hi = min(3, s);
+            double2 X = make_double2(0.0, 0.0);
+            if (k_lo == 0) X = ex_oddext(xat, n, EX_PAD1, e_lo + s);
+            skew_step_some(a.cf, st, X.x, X.y, k_lo, k_hi);
+            if (k_hi == 3) s1[s - 3] = make_double2(st.yl[3][0], st.yl[3][1]);
+        };
+        int s = 0;
+        while (s < nf + 3 && (s < 3 || e_lo + s < EX_PAD1)) { slow(s); ++s; }
+        const int fast_end = (int)min((int64_t)nf, (int64_t)EX_PAD1 + n - e_lo);   // samples below lie inside the block
+        if (s + EXT_FB <= fast_end) {
+            float2 cur[EXT_FB], nxt[EXT_FB];
+            const float2* p = xc + (e_lo + s - EX_PAD1);
 #pragma unroll
-        for (int g = 0; g < EXL_BLK / 4; ++g) hn[g] = fetch(4 * g + (t >> 1), t & 1);
+            for (int u = 0; u < EXT_FB; ++u) cur[u] = __ldg(p + u);
+            while (s + EXT_FB <= fast_end) {
+                const bool more = s + 2 * EXT_FB <= fast_end;
+                const float2* pn = p + (more ? EXT_FB : 0);
 #pragma unroll
-        for (int g = 0; g < EXL_BLK / 4; ++g) hc[g] = cook(hn[g], 4 * g + (t >> 1), t & 1);
-        y_last = 0.0; in_next = 0.0; z0 = zinit0; z1 = zinit1;
-        hx_next = __shfl_sync(0xffffffffu, hc[0], team_base + c);          // sample 0
-        // the four jobs of a warp may have windows of different length: every lane runs the longest
-        // one (the shuffles below need the whole warp); steps beyond a job's own range are predicated off
-        int n_loop = n_steps;
+                for (int u = 0; u < EXT_FB; ++u) nxt[u] = __ldg(pn + u);
 #pragma unroll
-        for (int o = 16; o >= EXL_TEAM; o >>= 1) n_loop = max(n_loop, __shfl_xor_sync(0xffffffffu, n_loop, o));
-        for (int sb = 0; sb < n_loop + 6; sb += EXL_BLK) {
-#pragma unroll
-            for (int g = 0; g < EXL_BLK / 4; ++g) hn[g] = fetch(sb + EXL_BLK + 4 * g + (t >> 1), t & 1);
-#pragma unroll
-            for (int u = 0; u < EXL_BLK; ++u) {
-                const int s = sb + u;
-                const double in_cur = in_next;
-                in_next = __shfl_sync(0xffffffffu, y_last, src_prev);      // consumed at step s + 1
-                const double hx_cur = hx_next;
-                if (u + 1 < EXL_BLK) {
-                    hx_next = __shfl_sync(0xffffffffu, hc[(u + 1) >> 2], team_base + 2 * ((u + 1) & 3) + c);
-                } else {                                                   // sample s + 1 opens the next block
-#pragma unroll
-                    for (int g = 0; g < EXL_BLK / 4; ++g) hc[g] = cook(hn[g], sb + EXL_BLK + 4 * g + (t >> 1), t & 1);
-                    hx_next = __shfl_sync(0xffffffffu, hc[0], team_base + c);
+                for (int u = 0; u < EXT_FB; ++u) {
+                    skew_step_all(a.cf, st, (double)cur[u].x, (double)cur[u].y);
+                    s1[s + u - 3] = make_double2(st.yl[3][0], st.yl[3][1]);
                 }
-                const int idx = s - 2 * k;                                 // sample this section works on
-                const double X = k == 0 ? hx_cur : in_cur;
-                // a section starts from its steady state when its first sample arrives; what it does before
-                // (idx < 0) or after its range never reaches a kept output
-                const double s0 = idx == 0 ? zinit0 : z0, s1v = idx == 0 ? zinit1 : z1;
-                const double tz = b1 * X + s1v;                            // off the recurrence
-                const double yv = b0 * X + s0;
-                z0 = tz - a1 * yv;
-                z1 = b2 * X - a2 * yv;
-                y_last = yv;
-                emit(idx, yv, k == 3 && (unsigned)idx < (unsigned)n_steps);
+#pragma unroll
+                for (int u = 0; u < EXT_FB; ++u) cur[u] = nxt[u];
+                s += EXT_FB; p += EXT_FB;
             }
         }
-    };
-
-    // ---------------- stage 1, forward: f = sosfilt(ext[e_lo .. e_hi)) ----------------
-    {
-        const double x0 = xext(e_lo, c);
-        const double edge_lo = (double)__ldg(xc + (t & 1)), edge_hi = (double)__ldg(xc + 2 * (n - 1) + (t & 1));
-        // sample np of the pass <-> extended index e = e_lo + np <-> input index i = e - PAD1, reflected at the ends
-        run_pass(nf, zi0 * x0, zi1 * x0,
-                 [&](int np, int cc) -> float {
-                     const int64_t i = e_lo + min(np, nf - 1) - EX_PAD1;
-                     const int64_t ir = i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);
-                     return __ldg(xc + 2 * ir + cc);
-                 },
-                 [&](float raw, int np, int cc) -> double {
-                     const int64_t i = e_lo + min(np, nf - 1) - EX_PAD1;
-                     return i < 0 ? 2.0 * edge_lo - (double)raw : (i >= n ? 2.0 * edge_hi - (double)raw : (double)raw);
-                 },
-                 [&](int idx, double yv, bool on) { if (on && live) s1[2 * (int64_t)idx + c] = yv; });
+        while (s < nf + 3) { slow(s); ++s; }
     }
-    __syncwarp();
-    // ---------------- stage 1, backward over the forward output, keep every q-th ----------------
+    // ---------------- stage 1, backward over the forward output (step s <-> e = e_hi - 1 - s), keep every q-th ----------------
     {
-        const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);
-        const int nb = (int)(e_hi - e_stop);             // steps n' = 0 .. nb-1 <-> e = e_hi - 1 - n'
-        const double x0 = s1[2 * (int64_t)(nf - 1) + c];
-        // decimation bookkeeping (used by the last section only): i = e - PAD1 = q m + r
+        const int64_t e_stop = max(e_lo, (int64_t)EX_PAD1 + (int64_t)q * m_lo);   // >= PAD1
+        const int nb = (int)(e_hi - e_stop);
+        skew_init(a.cf, st, s1[nf - 1]);
+        // decimation bookkeeping of the emitted samples: input index i = e - PAD1 = q m + r
         const int64_t i0 = e_hi - 1 - EX_PAD1;
         int m = (int)(i0 / q), r = (int)(i0 % q);
-        run_pass(nb, zi0 * x0, zi1 * x0,
-                 [&](int np, int cc) -> double { return s1[2 * (int64_t)(nf - 1 - min(np, nb - 1)) + cc]; },
-                 [&](double raw, int, int) -> double { return raw; },
-                 [&](int idx, double yv, bool on) {
-                     const bool hit = on && r == 0;
-                     if (hit && live && (int64_t)q * m < n && m >= m_lo && m < m_hi) sz[2 * (int64_t)(m - m_lo) + c] = yv;
-                     m -= hit ? 1 : 0;
-                     r = hit ? q - 1 : r - (on ? 1 : 0);
-                 });
-    }
-    __syncwarp();
-    // ---------------- stage 2: filtfilt(b, a) on z, two lanes (re, im) per job ----------------
-    if (k == 0) {
-        auto zat = [&](int64_t mm) { return sz[2 * (mm - m_lo) + c]; };
-        auto z2 = [&](int64_t e) -> double {             // odd extension around the true block ends
-            const int64_t i = e - EX_PAD2;
-            if (i < 0) return 2.0 * zat(0) - zat(-i);
-            if (i >= L) return 2.0 * zat(L - 1) - zat(2 * ((int64_t)L - 1) - i);
-            return zat(i);
+        auto emit = [&]() {
+            if (r == 0) {
+                if ((int64_t)q * m < n && m >= m_lo && m < m_hi) sz[m - m_lo] = make_double2(st.yl[3][0], st.yl[3][1]);
+                r = q; --m;
+            }
+            --r;
         };
+        auto slow = [&](int s) {
+            const int k_lo = max(0, s - nb + 1), k_hi = min(3, s);
+            double2 X = make_double2(0.0, 0.0);
+            if (k_lo == 0) X = s1[nf - 1 - s];
+            skew_step_some(a.cf, st, X.x, X.y, k_lo, k_hi);
+            if (k_hi == 3) emit();
+        };
+        int s = 0;
+        while (s < nb + 3 && s < 3) { slow(s); ++s; }
+        if (s + EXT_BB <= nb) {
+            double2 cur[EXT_BB], nxt[EXT_BB];
+            const double2* p = s1 + (nf - 1 - s);
+#pragma unroll
+            for (int u = 0; u < EXT_BB; ++u) cur[u] = p[-u];
+            while (s + EXT_BB <= nb) {
+                const bool more = s + 2 * EXT_BB <= nb;
+                const double2* pn = p - (more ? EXT_BB : 0);
+#pragma unroll
+                for (int u = 0; u < EXT_BB; ++u) nxt[u] = pn[-u];
+#pragma unroll
+                for (int u = 0; u < EXT_BB; ++u) {
+                    skew_step_all(a.cf, st, cur[u].x, cur[u].y);
+                    emit();
+                }
+#pragma unroll
+                for (int u = 0; u < EXT_BB; ++u) cur[u] = nxt[u];
+                s += EXT_BB; p -= EXT_BB;
+            }
+        }
+        while (s < nb + 3) { slow(s); ++s; }
+    }
+    // ---------------- stage 2: filtfilt(b, a) on z ----------------
+    {
+        auto zat = [&](int64_t mm) { return sz[mm - m_lo]; };
+        auto z2 = [&](int64_t e) { return ex_oddext(zat, (int64_t)L, EX_PAD2, e); };   // folds around the true block ends
         const int64_t tot2 = (int64_t)L + 2 * EX_PAD2;
         int64_t f_lo = 0, f_hi = tot2;
         if (mode == EX_LEFT) f_hi = min(tot2, (int64_t)EX_PAD2 + m_hi);
         else f_lo = (int64_t)EX_PAD2 + m_lo;
-        const double* cb = a.cf.b; const double* ca = a.cf.a;
-        double z[4] = {0.0, 0.0, 0.0, 0.0};
-        auto step = [&](double X) {
-            const double yv = cb[0] * X + z[0];
-            z[0] = cb[1] * X - ca[1] * yv + z[1];
-            z[1] = cb[2] * X - ca[2] * yv + z[2];
-            z[2] = cb[3] * X - ca[3] * yv + z[3];
-            z[3] = cb[4] * X - ca[4] * yv;
-            return yv;
-        };
-        {
-            const double x0 = z2(f_lo);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) z[u] = a.cf.zi2[u] * x0;
-        }
+        BaState bs;
+        ba_init(bs, a.cf, z2(f_lo));
         for (int64_t e = f_lo; e < f_hi; e += EX_U) {
-            double g[EX_U];
+            double2 g[EX_U];
 #pragma unroll
             for (int u = 0; u < EX_U; ++u) g[u] = z2(min(e + u, f_hi - 1));
 #pragma unroll
             for (int u = 0; u < EX_U; ++u) {
-                const double yv = step(g[u]);
-                if (e + u < f_hi && live) s2[2 * (e + u - f_lo) + c] = yv;
+                const double2 v = ba_step(bs, a.cf, g[u]);
+                if (e + u < f_hi) s2[e + u - f_lo] = v;
             }
         }
-        {
-            const double x0 = s2[2 * (f_hi - 1 - f_lo) + c];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) z[u] = a.cf.zi2[u] * x0;
-        }
+        ba_init(bs, a.cf, s2[f_hi - 1 - f_lo]);
         const int64_t f_stop = (int64_t)EX_PAD2 + o_lo;
-        float* yc = reinterpret_cast<float*>(a.y + (int64_t)car * a.y_pitch);
+        float2* yc = a.y + (int64_t)car * a.y_pitch;
         for (int64_t e = f_hi - 1; e >= f_stop; e -= EX_U) {
-            double g[EX_U];
+            double2 g[EX_U];
 #pragma unroll
-            for (int u = 0; u < EX_U; ++u) g[u] = s2[2 * (max(e - u, f_stop) - f_lo) + c];
+            for (int u = 0; u < EX_U; ++u) g[u] = s2[max(e - u, f_stop) - f_lo];
 #pragma unroll
             for (int u = 0; u < EX_U; ++u) {
                 if (e - u >= f_stop) {
-                    const double yv = step(g[u]);
+                    const double2 v = ba_step(bs, a.cf, g[u]);
                     const int64_t mm = e - u - EX_PAD2;
-                    if (live && mm >= o_lo && mm < o_hi) yc[2 * mm + c] = (float)yv;
+                    if (mm >= o_lo && mm < o_hi) yc[mm] = make_float2((float)v.x, (float)v.y);
                 }
             }
         }
