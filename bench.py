@@ -162,7 +162,7 @@ def run_reference(a):
     v = cores * reps * steps * N_SAMPLES / wall / 1e6
     sample = (f"{steps} steps x {cores} processes x {reps} carrier-blocks x 2^20 samples "
               f"(process + symbols_to_bits + TS1/TS2 match counts), {wall:.1f} s")
-    print(json.dumps({
+    a.out.write(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "MS/s", "n_gpus": a.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": 1e3 * wall / steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -171,7 +171,8 @@ def run_reference(a):
         "cpu_baseline": {"value": v, "unit": "MS/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }) + "\n")
+    a.out.flush()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -211,13 +212,13 @@ def run_ours(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    from tetraear_b200 import shard
     total = a.carriers
-    assert total % world == 0
-    n_local = total // world
+    first_carrier, n_local = shard.partition(total, world, rank)
     sp = SignalProcessor(2.4e6, device=local)
     cap = sp.dibit_capacity(N_SAMPLES)
 
-    x, base = make_inputs(torch, dev, n_local, rank * n_local)
+    x, base = make_inputs(torch, dev, n_local, first_carrier)
     dib = torch.zeros((n_local, cap), dtype=torch.uint8, device=dev)
     nd = torch.zeros(n_local, dtype=torch.int32, device=dev)
     sym = torch.zeros((n_local, cap + 1, 2), dtype=torch.float32, device=dev)
@@ -234,8 +235,7 @@ def run_ours(a):
         sp.process_batch_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
                                 sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream)
         if world > 1:
-            dist.all_gather_into_tensor(all_dib, dib)
-            dist.all_gather_into_tensor(all_nd, nd)
+            shard.gather_dibits(dib, nd, total, all_dib, all_nd)      # one NCCL all-gather per tensor
 
     torch.cuda.synchronize()
     with torch.cuda.stream(work):
@@ -243,12 +243,12 @@ def run_ours(a):
             step()
         torch.cuda.synchronize()
         sp.kernel_time_ms()                                  # drop the warm-up launches from the record
-        if world > 1:
-            dist.barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
             time.sleep(0.5)
+        if world > 1:
+            dist.barrier()                                   # every rank enters the timed region together
         l0 = sp.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
@@ -266,10 +266,7 @@ def run_ours(a):
     if rank == 0:
         time.sleep(0.3)
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = shard.max_over_ranks(ms_total, dev)
     ms_step = ms_total / a.steps
     value = total * N_SAMPLES / (ms_step * 1e-3) / 1e6
 
@@ -303,10 +300,7 @@ def run_ours(a):
     for _ in range(reps):
         r0 = sp.process_batch(hx_np, None, want_symbols=False, want_match=False)
     dt = (time.perf_counter() - t0) / reps
-    te = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    dt = float(te.item())
+    dt = shard.max_over_ranks(dt, dev)
     e2e = {"value": world * ce * N_SAMPLES / dt / 1e6, "unit": "MS/s",
            "h2d_bytes_per_step": int(ce * N_SAMPLES * 8), "d2h_bytes_per_step": int(ce * (cap + 8)),
            "carriers_per_rank": ce, "timed": "host wall clock around SignalProcessor.process_batch, max over ranks",
@@ -341,10 +335,20 @@ def run_ours(a):
             "cpu_baseline": cpu,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity,
         }
-        print(json.dumps(out))
+        a.out.write(json.dumps(out) + "\n")
+        a.out.flush()
     if world > 1:
         dist.destroy_process_group()
     sp.close()
+
+
+def _claim_stdout():
+    """Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout. Point fd 1
+    at stderr for the run and return a writer bound to the real stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
@@ -359,6 +363,7 @@ def main():
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the fused kernel from an ncu --set full capture (profiles/), if known")
     a = ap.parse_args()
+    a.out = _claim_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -1,0 +1,85 @@
+"""Carrier sharding over ranks (one process per GPU) and the one collective of the path.
+
+Every (carrier, block) is independent in the reference (``SignalProcessor.process`` keeps no state
+across calls, tetraear/signal/processor.py:221-273; one processor per capture device,
+tetraear/ui/modern.py:1879), so carriers are block-partitioned over the ranks, each rank demodulates
+only its own IQ, and the decoded dibit streams are exchanged once with an all-gather so that every rank
+can run the host-side ``TetraDecoder`` on all carriers (BASELINE.json north_star).
+
+torch.distributed is plumbing here (NCCL over NVLink on the GPU box, gloo in the CPU tests); nothing in
+this module computes.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition(n_carriers: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """(first carrier, number of carriers) owned by `rank`: contiguous blocks, the first
+    ``n_carriers % world_size`` ranks hold one carrier more."""
+    if world_size <= 0 or not 0 <= rank < world_size or n_carriers < 0:
+        raise ValueError("bad partition arguments")
+    base, extra = divmod(n_carriers, world_size)
+    count = base + (1 if rank < extra else 0)
+    first = rank * base + min(rank, extra)
+    return first, count
+
+
+def owner_of(carrier: int, n_carriers: int, world_size: int) -> int:
+    """Rank that owns `carrier` under `partition`."""
+    base, extra = divmod(n_carriers, world_size)
+    split = extra * (base + 1)
+    if carrier < split:
+        return carrier // (base + 1)
+    return extra + (carrier - split) // max(base, 1)
+
+
+def gather_dibits(dibits: torch.Tensor, n_dibits: torch.Tensor, n_carriers: int,
+                  out_dibits: Optional[torch.Tensor] = None, out_n: Optional[torch.Tensor] = None,
+                  group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-gather the fixed-stride dibit streams ``[c_local, cap]`` uint8 and their lengths ``[c_local]``
+    int32 of every rank into ``[n_carriers, cap]`` / ``[n_carriers]`` on every rank (carrier order = rank
+    order = global carrier index). With an even partition this is one ``all_gather_into_tensor`` per
+    tensor (NCCL: a single ncclAllGather); a ragged partition pads every rank to the largest shard."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return dibits, n_dibits
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    first, count = partition(n_carriers, world, rank)
+    if dibits.shape[0] != count or n_dibits.shape[0] != count:
+        raise ValueError(f"rank {rank} holds {dibits.shape[0]} carriers, partition says {count}")
+    cap = dibits.shape[1]
+    if out_dibits is None:
+        out_dibits = torch.empty((n_carriers, cap), dtype=dibits.dtype, device=dibits.device)
+    if out_n is None:
+        out_n = torch.empty((n_carriers,), dtype=n_dibits.dtype, device=n_dibits.device)
+    if n_carriers % world == 0:
+        dist.all_gather_into_tensor(out_dibits, dibits.contiguous(), group=group)
+        dist.all_gather_into_tensor(out_n, n_dibits.contiguous(), group=group)
+        return out_dibits, out_n
+    biggest = partition(n_carriers, world, 0)[1]
+    pad_d = torch.zeros((biggest, cap), dtype=dibits.dtype, device=dibits.device)
+    pad_n = torch.zeros((biggest,), dtype=n_dibits.dtype, device=n_dibits.device)
+    pad_d[:count] = dibits
+    pad_n[:count] = n_dibits
+    all_d = torch.empty((world * biggest, cap), dtype=dibits.dtype, device=dibits.device)
+    all_n = torch.empty((world * biggest,), dtype=n_dibits.dtype, device=n_dibits.device)
+    dist.all_gather_into_tensor(all_d, pad_d, group=group)
+    dist.all_gather_into_tensor(all_n, pad_n, group=group)
+    for r in range(world):
+        f, c = partition(n_carriers, world, r)
+        out_dibits[f:f + c] = all_d[r * biggest: r * biggest + c]
+        out_n[f:f + c] = all_n[r * biggest: r * biggest + c]
+    return out_dibits, out_n
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Max of a per-rank scalar (the timing rule: a multi-GPU step takes as long as its slowest rank)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
