@@ -24,6 +24,7 @@
 #include "tetra_stft.cuh"
 
 using namespace tetra;
+static_assert(K1_EDGE == K_EDGE, "edge width of the fused and the exact kernels must agree");
 
 namespace {
 
@@ -60,7 +61,8 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats;
+    std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
 
@@ -205,6 +207,94 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
 }
 
 
+// ---- zero-input chunk transitions for k_exact_edges_warp (see tetra_exact.cuh) ----
+template <int DIM>
+void mat_mul(const double* a, const double* b, double* c) {
+    for (int i = 0; i < DIM; ++i)
+        for (int j = 0; j < DIM; ++j) {
+            double t = 0.0;
+            for (int k = 0; k < DIM; ++k) t += a[i * DIM + k] * b[k * DIM + j];
+            c[i * DIM + j] = t;
+        }
+}
+// out[5][64]: M^(2^r), M = zero-input evolution of the 4-biquad cascade state (z0_0, z1_0, ...) over `steps` samples
+void sos_transition_powers(const ExactCoef& cf, int steps, double* out) {
+    double m[64];
+    for (int col = 0; col < 8; ++col) {
+        double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        z[col] = 1.0;
+        for (int t = 0; t < steps; ++t) {
+            double x = 0.0;
+            for (int k = 0; k < 4; ++k) {
+                const double y = cf.sos[k][0] * x + z[2 * k];
+                z[2 * k] = cf.sos[k][1] * x - cf.sos[k][4] * y + z[2 * k + 1];
+                z[2 * k + 1] = cf.sos[k][2] * x - cf.sos[k][5] * y;
+                x = y;
+            }
+        }
+        for (int i = 0; i < 8; ++i) m[i * 8 + col] = z[i];
+    }
+    memcpy(out, m, sizeof m);
+    for (int r = 1; r < 5; ++r) mat_mul<8>(out + (r - 1) * 64, out + (r - 1) * 64, out + r * 64);
+}
+void ba_transition_powers(const ExactCoef& cf, int steps, double* out) {
+    double m[16];
+    for (int col = 0; col < 4; ++col) {
+        double z[4] = {0, 0, 0, 0};
+        z[col] = 1.0;
+        for (int t = 0; t < steps; ++t) {
+            const double y = z[0];
+            for (int k = 0; k < 3; ++k) z[k] = -cf.a[k + 1] * y + z[k + 1];
+            z[3] = -cf.a[4] * y;
+        }
+        for (int i = 0; i < 4; ++i) m[i * 4 + col] = z[i];
+    }
+    memcpy(out, m, sizeof m);
+    for (int r = 1; r < 5; ++r) mat_mul<4>(out + (r - 1) * 16, out + (r - 1) * 16, out + r * 16);
+}
+
+// small batches: one warp per edge job, chunk-parallel recursion (k_exact_edges_warp)
+int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std::vector<int2>& jobs) {
+    if (jobs.empty()) return 0;
+    int64_t w1 = 1, wz = 1;
+    for (int m = EX_LEFT; m <= EX_RIGHT; ++m) {
+        int64_t a1, az; exact_extents(m, ea.n, ea.L, ea.q, ea.edge, true, &a1, &az);
+        w1 = std::max(w1, a1); wz = std::max(wz, az);
+    }
+    const size_t nj = jobs.size();
+    CK(ctx->scr1.ensure((size_t)w1 * nj * sizeof(double2)));
+    CK(ctx->scrz.ensure((size_t)wz * nj * sizeof(double2)));
+    CK(ctx->scr2.ensure((size_t)(wz + 2 * EX_PAD2) * nj * sizeof(double2)));
+    CK(ctx->jobs.ensure(nj * sizeof(int2)));
+    CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
+    // transitions for the four (mode, direction) variants of each stage
+    ctx->edge_mats.assign(4 * 5 * 64 + 4 * 5 * 16, 0.0);
+    for (int m = EX_LEFT; m <= EX_RIGHT; ++m) {
+        const EdgeRange rg = edge_range(m, ea.n, ea.L, ea.q, ea.edge);
+        const int var = m == EX_LEFT ? 0 : 2;
+        const int nf = (int)(rg.e_hi - rg.e_lo), nb = (int)(rg.e_hi - rg.e_stop);
+        const int n2 = (int)(rg.f_hi - rg.f_lo), nb2 = (int)(rg.f_hi - rg.f_stop);
+        if (n2 > 32 * EXW_S2MAX || nb2 > 32 * EXW_S2MAX) return fail(ctx, TETRA_E_UNSUPPORTED, "edge window too long for the warp kernel");
+        sos_transition_powers(ea.cf, (nf + 31) / 32, ctx->edge_mats.data() + (var + 0) * 5 * 64);
+        sos_transition_powers(ea.cf, (nb + 31) / 32, ctx->edge_mats.data() + (var + 1) * 5 * 64);
+        ba_transition_powers(ea.cf, (n2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 0) * 5 * 16);
+        ba_transition_powers(ea.cf, (nb2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 1) * 5 * 16);
+    }
+    CK(ctx->mats.ensure(ctx->edge_mats.size() * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->mats.p, ctx->edge_mats.data(), ctx->edge_mats.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    EdgeWarpArgs g;
+    g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
+    g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
+    g.e.scr1 = (double2*)ctx->scr1.p; g.e.scrz = (double2*)ctx->scrz.p; g.e.scr2 = (double2*)ctx->scr2.p;
+    g.e.w1 = w1; g.e.wz = wz;
+    g.m1 = (const double*)ctx->mats.p;
+    g.m2 = (const double*)ctx->mats.p + 4 * 5 * 64;
+    k_exact_edges_warp<<<(int)nj, 32, 0, st>>>(g);          // one warp = one job = one block: fits beside the fused kernel's CTA
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -244,7 +334,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -425,7 +515,9 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
         // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
         static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
+        // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
         if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
         else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
         if (rc) return rc;
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
