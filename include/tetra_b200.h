@@ -71,6 +71,17 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int
                         uint8_t* dibits, int64_t cap, int32_t* n_dibits,
                         float* symbols, int32_t* best_phase, uint8_t* ts_match, int32_t async);
 
+/*
+ * BASELINE config 3 -- C channels out of ONE wideband capture: for every channel centre f_c (Hz, relative
+ * to the capture centre) the composition  process(frequency_shift(iq, f_c, sample_rate), 0)  of the
+ * reference's own methods (signal/processor.py:85-100 and :221-273). The reference has no channelizer; its
+ * scanner retunes the hardware in 25 kHz steps instead (signal/scanner.py:383-445).
+ *   iq [n_samples] complex64, host or device; channel_hz host [C]; outputs as in tetra_process_batch.
+ */
+int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t n_samples, const double* channel_hz,
+                           int32_t n_channels, uint8_t* dibits, int64_t cap, int32_t* n_dibits,
+                           float* symbols, int32_t* best_phase, uint8_t* ts_match);
+
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches). */
 int64_t tetra_launch_count(const tetra_ctx* ctx);
 /* With timing enabled every fused channelize+demod kernel launch is bracketed by a CUDA-event pair

@@ -1,0 +1,70 @@
+"""GPU: the remaining BASELINE configs -- 96-channel wideband capture (config 3) and the waterfall STFT (config 5)."""
+import numpy as np
+import pytest
+
+from oracle import ref_dsp
+from tetraear_b200 import synth
+
+pytestmark = pytest.mark.gpu
+SOFT_TOL = 1e-5
+
+
+def test_config3_wideband_channels_match_reference_composition(gpu_processor):
+    """Oracle per channel: process(frequency_shift(x128, f_k, 2.4e6), 0)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n = 1 << 17
+    x, active, freqs = synth.wideband_capture(n, seed=3)
+    pick = [0, 1, 17, 47, 48, 49, 80, 95]                      # band edges, centre, odd/even alphabets
+    pick += [int(k) for k in np.flatnonzero(~active)[:2]]       # and two idle channels (noise only)
+    res = sp.process_wideband(x, freqs[pick], want_symbols=True, want_match=True)
+    x128 = x.astype(np.complex128)
+    for row, k in enumerate(pick):
+        r = ref_dsp.process(ref_dsp.nco(x128, freqs[k], 2.4e6), 0.0, 2.4e6)
+        nd = int(res["n_dibits"][row])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][row]) == r["best_phase"], k
+        err = np.abs(res["symbols"][row, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (k, err)
+        if active[k]:                                           # idle channels are pure noise: decisions sit on the rays
+            assert np.array_equal(res["dibits"][row, :nd], r["dibits"]), k
+            bits = ref_dsp.symbols_to_bits(r["dibits"])
+            assert np.array_equal(res["ts_match"][row, : 2 * nd - 21], ref_dsp.match_counts(bits))
+        else:
+            assert np.mean(res["dibits"][row, :nd] == r["dibits"]) > 0.999
+
+
+def test_config5_waterfall_rows(gpu_processor):
+    """4096-pt symmetric Hann, hop 1024 (75 % overlap), fftshift, 20 log10(|X|/N + 1e-20) on 1 s of IQ."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    x = synth.stft_test_signal(2_400_000, 5)
+    rows = sp.stft_db(x, 4096, 1024)
+    ref = ref_dsp.stft_db(x, 4096, 1024)
+    assert rows.shape == ref.shape == (2340, 4096)
+    # fp32 FFT: rounding noise sits ~140 dB below the strongest bin; compare where the reference is above -100 dBFS
+    mask = ref > -100.0
+    assert mask.mean() > 0.5
+    assert np.abs(rows - ref)[mask].max() < 1e-2
+    assert np.abs(rows - ref)[ref > -60.0].max() < 1e-3
+
+
+@pytest.mark.parametrize("nfft,hop,n", [(2048, 2048, 131072), (64, 16, 1000), (8192, 4096, 20000), (4096, 1024, 4095)])
+def test_stft_shapes_and_values(gpu_processor, nfft, hop, n):
+    sp = gpu_processor
+    x = synth.carrier_iq(n, 31, snr_db=20.0)
+    rows = sp.stft_db(x, nfft, hop)
+    ref = ref_dsp.stft_db(x, nfft, hop)
+    assert rows.shape == ref.shape
+    if len(ref):
+        assert np.abs(rows - ref)[ref > -100.0].max() < 1e-2
+
+
+def test_spectrum_block_of_capture_thread(gpu_processor):
+    """ui/modern.py:1921-1937: first 2048 samples of a chunk, frequency axis fftshift(fftfreq) + f_c."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    x = synth.carrier_iq(131072, 32, snr_db=25.0)
+    freqs, power = sp.spectrum(x, 2048, center_frequency=390.0e6)
+    assert np.array_equal(freqs, np.fft.fftshift(np.fft.fftfreq(2048, 1 / 2.4e6)) + 390.0e6)
+    ref = ref_dsp.spectrum_db(x, 2048)
+    assert power.dtype == np.float64 and np.abs(power - ref)[ref > -100].max() < 1e-2

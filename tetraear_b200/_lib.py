@@ -21,6 +21,8 @@ _SIGS = {
     "tetra_process_batch": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int32]),
+    "tetra_process_wideband": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),
     "tetra_enable_kernel_timing": (C.c_int, [c_ctx_p, C.c_int]),
     "tetra_kernel_time_ms": (C.c_double, [c_ctx_p, C.POINTER(C.c_int32)]),

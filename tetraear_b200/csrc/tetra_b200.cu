@@ -61,7 +61,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
@@ -334,7 +334,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -567,6 +567,34 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (ts_match && !d_match) CK(cudaMemcpyAsync(ts_match, k_match, (size_t)C * cap * 4, cudaMemcpyDeviceToHost, st));
     if (!async) CK(cudaStreamSynchronize(st));
     return TETRA_OK;
+}
+
+int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const double* channel_hz, int32_t C,
+                           uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                           uint8_t* ts_match) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || N < 0 || (C > 0 && (!channel_hz || !n_dibits)) || (C > 0 && N > 0 && !iq))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_wideband: bad arguments");
+    if (C == 0) return TETRA_OK;
+    if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_process_wideband: at most 65535 channels per call");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (N == 0) return tetra_process_batch(ctx, nullptr, C, 0, 0, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, 0);
+    const float2* dx = (const float2*)iq;
+    if (!is_device_ptr(iq)) {
+        CK(ctx->tmp_a.ensure((size_t)N * sizeof(float2)));
+        CK(cudaMemcpyAsync(ctx->tmp_a.p, iq, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, st));
+        dx = (const float2*)ctx->tmp_a.p;
+    }
+    CK(ctx->fo.ensure(sizeof(double) * C));
+    CK(cudaMemcpyAsync(ctx->fo.p, channel_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+    CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
+    k_mix_wide<<<dim3((unsigned)std::min<int64_t>((N + 255) / 256, 1024), C), 256, 0, st>>>(dx, N, (const double*)ctx->fo.p,
+                                                                                            ctx->sample_rate, (float2*)ctx->wide.p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    // every channel is now an ordinary carrier at baseband: process(shifted, 0)
+    return tetra_process_batch(ctx, (const float*)ctx->wide.p, C, N, N, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -109,6 +109,23 @@ __global__ void k_nco_c128(double2* x, int64_t n, double fo, double fs) {
     }
 }
 
+// Wideband channel selection (BASELINE config 3; the scanner's retune sweep, signal/scanner.py:383-445, done in
+// software): out[c][n] = x[n] * exp(-1j * 2 pi f_c * (n / fs)), i.e. frequency_shift (processor.py:97-100) of one
+// capture to C channel centres, with the reference's float64 phase and a complex64 result.
+__global__ void __launch_bounds__(256) k_mix_wide(const float2* __restrict__ x, int64_t n, const double* __restrict__ freqs,
+                                                    double fs, float2* __restrict__ out) {
+    const int c = blockIdx.y;
+    const double w = (2.0 * M_PI) * freqs[c];
+    float2* oc = out + (int64_t)c * n;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double t = (double)i / fs;
+        double sn, cs;
+        sincos(-(w * t), &sn, &cs);
+        const float2 v = __ldg(x + i);
+        oc[i] = make_float2((float)((double)v.x * cs - (double)v.y * sn), (float)((double)v.x * sn + (double)v.y * cs));
+    }
+}
+
 // extract_symbols (processor.py:179-219) on complex128: res[0] = n_symbols, res[1] = best phase
 __global__ void __launch_bounds__(256) k_extract_c128(const double2* x, int64_t n, int sps, int step, double2* out, int64_t* res) {
     __shared__ double red[8];

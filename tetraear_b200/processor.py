@@ -182,6 +182,32 @@ class SignalProcessor:
             out["ts_match"] = mt[:, : 2 * cap]
         return out
 
+    def process_wideband(self, samples, channel_freqs, want_symbols=True, want_match=False):
+        """BASELINE config 3: every channel of one wideband capture, i.e. for each centre f_c the composition
+        ``process(frequency_shift(samples, f_c), 0)`` of the reference's methods (processor.py:85-100, 221-273).
+        samples complex [N]; channel_freqs [C] in Hz relative to the capture centre. Returns the dict of
+        ``process_batch`` with one row per channel."""
+        self._sync_rate()
+        x = _as_c64(samples)
+        fr = np.ascontiguousarray(channel_freqs, dtype=np.float64)
+        n_ch, n = len(fr), len(x)
+        cap = int(self._lib.tetra_dibit_capacity(self._ctx, n))
+        dib = np.zeros((n_ch, max(cap, 1)), dtype=np.uint8)
+        nd = np.zeros(n_ch, dtype=np.int32)
+        ph = np.zeros(n_ch, dtype=np.int32)
+        sym = np.zeros((n_ch, cap + 1), dtype=np.complex64) if want_symbols else None
+        mt = np.zeros((n_ch, 2 * max(cap, 1), 2), dtype=np.uint8) if want_match else None
+        self._check(self._lib.tetra_process_wideband(
+            self._ctx, x.ctypes.data, n, fr.ctypes.data, n_ch, dib.ctypes.data, cap, nd.ctypes.data,
+            sym.ctypes.data if sym is not None else None, ph.ctypes.data,
+            mt.ctypes.data if mt is not None else None), "process_wideband")
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=np.where(nd > 0, nd + 1, 0).astype(np.int32), best_phase=ph)
+        if sym is not None:
+            out["symbols"] = sym
+        if mt is not None:
+            out["ts_match"] = mt[:, : 2 * cap]
+        return out
+
     # -- device-resident batch (bench / multi-GPU): pointers are raw CUDA addresses ----------
     def process_batch_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int,
                              cap: int, n_dibits_ptr: int, symbols_ptr: int = 0, best_phase_ptr: int = 0,
