@@ -496,9 +496,20 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
 
     if (use_fast) {
         // segments: enough CTAs to fill the machine when there are few carriers
-        int n_seg = 1;
+        // Segments per carrier: one CTA per SM, so the launch takes ceil(C*n_seg / SMs) waves of
+        // (tiles per segment + pipeline fill/drain + pre-roll tile) iterations; take the cheapest split.
         const int tiles = (int)((pl.L + K1_W - 1) / K1_W);
-        if (C < 296) n_seg = std::min(tiles, std::max(1, (296 + C - 1) / C));
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        int n_seg = 1;
+        double best_cost = 1e300;
+        for (int cand = 1; cand <= std::min(tiles, 64); ++cand) {
+            const int seg_tiles = (tiles + cand - 1) / cand;
+            const int real = (tiles + seg_tiles - 1) / seg_tiles;
+            const double waves = (double)(((int64_t)C * real + sms - 1) / sms);
+            const double cost = waves * (seg_tiles + 9);
+            if (cost < best_cost * 0.999) { best_cost = cost; n_seg = cand; }
+        }
         int seg_len = ((tiles + n_seg - 1) / n_seg) * K1_W;
         n_seg = (int)((pl.L + seg_len - 1) / seg_len);
         CK(ctx->partial.ensure((size_t)C * n_seg * 16 * sizeof(double)));
