@@ -28,6 +28,9 @@ sys.path.insert(0, ROOT)
 N_SAMPLES = 1 << 20
 TOTAL_CARRIERS = 4096
 BYTES_PER_SAMPLE = 8.10      # 8 B read + (1 B dibit + 8 B soft symbol + ~4 B match) per 130 samples
+# dram__bytes_read.sum + dram__bytes_write.sum of k1_channelize_demod per input sample, from the committed
+# ncu --set full capture (profiles/r01_k1_ncu_full_summary.txt: 4.9666 GB + 0.4852 GB for 592 carriers x 2^20)
+NCU_TRAFFIC_BYTES_PER_SAMPLE = (4.966612e9 + 0.485205e9) / (592 * (1 << 20))
 METRIC = "IQ MS/s demodulated"
 WORKLOAD = "configs[3]: %d carriers x 2^20 complex64 samples @2.4 MS/s, sharded %d per GPU"
 
@@ -326,7 +329,9 @@ def run_ours(a):
                        "l2": "inputs (%.1f GiB per GPU) far larger than L2; no flush needed" % (n_local * N_SAMPLES * 8 / 2**30),
                        "outputs": "dibits + soft symbols + best phase + TS1/TS2 match counts"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": a.traffic,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": a.traffic if a.traffic is not None else NCU_TRAFFIC_BYTES_PER_SAMPLE * n_local * N_SAMPLES,
+                         "traffic_source": "ncu --set full, profiles/r01_k1_ncu_full_summary.txt, scaled per sample",
                          "kernel": "k1_channelize_demod", "kernel_ms": k_avg, "kernel_launches_timed": k_n,
                          "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
