@@ -233,10 +233,13 @@ def run_ours(a):
     # every kernel of the step, the NCCL gather and the timing events share ONE explicit stream
     work = torch.cuda.Stream(device=dev)
     sp.enable_kernel_timing(True)
+    fos = None
+    if a.fo_max > 0:          # not the BASELINE workload: per-carrier AFC-style offsets exercise the freq_offset != 0 kernel
+        fos = np.random.default_rng(6).uniform(-a.fo_max, a.fo_max, size=total)[first_carrier:first_carrier + n_local]
 
     def step():
         sp.process_batch_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
-                                sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream)
+                                sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream, freq_offsets=fos)
         if world > 1:
             shard.gather_dibits(dib, nd, total, all_dib, all_nd)      # one NCCL all-gather per tensor
 
@@ -280,7 +283,7 @@ def run_ours(a):
         ok = True
         for i in (0, 1, n_local - 1):
             xi = torch.view_as_complex(x[i]).cpu().numpy()
-            r = ref_dsp.process(xi.astype(np.complex128), 0.0, 2.4e6)
+            r = ref_dsp.process(xi.astype(np.complex128), float(fos[i]) if fos is not None else 0.0, 2.4e6)
             n_i = int(nd[i].item())
             ok &= n_i == len(r["dibits"]) and bool(np.array_equal(dib[i, :n_i].cpu().numpy(), r["dibits"]))
             s = torch.view_as_complex(sym[i, : n_i + 1]).cpu().numpy()
@@ -325,14 +328,15 @@ def run_ours(a):
             "dtype": "f32", "data": "synthetic",
             "carriers_per_s": value / 2.4,
             "config": {"workload": WORKLOAD % (total, n_local),
-                       "n_samples": N_SAMPLES, "carriers": total, "freq_offset": 0,
+                       "n_samples": N_SAMPLES, "carriers": total,
+                       "freq_offset": 0 if fos is None else "uniform +-%g Hz per carrier" % a.fo_max,
                        "l2": "inputs (%.1f GiB per GPU) far larger than L2; no flush needed" % (n_local * N_SAMPLES * 8 / 2**30),
                        "outputs": "dibits + soft symbols + best phase + TS1/TS2 match counts"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": a.traffic if a.traffic is not None else NCU_TRAFFIC_BYTES_PER_SAMPLE * n_local * N_SAMPLES,
                          "traffic_source": "ncu --set full, profiles/r01_k1_ncu_full_summary.txt, scaled per sample",
-                         "kernel": "k1_channelize_demod", "kernel_ms": k_avg, "kernel_launches_timed": k_n,
+                         "kernel": "k1_channelize_demod<%d>" % (1 if fos is not None else 0), "kernel_ms": k_avg, "kernel_launches_timed": k_n,
                          "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
                          "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES,
@@ -365,6 +369,7 @@ def main():
     ap.add_argument("--carriers", type=int, default=TOTAL_CARRIERS)
     ap.add_argument("--e2e-carriers", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--fo-max", type=float, default=0.0, help="per-carrier freq_offset drawn from +-this (Hz); 0 = BASELINE workload")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the fused kernel from an ncu --set full capture (profiles/), if known")
     a = ap.parse_args()

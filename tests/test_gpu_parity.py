@@ -68,6 +68,40 @@ def test_batch_of_carriers_fast_path(gpu_processor):
         assert err <= SOFT_TOL
 
 
+def test_batch_with_mixed_freq_offsets(gpu_processor):
+    """freq_offset per carrier (the GUI passes its AFC offset, ui/modern.py:2021-2022): zero and non-zero offsets in
+    one batch, up to the edge of the fused path's range; noise-only input included."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n = 1 << 17
+    fos = [0.0, 1234.5, -5000.0, 12500.0, -12499.0, 333.25]
+    xs = [synth.carrier_iq(n, 200 + c, snr_db=20.0, alphabet="centred" if c % 2 else "pi4") for c in range(5)]
+    rng = np.random.default_rng(77)
+    xs.append((rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64))   # the reference tests' input
+    xs = np.stack(xs)
+    res = sp.process_batch(xs, fos, want_symbols=True)
+    for c, fo in enumerate(fos):
+        r = ref_dsp.process(xs[c].astype(np.complex128), fo, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], (c, fo)
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, fo, err)
+        if c < 5:
+            assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), (c, fo)
+        else:
+            assert np.mean(res["dibits"][c, :nd] == r["dibits"]) > 0.999
+
+
+def test_freq_offset_outside_fused_range_uses_exact_path(gpu_processor):
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    x = synth.carrier_iq(1 << 15, 210, snr_db=20.0)
+    r = ref_dsp.process(x.astype(np.complex128), 30000.0, 2.4e6)
+    d = sp.process(x, 30000.0)
+    assert np.array_equal(d, r["dibits"])
+    assert np.abs(sp.symbols - r["symbols"]).max() / np.abs(r["symbols"]).max() <= SOFT_TOL
+
+
 def test_full_size_properties(gpu_processor):
     """BASELINE size (2^20): structural checks that do not need the oracle."""
     sp = gpu_processor

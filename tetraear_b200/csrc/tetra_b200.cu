@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <cmath>
 
 #include "../../include/tetra_b200.h"
 #include "filter_design.h"
@@ -61,7 +62,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
@@ -117,7 +118,8 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_hb, TB_HB_TAPS, sizeof(float) * (2 * TB_HB_H + 1)));
     CK(cudaMemcpyToSymbol(c_fir, fir, sizeof fir));
     CK(cudaMemcpyToSymbol(c_interp, TB_INTERP_TAPS, sizeof(float) * TB_INT_K));
-    CK(cudaFuncSetAttribute(k1_channelize_demod, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     ctx->tables_uploaded = true;
     return 0;
 }
@@ -199,7 +201,7 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
     g.x = ea.x32; g.pitch = ea.pitch; g.n = ea.n; g.q = ea.q; g.L = ea.L; g.edge = ea.edge; g.cf = ea.cf;
     g.y = ea.y32; g.y_pitch = ea.y_pitch; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
     g.scr1 = (double2*)ctx->scr1.p; g.scrz = (double2*)ctx->scrz.p; g.scr2 = (double2*)ctx->scr2.p;
-    g.w1 = w1; g.wz = wz;
+    g.w1 = w1; g.wz = wz; g.fo = ea.fo; g.fs_dec = ea.fs_dec;
     k_exact_edges<<<(int)((nj + EXT_THREADS - 1) / EXT_THREADS), EXT_THREADS, 0, st>>>(g);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -286,7 +288,7 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
     g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
     g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
     g.e.scr1 = (double2*)ctx->scr1.p; g.e.scrz = (double2*)ctx->scrz.p; g.e.scr2 = (double2*)ctx->scr2.p;
-    g.e.w1 = w1; g.e.wz = wz;
+    g.e.w1 = w1; g.e.wz = wz; g.e.fo = ea.fo; g.e.fs_dec = ea.fs_dec;
     g.m1 = (const double*)ctx->mats.p;
     g.m2 = (const double*)ctx->mats.p + 4 * 5 * 64;
     k_exact_edges_warp<<<(int)nj, 32, 0, st>>>(g);          // one warp = one job = one block: fits beside the fused kernel's CTA
@@ -334,7 +336,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -446,18 +448,21 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     // ---- which carriers take the fused path ----
     const bool fast_ok = ctx->sample_rate == 2.4e6 && pl.q == 10 && pl.has_s1 && pl.has_s2 && N >= 16384 && pl.sps == K1_NPH;
     std::vector<int2> edge_jobs, full_jobs;
-    bool any_fo = false;
+    bool any_fo = false, fo_in_range = true;
     for (int c = 0; c < C; ++c) {
-        const bool zero_fo = !fo_hz || fo_hz[c] == 0.0;
-        if (!zero_fo) any_fo = true;
-        if (fast_ok && zero_fo) edge_jobs.push_back(make_int2(c, EX_LEFT));
+        const double f = fo_hz ? fo_hz[c] : 0.0;
+        if (f != 0.0) any_fo = true;
+        if (!(std::fabs(f) <= K1_FO_MAX_HZ)) fo_in_range = false;     // also catches NaN
+    }
+    // The fused path covers freq_offset = 0 (MODE 0) and, with per-carrier complex taps, |freq_offset| <= 12.5 kHz
+    // (MODE 1: the GUI's AFC range, ui/modern.py:1949-1967); anything else runs the exact recursion over the block.
+    const bool use_fast = fast_ok && (!any_fo || fo_in_range);
+    for (int c = 0; c < C; ++c) {
+        if (use_fast) edge_jobs.push_back(make_int2(c, EX_LEFT));
         else full_jobs.push_back(make_int2(c, EX_FULL));
     }
     // LEFT jobs first, then RIGHT: the two window shapes differ in length, keep warps homogeneous
     for (size_t k = 0, n_left = edge_jobs.size(); k < n_left; ++k) edge_jobs.push_back(make_int2(edge_jobs[k].x, EX_RIGHT));
-    const bool use_fast = !edge_jobs.empty();
-    if (use_fast && !full_jobs.empty())
-        return fail(ctx, TETRA_E_UNSUPPORTED, "mixing zero and non-zero freq_offset in one batch: split the call");
     const double* d_fo = nullptr;
     if (any_fo) {
         CK(ctx->fo.ensure(sizeof(double) * C));
@@ -517,6 +522,18 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg;
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
+        ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate;
+        if (any_fo) {
+            // this batch's complex fir120 tables, designed on the device from the same IIR coefficients
+            CK(ctx->ctaps.ensure((size_t)C * 128 * sizeof(float2)));
+            FoDesignArgs fd;
+            fd.fo = d_fo; fd.fs = ctx->sample_rate; fd.fs_dec = pl.rate; fd.ctaps = (float2*)ctx->ctaps.p;
+            memcpy(fd.sos, ea.cf.sos, sizeof fd.sos); memcpy(fd.b, ea.cf.b, sizeof fd.b); memcpy(fd.a, ea.cf.a, sizeof fd.a);
+            k_design_fo_taps<<<C, 128, 0, st>>>(fd);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            ka.ctaps = (const float2*)ctx->ctaps.p;
+        }
         // edge windows run beside the bulk kernel on the side stream
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&ctx->ph_ev[k]));
@@ -543,7 +560,8 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ctx->ev_used++;
             CK(cudaEventRecord(t0, st));
         }
-        k1_channelize_demod<<<dim3(n_seg, C), K1_THREADS, sizeof(K1Smem), st>>>(ka);
+        if (any_fo) k1_channelize_demod<1><<<dim3(n_seg, C), K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+        else k1_channelize_demod<0><<<dim3(n_seg, C), K1_THREADS, sizeof(K1Smem), st>>>(ka);
         ctx->launches++;
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));

@@ -291,7 +291,18 @@ struct EdgeArgs {
     double2* scrz;           // [n_jobs][wz] stage-1 result
     double2* scr2;           // [n_jobs][wz + 2 PAD2] forward stage-2 output
     int64_t w1, wz;
+    const double* fo;        // [C] freq offsets in Hz (device) or null: NCO between the two filters
+    double fs_dec;           // sample rate after stage 1
 };
+
+// frequency_shift (processor.py:97-100) of stage-1 output sample m
+__device__ __forceinline__ double2 edge_nco(double2 v, int m, double w_nco, double fs_dec) {
+    if (w_nco == 0.0) return v;
+    const double t = (double)m / fs_dec;
+    double sn, cs;
+    sincos(-(w_nco * t), &sn, &cs);
+    return make_double2(v.x * cs - v.y * sn, v.x * sn + v.y * cs);
+}
 
 struct SkewState {
     double z0[4][2], z1[4][2];            // biquad states [section][re, im]
@@ -398,9 +409,11 @@ __global__ void __launch_bounds__(EXT_THREADS) k_exact_edges(const EdgeArgs a) {
         // decimation bookkeeping of the emitted samples: input index i = e - PAD1 = q m + r
         const int64_t i0 = e_hi - 1 - EX_PAD1;
         int m = (int)(i0 / q), r = (int)(i0 % q);
+        const double w_nco = a.fo ? (2.0 * M_PI) * a.fo[car] : 0.0;
         auto emit = [&]() {
             if (r == 0) {
-                if ((int64_t)q * m < n && m >= m_lo && m < m_hi) sz[m - m_lo] = make_double2(st.yl[3][0], st.yl[3][1]);
+                if ((int64_t)q * m < n && m >= m_lo && m < m_hi)
+                    sz[m - m_lo] = edge_nco(make_double2(st.yl[3][0], st.yl[3][1]), m, w_nco, a.fs_dec);
                 r = q; --m;
             }
             --r;
@@ -701,6 +714,7 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
     // ---- stage 1 backward: step s <-> e = e_hi - 1 - s; keep every q-th ----
     {
         const int nb = (int)(e_hi - rg.e_stop);
+        const double w_nco = a.fo ? (2.0 * M_PI) * a.fo[car] : 0.0;
         sos_pass_warp<double2>(a.cf, nb, s1[nf - 1], w.m1 + (var + 1) * 5 * 64, lane,
             [&](int s) { return s1[nf - 1 - min(s, nb - 1)]; },
             [&](double2 r, int) { return r; },
@@ -708,7 +722,7 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
                 const int64_t i = e_hi - 1 - s - EX_PAD1;  // >= 0
                 if (i % q == 0) {
                     const int m = (int)(i / q);
-                    if (i < n && m >= m_lo && m < m_hi) sz[m - m_lo] = make_double2(yr, yi);
+                    if (i < n && m >= m_lo && m < m_hi) sz[m - m_lo] = edge_nco(make_double2(yr, yi), m, w_nco, a.fs_dec);
                 }
             });
     }

@@ -90,6 +90,7 @@ constexpr int K1_D0 = -1902;              // v pairs [320 i + D0, +320) -> y [64
 constexpr int K1_PREROLL = 640;           // stream origin = n_lo - PREROLL (w samples)
 constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
 constexpr int K1_NPH = 13;
+constexpr double K1_FO_MAX_HZ = 12500.0;  // freq_offset range of the fused path (the proto's alias nulls cover +-60 kHz +- this)
 
 static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K == 8, "tables changed: re-derive lags");
 // dependency checks (each stage only reads what earlier iterations produced)
@@ -113,6 +114,13 @@ struct K1Smem {
     double bins[K1_NPH][K1_DLANES];
     uint64_t full[K1_NBUF];
 };
+// freq_offset != 0 variant: the NCO phasors of the w samples of the current / next iteration and this
+// carrier's complex fir120 taps
+struct K1SmemFo {
+    K1Smem base;
+    float2 ph[2][K1_W];
+    float2 ctap[128];
+};
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
 __constant__ float c_hb[2 * TB_HB_H + 1];
@@ -130,6 +138,10 @@ struct K1Args {
     int64_t y_pitch;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x base/pitch allow 16-byte bulk copies
+    // MODE 1 (freq_offset != 0) only
+    const double* fo;       // [C] Hz
+    const float2* ctaps;    // [C][128] complex fir120 taps for each carrier's offset (k_design_fo_taps)
+    double fs_dec;          // 240000
 };
 
 // fill one input buffer body with tile k of the stream (global x index gx0 .. gx0+6400)
@@ -174,11 +186,59 @@ __device__ __forceinline__ void k1_fir_quarter(const float2* __restrict__ u, int
     }
 }
 
+// the same with this carrier's complex taps (freq_offset != 0): acc += x * (tr + j ti)
+__device__ __forceinline__ void k1_fir_quarter_cplx(const float2* __restrict__ u, int s0, const float2* __restrict__ taps,
+                                                    float2 (&acc)[10]) {
+    float2 tp[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) tp[k] = taps[k];         // broadcast shared-memory loads
+#pragma unroll
+    for (int t2 = 0; t2 < 21; ++t2) {
+        const float4 v = *reinterpret_cast<const float4*>(&u[(s0 + 2 * t2) & (K1_URING - 1)]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int t = 2 * t2 + h;
+            const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+            const float2 xs = make_float2(-xv.y, xv.x);    // j * x
+#pragma unroll
+            for (int r = 0; r < 10; ++r) {
+                const int k = t - r;
+                if (k >= 0 && k < 32) {
+                    acc[r] = ffma2(xv, tp[k].x, acc[r]);
+                    acc[r] = ffma2(xs, tp[k].y, acc[r]);
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ void k1_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
+// NCO phasors exp(-j 2 pi f m / fs_dec) of ten consecutive w samples starting at global index m0 (float64 phase,
+// reduced to one turn before the sine/cosine: processor.py:97-100 evaluated at the decimated rate)
+__device__ __forceinline__ void k1_phasors10(double fo, double fs_dec, int64_t m0, float2* dst) {
+    const double turns = fo * (double)m0 / fs_dec;
+    double sn, cs, sr, cr;
+    sincospi(-2.0 * (turns - rint(turns)), &sn, &cs);
+    const double step = fo / fs_dec;
+    sincospi(-2.0 * step, &sr, &cr);
+#pragma unroll
+    for (int g = 0; g < 10; ++g) {
+        dst[g] = make_float2((float)cs, (float)sn);
+        const double c2 = cs * cr - sn * sr;
+        sn = cs * sr + sn * cr;
+        cs = c2;
+    }
+}
+
+// MODE 0: freq_offset == 0 (real fir120 taps from constant memory). MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w
+// samples are rotated by the NCO phasor (stage B's warps prepare them one iteration ahead) and stage C applies this
+// carrier's complex taps  B2(f) C2(f + f_off) / (HB(f) P(f + f_off)).
+template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
+    K1SmemFo& sf = *reinterpret_cast<K1SmemFo*>(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int seg = blockIdx.x, car = blockIdx.y;
@@ -205,6 +265,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    double fo_hz = 0.0;
+    if (MODE == 1) {
+        fo_hz = a.fo[car];
+        if (tid < 128) sf.ctap[tid] = a.ctaps[(int64_t)car * 128 + tid];
+        if (tid >= 256 && tid < 320)                      // phasors of iteration 0: w [A0, A0 + 640)
+            k1_phasors10(fo_hz, a.fs_dec, (int64_t)O + K1_A0 + 10 * (tid - 256), &sf.ph[0][10 * (tid - 256)]);
     }
     __syncthreads();
     // tile k lives in buffer (k - i_first) % NBUF and completes phase (k - i_first) / NBUF of its barrier
@@ -244,6 +311,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     }
                 }
                 const int wbase = K1_W * i + K1_A0 + 5 * L5;
+                if (MODE == 1) {                            // frequency_shift at the decimated rate (processor.py:259-261)
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) {
+                        const float2 p = sf.ph[i & 1][5 * L5 + g];
+                        acc[g] = make_float2(acc[g].x * p.x - acc[g].y * p.y, acc[g].x * p.y + acc[g].y * p.x);
+                    }
+                }
 #pragma unroll
                 for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
                 // tail of this tile -> header of the next buffer
@@ -264,7 +338,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                 for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
             }
-            k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
+            if (MODE == 1) k1_fir_quarter_cplx(s.u, s0, sf.ctap + 32 * q, cacc);
+            else k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
             if (q == 3) {
 #pragma unroll
                 for (int r = 0; r < 10; r += 2)
@@ -294,6 +369,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
 #pragma unroll
             for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
+            if (MODE == 1)                                  // phasors for the w samples stage A produces next iteration
+                k1_phasors10(fo_hz, a.fs_dec, (int64_t)O + K1_W * (i + 1) + K1_A0 + 10 * lb, &sf.ph[(i + 1) & 1][10 * lb]);
             k1_bar_sync();
         }
     } else {
@@ -359,6 +436,70 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         double t = 0.0;
         for (int j = 0; j < K1_DLANES; ++j) t += s.bins[tid][j];
         a.partial[((int64_t)car * a.n_seg + seg) * 16 + tid] = t;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_design_fo_taps: the complex fir120 table of one carrier with freq_offset f_off,
+//   Gc(f) = B2(f) C2(f + f_off) / (HB(f) P(f + f_off))   on |f| < 60 kHz at 120 kS/s,
+// by frequency sampling (FO_NG points) and an inverse DFT truncated to 127 taps -- the same recipe
+// tools/design_filters.py uses for the real table. Everything in float64; one CTA per carrier.
+// Layout as c_fir: ctaps[0] = 0, ctaps[k] = g[lag = 64 - k]  (v[n] = sum_k ctaps[k] u[n - 64 + k]).
+// ----------------------------------------------------------------------------------------------
+constexpr int FO_NG = 1024;
+struct FoDesignArgs {
+    const double* fo;        // [C] Hz
+    double sos[4][6];        // cheby1(8, 0.05, 0.08) sections at fs
+    double b[5], a[5];       // butter(4, 12.5k / 120k) at fs_dec
+    double fs, fs_dec;
+    float2* ctaps;           // [C][128]
+};
+
+__global__ void __launch_bounds__(128) k_design_fo_taps(const FoDesignArgs g) {
+    __shared__ double T[FO_NG];
+    __shared__ double2 tw[FO_NG];
+    const int car = blockIdx.x, tid = threadIdx.x;
+    const double fo = g.fo[car];
+    for (int i = tid; i < FO_NG; i += 128) {
+        const double f = (double)(i < FO_NG / 2 ? i : i - FO_NG) * (0.5 * g.fs_dec / FO_NG);
+        // |H_butter|^2 at f (rate fs_dec)
+        double s1, c1;
+        double nr = 0, ni = 0, dr = 0, di = 0;
+        for (int k = 0; k < 5; ++k) {
+            sincospi(-2.0 * f * k / g.fs_dec, &s1, &c1);
+            nr += g.b[k] * c1; ni += g.b[k] * s1; dr += g.a[k] * c1; di += g.a[k] * s1;
+        }
+        const double B2 = (nr * nr + ni * ni) / (dr * dr + di * di);
+        // |H_cheby|^2 at f + fo (rate fs)
+        double C2 = 1.0;
+        for (int sct = 0; sct < 4; ++sct) {
+            double n_r = 0, n_i = 0, d_r = 0, d_i = 0;
+            for (int k = 0; k < 3; ++k) {
+                sincospi(-2.0 * (f + fo) * k / g.fs, &s1, &c1);
+                n_r += g.sos[sct][k] * c1; n_i += g.sos[sct][k] * s1;
+                d_r += g.sos[sct][3 + k] * c1; d_i += g.sos[sct][3 + k] * s1;
+            }
+            C2 *= (n_r * n_r + n_i * n_i) / (d_r * d_r + d_i * d_i);
+        }
+        double hbv = c_hb[TB_HB_H], pv = c_proto[TB_PROTO_H];
+        for (int k = 1; k <= TB_HB_H; ++k) hbv += 2.0 * (double)c_hb[TB_HB_H + k] * cospi(2.0 * f * k / g.fs_dec);
+        for (int k = 1; k <= TB_PROTO_H; ++k) pv += 2.0 * (double)c_proto[TB_PROTO_H + k] * cospi(2.0 * (f + fo) * k / g.fs);
+        T[i] = B2 * C2 / (hbv * pv);
+        sincospi(2.0 * (double)i / FO_NG, &s1, &c1);
+        tw[i] = make_double2(c1, s1);
+    }
+    __syncthreads();
+    float2* out = g.ctaps + (int64_t)car * 128;
+    if (tid == 0) out[0] = make_float2(0.f, 0.f);
+    if (tid >= 1) {
+        const int lag = 64 - tid;                        // 63 .. -63
+        double ar = 0.0, ai = 0.0;
+        for (int i = 0; i < FO_NG; ++i) {
+            const int idx = (((i * lag) % FO_NG) + FO_NG) % FO_NG;
+            ar += T[i] * tw[idx].x;
+            ai += T[i] * tw[idx].y;
+        }
+        out[tid] = make_float2((float)(ar / FO_NG), (float)(ai / FO_NG));
     }
 }
 
