@@ -1,0 +1,92 @@
+#!/usr/bin/env python
+"""Timings of the BASELINE configs that are not the bench line (configs[1], [2], [4]): single-carrier latency,
+96-channel wideband capture, waterfall STFT. CUDA-event timed through the C ABI with device-resident buffers
+where the entry point accepts them. Writes one JSON object (stdout) for profiles/.
+
+    python tools/bench_configs.py > gpurun_out/configs.json
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from tetraear_b200 import synth
+    from tetraear_b200.processor import SignalProcessor
+    out = {}
+    dev = torch.device("cuda", 0)
+    sp = SignalProcessor(2.4e6, device=0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+    def timed(fn, reps=20, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) * 1e3 / reps
+
+    # ---- config 2: one carrier, 2^20 samples, device-resident (latency-bound) ----
+    n = 1 << 20
+    cap = sp.dibit_capacity(n)
+    x = torch.view_as_real(torch.from_numpy(synth.carrier_iq(n, 0, snr_db=30.0)).to(dev)).contiguous()
+    dib = torch.zeros((1, cap), dtype=torch.uint8, device=dev)
+    nd = torch.zeros(1, dtype=torch.int32, device=dev)
+    sym = torch.zeros((1, cap + 1, 2), dtype=torch.float32, device=dev)
+    mt = torch.zeros((1, 2 * cap, 2), dtype=torch.uint8, device=dev)
+    ph = torch.zeros(1, dtype=torch.int32, device=dev)
+    for name, fo in (("config2_one_carrier_fo0", None), ("config2_one_carrier_fo1234.5", [1234.5])):
+        ms, wall = timed(lambda: sp.process_batch_device(x.data_ptr(), 1, n, n, dib.data_ptr(), cap, nd.data_ptr(), sym.data_ptr(),
+                                                         ph.data_ptr(), mt.data_ptr(), stream=0, freq_offsets=fo))
+        out[name] = {"ms_per_block": ms, "host_wall_ms": wall, "MS_per_s": n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3)}
+    hx = synth.carrier_iq(n, 0, snr_db=30.0)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        sp.process(hx)
+    out["config2_process_host_call_ms"] = (time.perf_counter() - t0) * 100
+
+    # ---- config 3: 96 channels of one 2^20-sample wideband capture ----
+    xw, active, freqs = synth.wideband_capture(n, seed=3)
+    t0 = time.perf_counter()
+    reps = 5
+    sp.process_wideband(xw, freqs, want_symbols=True, want_match=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sp.process_wideband(xw, freqs, want_symbols=True, want_match=True)
+    wall = (time.perf_counter() - t0) / reps
+    out["config3_wideband_96ch"] = {"host_call_ms": wall * 1e3, "wideband_MS_per_s": n / wall / 1e6, "channel_MS_per_s": 96 * n / wall / 1e6,
+                                    "x_real_time": (n / 2.4e6) / wall, "note": "host capture in, host dibits/symbols/match out (PCIe + 96 result rows inside)"}
+
+    # ---- config 5: waterfall STFT 4096 / hop 1024 on 1 s of IQ, device-resident ----
+    ns = 2_400_000
+    xs = torch.view_as_real(torch.from_numpy(synth.stft_test_signal(ns, 5)).to(dev)).contiguous()
+    rows = (ns - 4096) // 1024 + 1
+    o = torch.zeros((rows, 4096), dtype=torch.float32, device=dev)
+    import ctypes as C
+    r64 = C.c_int64(0)
+    ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xs.data_ptr(), ns, 4096, 1024, o.data_ptr(), C.byref(r64)), reps=50)
+    by = 24.0 * ns
+    out["config5_stft_4096_hop1024"] = {"ms_per_second_of_iq": ms, "rows_per_s": rows / (ms * 1e-3), "MS_per_s": ns / ms / 1e3,
+                                        "x_real_time": 1e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
+                                        "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak, "frames_at_60fps_rows": rows / 60.0}
+    print(json.dumps(out, indent=1))
+    sp.close()
+
+
+if __name__ == "__main__":
+    main()
