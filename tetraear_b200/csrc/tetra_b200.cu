@@ -501,8 +501,8 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
 
     if (use_fast) {
         // segments: enough CTAs to fill the machine when there are few carriers
-        // Segments per carrier: one CTA per SM, so the launch takes ceil(C*n_seg / SMs) waves of
-        // (tiles per segment + pipeline fill/drain + pre-roll tile) iterations; take the cheapest split.
+        // Work items = (carrier, segment), streamed back to back by min(SMs, items) persistent CTAs: the launch takes
+        // ceil(items / CTAs) slots of (tiles per segment + 1) iterations; take the cheapest split of a carrier.
         const int tiles = (int)((pl.L + K1_W - 1) / K1_W);
         int sms = 148;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -510,16 +510,20 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         double best_cost = 1e300;
         for (int cand = 1; cand <= std::min(tiles, 64); ++cand) {
             const int seg_tiles = (tiles + cand - 1) / cand;
+            if (cand > 1 && seg_tiles < 8) break;              // keep slots much longer than the pipeline
             const int real = (tiles + seg_tiles - 1) / seg_tiles;
-            const double waves = (double)(((int64_t)C * real + sms - 1) / sms);
-            const double cost = waves * (seg_tiles + 9);
+            const int64_t items = (int64_t)C * real;
+            const int64_t ctas = std::min<int64_t>(sms, items);
+            const double cost = (double)((items + ctas - 1) / ctas) * std::max(seg_tiles + 1, K1_MIN_T_ITEM) + 6;
             if (cost < best_cost * 0.999) { best_cost = cost; n_seg = cand; }
         }
         int seg_len = ((tiles + n_seg - 1) / n_seg) * K1_W;
         n_seg = (int)((pl.L + seg_len - 1) / seg_len);
+        const int n_items = C * n_seg;
+        const int k1_grid = std::min(sms, n_items);
         CK(ctx->partial.ensure((size_t)C * n_seg * 16 * sizeof(double)));
         K1Args ka;
-        ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg;
+        ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg; ka.n_items = n_items; ka.t_item = std::max(seg_len / K1_W + 1, K1_MIN_T_ITEM);
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
         ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate;
@@ -560,8 +564,8 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ctx->ev_used++;
             CK(cudaEventRecord(t0, st));
         }
-        if (any_fo) k1_channelize_demod<1><<<dim3(n_seg, C), K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
-        else k1_channelize_demod<0><<<dim3(n_seg, C), K1_THREADS, sizeof(K1Smem), st>>>(ka);
+        if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+        else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
         ctx->launches++;
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));

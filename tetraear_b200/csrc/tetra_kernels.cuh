@@ -87,9 +87,10 @@ constexpr int K1_A0 = -2;                 // w: [640 i + A0, +640)
 constexpr int K1_B0 = -326;               // u: [320 i + B0, +320)
 constexpr int K1_C0 = -614;               // v group g: [320 g + C0, +320), finished in iteration g + 3
 constexpr int K1_D0 = -1902;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
-constexpr int K1_PREROLL = 640;           // stream origin = n_lo - PREROLL (w samples)
+constexpr int K1_PREROLL = 320;           // pre-roll and post-roll of a slot in w samples (> the cascade's reach of 157)
 constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
 constexpr int K1_NPH = 13;
+constexpr int K1_MIN_T_ITEM = 6;           // a slot outlasts stage C's lag behind stage A (two tap buffers suffice)
 constexpr double K1_FO_MAX_HZ = 12500.0;  // freq_offset range of the fused path (the proto's alias nulls cover +-60 kHz +- this)
 
 static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K == 8, "tables changed: re-derive lags");
@@ -119,7 +120,7 @@ struct K1Smem {
 struct K1SmemFo {
     K1Smem base;
     float2 ph[2][K1_W];
-    float2 ctap[128];
+    float2 ctap[2][128];
 };
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
@@ -133,7 +134,9 @@ struct K1Args {
     int64_t n;              // samples per carrier
     int32_t L;              // ceil(n/10)
     int32_t seg_len;        // y samples per segment (multiple of 640)
-    int32_t n_seg;
+    int32_t n_seg;          // segments per carrier
+    int32_t n_items;        // carriers * n_seg work items
+    int32_t t_item;         // tiles per item = seg_len / 640 + 1 (pre-roll + post-roll)
     float2* y;              // [C][y_pitch]
     int64_t y_pitch;
     double* partial;        // [C][n_seg][16]
@@ -143,28 +146,6 @@ struct K1Args {
     const float2* ctaps;    // [C][128] complex fir120 taps for each carrier's offset (k_design_fo_taps)
     double fs_dec;          // 240000
 };
-
-// fill one input buffer body with tile k of the stream (global x index gx0 .. gx0+6400)
-__device__ __forceinline__ void k1_issue_tile(K1Smem& s, const K1Args& a, const float2* xc, int64_t gx0, int k, int lane) {
-    float2* dst = &s.in[k % K1_NBUF][K1_HDR];
-    uint64_t* bar = &s.full[k % K1_NBUF];
-    const bool inside = (gx0 >= 0) && (gx0 + K1_TILE <= a.n);
-    if (inside && a.aligned) {
-        if (lane == 0) {
-            mbar_expect_tx(bar, K1_TILE * 8);
-            tma_load_1d(dst, xc + gx0, K1_TILE * 8, bar);
-        }
-    } else {
-        // block-edge tile: bounds-checked copy with zero fill. Samples outside the block never reach
-        // an output this kernel keeps (those are K1_EDGE away from the ends), so the fill value is free.
-        for (int t = lane; t < K1_TILE; t += 32) {
-            int64_t g = gx0 + t;
-            dst[t] = (g >= 0 && g < a.n) ? __ldg(xc + g) : make_float2(0.f, 0.f);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar);
-    }
-}
 
 // one quarter (taps 32 q .. 32 q + 31 of the 128-entry table c_fir) of ten consecutive fir120 outputs;
 // q is warp-uniform, so the taps arrive through uniform constant loads and there is one copy of this code
@@ -231,8 +212,55 @@ __device__ __forceinline__ void k1_phasors10(double fo, double fs_dec, int64_t m
     }
 }
 
+// Work items and slots. An item is one (carrier, segment); CTA b of a grid of G persistent CTAs owns items
+// b, b + G, b + 2G, ... and streams them back to back as ONE continuous sample stream: slot q of the CTA's
+// stream is t_item tiles long (the segment plus 320 w samples of pre-roll and post-roll) and the four stages
+// simply keep flowing across slot boundaries -- the pipeline is filled and drained once per CTA, not once per
+// item. Only stage A (which tile of which carrier to fetch) and stage D (where an output belongs) look at slots.
+struct K1Slot {
+    int car, n_lo, n_hi, O;   // carrier, segment range in y samples, local origin O = n_lo - PREROLL
+};
+__device__ __forceinline__ K1Slot k1_slot(const K1Args& a, int q) {
+    const int it = blockIdx.x + q * gridDim.x;
+    K1Slot sl;
+    sl.car = it / a.n_seg;
+    const int seg = it - sl.car * a.n_seg;
+    sl.n_lo = seg * a.seg_len;
+    sl.n_hi = min(sl.n_lo + a.seg_len, a.L);
+    sl.O = sl.n_lo - K1_PREROLL;
+    return sl;
+}
+__device__ __forceinline__ int k1_floordiv(int x, int d) { return x >= 0 ? x / d : -((-x + d - 1) / d); }
+
+// fill buffer (i % NBUF) with tile i of this CTA's stream
+__device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
+    const float2* xc = a.x + (int64_t)sl.car * a.pitch;
+    const int64_t gx0 = (int64_t)sl.O * 10 + (int64_t)t * K1_TILE;
+    float2* dst = &s.in[i % K1_NBUF][K1_HDR];
+    uint64_t* bar = &s.full[i % K1_NBUF];
+    // in-block part [lo, hi) of the tile. Samples outside the block never reach an output this kernel keeps (those are
+    // K1_EDGE away from the block ends, the cascade reaches 157), so the rest of the buffer may hold anything finite.
+    const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
+    const int hi = (int)max((int64_t)lo, min((int64_t)K1_TILE, a.n - gx0));
+    if (a.aligned) {
+        const int cnt = (hi - lo) & ~1;                    // bulk copies move multiples of 16 bytes (lo and gx0 are even)
+        if (lane == 0) {
+            if (cnt > 0) {
+                mbar_expect_tx(bar, cnt * 8);
+                tma_load_1d(dst + lo, xc + gx0 + lo, cnt * 8, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    } else {
+        for (int tt = lo + lane; tt < hi; tt += 32) dst[tt] = __ldg(xc + gx0 + tt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+    }
+}
+
 // MODE 0: freq_offset == 0 (real fir120 taps from constant memory). MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w
-// samples are rotated by the NCO phasor (stage B's warps prepare them one iteration ahead) and stage C applies this
+// samples are rotated by the NCO phasor (stage B's warps prepare them one iteration ahead) and stage C applies the
 // carrier's complex taps  B2(f) C2(f + f_off) / (HB(f) P(f + f_off)).
 template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Args a) {
@@ -241,87 +269,85 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     K1SmemFo& sf = *reinterpret_cast<K1SmemFo*>(smem_raw);
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int seg = blockIdx.x, car = blockIdx.y;
-    const int n_lo = seg * a.seg_len;
-    const int n_hi = min(n_lo + a.seg_len, a.L);
-    const int O = n_lo - K1_PREROLL;                      // stream origin in w samples (even)
-    const float2* xc = a.x + (int64_t)car * a.pitch;
-    const int64_t gx_origin = (int64_t)O * 10;
-    // iterations: last y local index needed is (n_hi-1-O); D_i ends at 640 i + 2 D0 + 639
-    const int n_iter = (n_hi - 1 - O - 2 * K1_D0 - (K1_W - 1) + K1_W - 1) / K1_W + 1;
-    // tiles that hold samples of the block: [i_first, n_load); the others are never loaded nor filtered
-    const int i_first = gx_origin >= 0 ? 0 : (int)((-gx_origin) / K1_TILE);
-    const int n_load = (int)min((int64_t)n_iter, (a.n - gx_origin + K1_TILE - 1) / K1_TILE);
-    // valid y range written by this CTA (edges belong to the exact kernel)
-    const int y_lo = max(n_lo, K1_EDGE), y_hi = min(n_hi, a.L - K1_EDGE);
+    const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slots of this CTA
+    const int S = a.t_item * K1_W;                        // slot length in w / y samples
+    const int n_load = n_my * a.t_item;                   // tiles of the stream
+    // last kept output sits below stream coordinate n_my S - PREROLL; D_i ends at 640 i + 2 D0 + 639
+    const int n_iter = n_load + (-2 * K1_D0 - K1_PREROLL + K1_W - 1) / K1_W;
 
-    // ---- prologue: zero rings/bins/headers, init barriers, start the first two tiles ----
+    // ---- prologue: zero rings/headers, init barriers, start the first two tiles ----
     for (int i = tid; i < K1_WRING; i += K1_THREADS) s.w[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_URING; i += K1_THREADS) s.u[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_VRING; i += K1_THREADS) s.v[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < K1_NPH * K1_DLANES; i += K1_THREADS) (&s.bins[0][0])[i] = 0.0;
-    for (int i = tid; i < K1_NBUF * K1_HDR; i += K1_THREADS) s.in[i / K1_HDR][i % K1_HDR] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_NBUF * (K1_HDR + K1_TILE); i += K1_THREADS) (&s.in[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    double fo_hz = 0.0;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
     if (MODE == 1) {
-        fo_hz = a.fo[car];
-        if (tid < 128) sf.ctap[tid] = a.ctaps[(int64_t)car * 128 + tid];
-        if (tid >= 256 && tid < 320)                      // phasors of iteration 0: w [A0, A0 + 640)
-            k1_phasors10(fo_hz, a.fs_dec, (int64_t)O + K1_A0 + 10 * (tid - 256), &sf.ph[0][10 * (tid - 256)]);
+        const K1Slot s0 = k1_slot(a, 0);
+        if (tid < 128) sf.ctap[0][tid] = a.ctaps[(int64_t)s0.car * 128 + tid];
+        if (tid >= 256 && tid < 320)                      // phasors of iteration 0: w [A0, A0 + 640) of slot 0
+            k1_phasors10(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &sf.ph[0][10 * (tid - 256)]);
     }
     __syncthreads();
-    // tile k lives in buffer (k - i_first) % NBUF and completes phase (k - i_first) / NBUF of its barrier
     if (warp == 0) {
-        if (i_first < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)i_first * K1_TILE, 0, lane);
-        if (i_first + 1 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i_first + 1) * K1_TILE, 1, lane);
+        k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
+        if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
     }
 
     // Each role runs its own loop (own loop-carried registers); all of them meet once per iteration at
     // barrier 0 (bar.sync with the full CTA thread count is well defined from divergent code paths).
     if (warp < 4) {
         // ---------------- role A: proto, 5 outputs per lane ----------------
+        // (slot, tile-in-slot) of the tile being filtered and of the tile being fetched (two ahead), kept incrementally
+        int q = 0, t = 0, q2 = 2 / a.t_item, t2 = 2 % a.t_item;
+        K1Slot sl2 = k1_slot(a, min(q2, n_my - 1));
+        int64_t slot_gx = (int64_t)k1_slot(a, 0).O * 10;      // input index of the current slot's first sample
         for (int i = 0; i < n_iter; ++i) {
-            if (i >= i_first && i < n_load) {
-                const int k = i - i_first;
-                // producer: tile k+2 goes into the buffer tile k-1 just left (its tail is already copied)
-                if (warp == 0 && i + 2 < n_load) k1_issue_tile(s, a, xc, gx_origin + (int64_t)(i + 2) * K1_TILE, k + 2, lane);
+            if (i < n_load) {
+                // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
+                if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
+                if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
                 const int L5 = tid;                            // 0..127
-                mbar_wait(&s.full[k % K1_NBUF], (uint32_t)((k / K1_NBUF) & 1));
-                const float2* buf = &s.in[k % K1_NBUF][0];
-                const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
-                float2 acc[5];
+                const int64_t gx0 = slot_gx + (int64_t)t * K1_TILE;
+                if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
+                mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
+                if (gx0 < a.n && gx0 + K1_TILE > 0) {          // tiles entirely outside the block carry nothing
+                    const float2* buf = &s.in[i % K1_NBUF][0];
+                    const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
+                    float2 acc[5];
 #pragma unroll
-                for (int g = 0; g < 5; ++g) acc[g] = make_float2(0.f, 0.f);
+                    for (int g = 0; g < 5; ++g) acc[g] = make_float2(0.f, 0.f);
 #pragma unroll
-                for (int t2 = 0; t2 < 41; ++t2) {
-                    const float4 v = p4[t2];
+                    for (int t2 = 0; t2 < 41; ++t2) {
+                        const float4 v = p4[t2];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int t = 2 * t2 + h;
-                        const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                        for (int h = 0; h < 2; ++h) {
+                            const int tt = 2 * t2 + h;
+                            const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
 #pragma unroll
-                        for (int g = 0; g < 5; ++g) {
-                            const int d = t - 10 * g;
-                            if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                            for (int g = 0; g < 5; ++g) {
+                                const int d = tt - 10 * g;
+                                if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                            }
                         }
                     }
-                }
-                const int wbase = K1_W * i + K1_A0 + 5 * L5;
-                if (MODE == 1) {                            // frequency_shift at the decimated rate (processor.py:259-261)
+                    const int wbase = K1_W * i + K1_A0 + 5 * L5;
+                    if (MODE == 1) {                        // frequency_shift at the decimated rate (processor.py:259-261)
 #pragma unroll
-                    for (int g = 0; g < 5; ++g) {
-                        const float2 p = sf.ph[i & 1][5 * L5 + g];
-                        acc[g] = make_float2(acc[g].x * p.x - acc[g].y * p.y, acc[g].x * p.y + acc[g].y * p.x);
+                        for (int g = 0; g < 5; ++g) {
+                            const float2 p = sf.ph[i & 1][5 * L5 + g];
+                            acc[g] = make_float2(acc[g].x * p.x - acc[g].y * p.y, acc[g].x * p.y + acc[g].y * p.x);
+                        }
                     }
-                }
 #pragma unroll
-                for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
-                // tail of this tile -> header of the next buffer
-                if (L5 < K1_HDR) s.in[(k + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
+                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
+                    // tail of this tile -> header of the next buffer
+                    if (L5 < K1_HDR) s.in[(i + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
+                }
             }
             k1_bar_sync();
         }
@@ -330,16 +356,26 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         float2 cacc[10];                                    // outputs of the group in flight
 #pragma unroll
         for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
+        // slot of stream coordinate 640 i + 2 C0 + PREROLL (the kept outputs of group i), kept incrementally (MODE 1)
+        int qc = k1_floordiv(2 * K1_C0 + K1_PREROLL, S), rc = 2 * K1_C0 + K1_PREROLL - qc * S;
         for (int i = 0; i < n_iter; ++i) {
             const int q = (i - (warp - 4)) & 3;             // this warp's group is g = i - q
-            const int nu0 = K1_U * (i - q) + K1_C0 + 10 * lane;   // first output (local v index), even
+            const int nu0 = K1_U * (i - q) + K1_C0 + 10 * lane;   // first output (stream v index), even
             const int s0 = nu0 - 64 + 32 * q;               // first input sample of this quarter, even
             if (q == 0) {
 #pragma unroll
                 for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
             }
-            if (MODE == 1) k1_fir_quarter_cplx(s.u, s0, sf.ctap + 32 * q, cacc);
-            else k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
+            if (MODE == 1) {
+                // taps of the slot this group's kept outputs belong to (two slots can be in flight in stage C)
+                // group g = i - q lies q iterations back: at most one slot back (a slot is >= 6 iterations long)
+                const int qs = min(max(rc - K1_W * q < 0 ? qc - 1 : qc, 0), n_my - 1);
+                k1_fir_quarter_cplx(s.u, s0, sf.ctap[qs & 1] + 32 * q, cacc);
+                rc += K1_W;
+                if (rc >= S) { rc -= S; ++qc; }
+            } else {
+                k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
+            }
             if (q == 3) {
 #pragma unroll
                 for (int r = 0; r < 10; r += 2)
@@ -351,6 +387,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     } else if (warp < 10) {
         // ---------------- role B: half-band /2, 5 outputs per lane ----------------
         const int lb = tid - 256;                           // 0..63
+        int qn = 1 / a.t_item, tn = 1 % a.t_item;           // (slot, tile) of the tile stage A filters next iteration
+        K1Slot sn = k1_slot(a, qn);
         for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
             float2 acc[5];
@@ -369,20 +407,62 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
 #pragma unroll
             for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
-            if (MODE == 1)                                  // phasors for the w samples stage A produces next iteration
-                k1_phasors10(fo_hz, a.fs_dec, (int64_t)O + K1_W * (i + 1) + K1_A0 + 10 * lb, &sf.ph[(i + 1) & 1][10 * lb]);
+            if (MODE == 1 && i + 1 < n_load) {
+                // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
+                // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
+                k1_phasors10(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_W * tn + K1_A0 + 10 * lb, &sf.ph[(i + 1) & 1][10 * lb]);
+                if (tn == 0) {
+                    sf.ctap[qn & 1][2 * lb] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb];
+                    sf.ctap[qn & 1][2 * lb + 1] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb + 1];
+                }
+                if (++tn == a.t_item) { tn = 0; ++qn; if (qn < n_my) sn = k1_slot(a, qn); }
+            }
             k1_bar_sync();
         }
     } else {
         // ---------------- role D: x2 interpolation, store, power sums per timing phase ----------------
         const int ld = tid - 320;                           // 0..63
-        float2* yc = a.y + (int64_t)car * a.y_pitch;
         double pacc[K1_NPH];                                // |y|^2 sums, pacc[j] <-> phase (n0 + j) % 13
 #pragma unroll
         for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
+        int q_cur = -1;                                     // slot the sums belong to (-1: none yet)
+        K1Slot sl = {0, 0, 0, 0};
+        int y_lo = 0, y_hi = 0;
+        float2* yc = a.y;
+        // hand the sums of slot q_cur to `partial`; i = iteration about to run (the rotations so far make slot j of
+        // pacc mean phase (n0 + j) % 13 with n0 this thread's first output of iteration i under the OLD slot)
+        auto flush = [&](int i) {
+            const int n0 = K1_W * i + 2 * K1_D0 + 10 * ld - q_cur * S + sl.O;
+            const int base = ((n0 % K1_NPH) + K1_NPH) % K1_NPH;
+#pragma unroll
+            for (int j = 0; j < K1_NPH; ++j) s.bins[(base + j) % K1_NPH][ld] = pacc[j];
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+            if (ld < K1_NPH) {
+                double t = 0.0;
+                for (int j = 0; j < K1_DLANES; ++j) t += s.bins[ld][j];
+                a.partial[((int64_t)blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
+            }
+            asm volatile("bar.sync 2, 64;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
+        };
+        // every output an iteration keeps lies in the slot of stream coordinate 640 i + 2 D0 + PREROLL (kept outputs
+        // are PREROLL away from slot ends); that slot index is kept incrementally
+        int q_it = k1_floordiv(2 * K1_D0 + K1_PREROLL, S), r_it = 2 * K1_D0 + K1_PREROLL - q_it * S;
         for (int i = 0; i < n_iter; ++i) {
-            const int nu0 = K1_U * i + K1_D0 + 5 * ld;      // local v index of first output pair
-            const int n0 = O + 2 * nu0;                     // global y index of the first output (even)
+            if (q_it != q_cur) {
+                if (q_cur >= 0 && q_cur < n_my) flush(i);
+                q_cur = q_it;
+                if (q_cur >= 0 && q_cur < n_my) {
+                    sl = k1_slot(a, q_cur);
+                    y_lo = max(sl.n_lo, K1_EDGE); y_hi = min(sl.n_hi, a.L - K1_EDGE);
+                    yc = a.y + (int64_t)sl.car * a.y_pitch;
+                } else {
+                    y_lo = y_hi = 0;
+                }
+            }
+            const int nu0 = K1_U * i + K1_D0 + 5 * ld;      // stream v index of the first output pair
+            const int n0 = 2 * nu0 - q_cur * S + sl.O;      // y index of the first output within the carrier (even)
             if (n0 + 10 > y_lo && n0 < y_hi) {
                 float2 v[5 + 2 * TB_INT_K - 1];             // v[nu0-7 .. nu0+4+8]
 #pragma unroll
@@ -423,19 +503,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 for (int j = 0; j < K1_NPH - 3; ++j) pacc[j] = pacc[j + 3];
                 pacc[10] = t0; pacc[11] = t1; pacc[12] = t2;
             }
+            r_it += K1_W;
+            if (r_it >= S) { r_it -= S; ++q_it; }
             k1_bar_sync();
         }
-        // after n_iter rotations slot j means phase (n0 + j) % 13 with n0 taken for iteration n_iter
-        const int n0e = O + 2 * (K1_U * n_iter + K1_D0 + 5 * ld);
-        const int base = ((n0e % K1_NPH) + K1_NPH) % K1_NPH;
-#pragma unroll
-        for (int j = 0; j < K1_NPH; ++j) s.bins[(base + j) % K1_NPH][ld] = pacc[j];
-    }
-    __syncthreads();
-    if (tid < K1_NPH) {
-        double t = 0.0;
-        for (int j = 0; j < K1_DLANES; ++j) t += s.bins[tid][j];
-        a.partial[((int64_t)car * a.n_seg + seg) * 16 + tid] = t;
+        if (q_cur >= 0 && q_cur < n_my) flush(n_iter);
     }
 }
 
