@@ -141,7 +141,7 @@ void fill_coef(ExactCoef& cf, int q, double wn) {
 void exact_extents(int mode, int64_t n, int64_t L, int q, int E, bool has_s1, int64_t* w1, int64_t* wz) {
     int64_t m_lo = 0, m_hi = L;
     if (mode == EX_LEFT) m_hi = std::min<int64_t>(L, E + EX_T2);
-    else if (mode == EX_RIGHT) m_lo = std::max<int64_t>(0, L - E - 2 * EX_T2);
+    else if (mode == EX_RIGHT) m_lo = std::max<int64_t>(0, L - E - EX_T2);
     *wz = m_hi - m_lo;
     if (!has_s1) { *w1 = 1; return; }
     int64_t tot = n + 2 * EX_PAD1, e_lo = 0, e_hi = tot;

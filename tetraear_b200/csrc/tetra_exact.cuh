@@ -12,7 +12,9 @@ namespace tetra {
 
 constexpr int EX_PAD1 = 27;   // sosfiltfilt: 3 * (2*n_sections + 1), n_sections = 4
 constexpr int EX_PAD2 = 15;   // filtfilt: 3 * max(len(a), len(b)) = 3 * 5
-constexpr int EX_T1 = 1024;   // warm-up of an approximate start/end, stage 1 (pole radius 0.9821 -> 9e-9)
+// Warm-up of an approximate start / end. What reaches a kept output has crossed the stage-1 warm-up AND the EX_T2
+// stage-2 samples between the window end and the kept range (0.8837^160 = 3e-9), so stage 1 needs little of its own.
+constexpr int EX_T1 = 256;    // stage 1 (pole radius 0.9821 per input sample)
 constexpr int EX_T2 = 160;    // same for stage 2 (pole radius 0.8837 -> 3e-9)
 constexpr int EX_U = 8;       // recursion steps per load group
 constexpr int K_EDGE = 160;   // outputs per block end owned by the exact path (= K1_EDGE)
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
     // ranges: z indices [m_lo, m_hi) are produced by stage 1, outputs [o_lo, o_hi) by stage 2
     int m_lo = 0, m_hi = L, o_lo = 0, o_hi = L;
     if (mode == EX_LEFT) { o_hi = min(L, E); m_hi = min(L, E + EX_T2); }
-    else if (mode == EX_RIGHT) { o_lo = max(0, L - E); m_lo = max(0, L - E - 2 * EX_T2); }
+    else if (mode == EX_RIGHT) { o_lo = max(0, L - E); m_lo = max(0, L - E - EX_T2); }
 
     auto xat = [&](int64_t i) { return ex_load(a, xb, i); };
     const double w_nco = a.fo ? (2.0 * M_PI) * a.fo[car] : 0.0;
@@ -353,7 +355,7 @@ __global__ void __launch_bounds__(EXT_THREADS) k_exact_edges(const EdgeArgs a) {
     const int64_t n = a.n;
     int m_lo = 0, m_hi = L, o_lo = 0, o_hi = L;
     if (mode == EX_LEFT) { o_hi = min(L, E); m_hi = min(L, E + EX_T2); }
-    else { o_lo = max(0, L - E); m_lo = max(0, L - E - 2 * EX_T2); }
+    else { o_lo = max(0, L - E); m_lo = max(0, L - E - EX_T2); }
     const int64_t tot = n + 2 * EX_PAD1;
     int64_t e_lo = 0, e_hi = tot;
     if (mode == EX_LEFT) e_hi = min(tot, (int64_t)EX_PAD1 + (int64_t)q * (m_hi - 1) + 1 + EX_T1);
@@ -498,7 +500,7 @@ __host__ __device__ inline EdgeRange edge_range(int mode, int64_t n, int L, int 
     EdgeRange r;
     r.m_lo = 0; r.m_hi = L; r.o_lo = 0; r.o_hi = L;
     if (mode == EX_LEFT) { r.o_hi = L < E ? L : E; r.m_hi = L < E + EX_T2 ? L : E + EX_T2; }
-    else { r.o_lo = L - E > 0 ? L - E : 0; r.m_lo = L - E - 2 * EX_T2 > 0 ? L - E - 2 * EX_T2 : 0; }
+    else { r.o_lo = L - E > 0 ? L - E : 0; r.m_lo = L - E - EX_T2 > 0 ? L - E - EX_T2 : 0; }
     const int64_t tot = n + 2 * EX_PAD1;
     r.e_lo = 0; r.e_hi = tot;
     if (mode == EX_LEFT) { const int64_t v = (int64_t)EX_PAD1 + (int64_t)q * (r.m_hi - 1) + 1 + EX_T1; r.e_hi = v < tot ? v : tot; }
