@@ -199,7 +199,7 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
     CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
     EdgeArgs g;
     g.x = ea.x32; g.pitch = ea.pitch; g.n = ea.n; g.q = ea.q; g.L = ea.L; g.edge = ea.edge; g.cf = ea.cf;
-    g.y = ea.y32; g.y_pitch = ea.y_pitch; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
+    g.y = ea.y32; g.y_pitch = ea.y_pitch; g.y_sps = ea.y_sps; g.y_rows = ea.y_rows; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
     g.scr1 = (double2*)ctx->scr1.p; g.scrz = (double2*)ctx->scrz.p; g.scr2 = (double2*)ctx->scr2.p;
     g.w1 = w1; g.wz = wz; g.fo = ea.fo; g.fs_dec = ea.fs_dec;
     k_exact_edges<<<(int)((nj + EXT_THREADS - 1) / EXT_THREADS), EXT_THREADS, 0, st>>>(g);
@@ -286,7 +286,7 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
     CK(cudaMemcpyAsync(ctx->mats.p, ctx->edge_mats.data(), ctx->edge_mats.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     EdgeWarpArgs g;
     g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
-    g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
+    g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.y_sps = ea.y_sps; g.e.y_rows = ea.y_rows; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
     g.e.scr1 = (double2*)ctx->scr1.p; g.e.scrz = (double2*)ctx->scrz.p; g.e.scr2 = (double2*)ctx->scr2.p;
     g.e.w1 = w1; g.e.wz = wz; g.e.fo = ea.fo; g.e.fs_dec = ea.fs_dec;
     g.m1 = (const double*)ctx->mats.p;
@@ -471,7 +471,10 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     }
 
     // ---- buffers ----
-    const int64_t y_pitch = (pl.L + 63) & ~(int64_t)63;
+    // y is stored timing-phase major (y_index): sps rows of y_rows samples
+    const int y_sps = pl.sps > 1 ? pl.sps : 1;
+    const int y_rows = pl.sps > 1 ? (int)((((pl.L + y_sps - 1) / y_sps) + 15) & ~(int64_t)15) : 0;
+    const int64_t y_pitch = y_rows > 0 ? (int64_t)y_sps * y_rows : ((pl.L + 63) & ~(int64_t)63);
     CK(ctx->y.ensure((size_t)C * y_pitch * sizeof(float2)));
     CK(ctx->phase.ensure(sizeof(int32_t) * C));
     uint8_t* k_dib = d_dib ? dibits : nullptr;
@@ -491,11 +494,11 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     ea.has_s1 = pl.has_s1; ea.has_s2 = pl.has_s2;
     fill_coef(ea.cf, pl.has_s1 ? pl.q : 1, pl.wn);
     ea.fo = d_fo; ea.fs_dec = pl.rate;
-    ea.y32 = (float2*)ctx->y.p; ea.y_pitch = y_pitch; ea.edge = K1_EDGE;
+    ea.y32 = (float2*)ctx->y.p; ea.y_pitch = y_pitch; ea.y_sps = y_sps; ea.y_rows = y_rows; ea.edge = K1_EDGE;
 
     FinArgs fa;
     memset(&fa, 0, sizeof fa);
-    fa.y = (const float2*)ctx->y.p; fa.y_pitch = y_pitch; fa.L = (int32_t)pl.L; fa.sps = pl.sps; fa.step = pl.step;
+    fa.y = (const float2*)ctx->y.p; fa.y_pitch = y_pitch; fa.y_rows = y_rows; fa.L = (int32_t)pl.L; fa.sps = pl.sps; fa.step = pl.step;
     fa.dibits = k_dib; fa.cap = cap; fa.n_dibits = k_nd; fa.symbols = k_sym; fa.best_phase = k_ph;
     fa.phase_scratch = (int32_t*)ctx->phase.p;
 
@@ -524,7 +527,7 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(ctx->partial.ensure((size_t)C * n_seg * 16 * sizeof(double)));
         K1Args ka;
         ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg; ka.n_items = n_items; ka.t_item = std::max(seg_len / K1_W + 1, K1_MIN_T_ITEM);
-        ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.partial = (double*)ctx->partial.p;
+        ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.y_rows = y_rows; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
         ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate;
         if (any_fo) {

@@ -22,6 +22,13 @@ constexpr int K_EDGE_MAX_S2 = K_EDGE + 2 * EX_T2 + 2 * EX_PAD2;   // longest sta
 
 enum { EX_FULL = 0, EX_LEFT = 1, EX_RIGHT = 2 };
 
+// Layout of the filtered 240 kS/s stream y of one carrier in HBM: timing-phase major, y[(n % sps) * rows + n / sps],
+// so that the symbols of the phase the timing pick chooses (every sps-th sample, processor.py:213-215) are contiguous.
+// rows == 0 means natural order.
+__host__ __device__ inline int64_t y_index(int64_t n, int sps, int rows) {
+    return rows > 0 ? (n % sps) * (int64_t)rows + n / sps : n;
+}
+
 struct ExactCoef {
     double sos[4][6];
     double zi1[4][2];
@@ -39,6 +46,7 @@ struct ExactArgs {
     ExactCoef cf;
     const double* fo;        // [C] freq offsets (device) or null
     double fs_dec;           // sample rate after stage 1
+    int32_t y_sps, y_rows;   // layout of y32 (y_index); y64 is always in natural order
     float2* y32;             // output [C][y_pitch] (complex64) ...
     double2* y64;            // ... or complex128
     int64_t y_pitch;
@@ -225,7 +233,7 @@ __global__ void __launch_bounds__(64) k_exact_chain(const ExactArgs a) {
     // ---------------- stage 2: filtfilt(b, a) ----------------
     auto zat = [&](int64_t m) { return a.scrz[(m - m_lo) * nj + j]; };
     auto put = [&](int m, double2 v) {
-        if (a.y32) a.y32[(int64_t)car * a.y_pitch + m] = make_float2((float)v.x, (float)v.y);
+        if (a.y32) a.y32[(int64_t)car * a.y_pitch + y_index(m, a.y_sps, a.y_rows)] = make_float2((float)v.x, (float)v.y);
         else a.y64[(int64_t)car * a.y_pitch + m] = v;
     };
     if (a.has_s2) {
@@ -285,8 +293,9 @@ struct EdgeArgs {
     int64_t pitch, n;
     int32_t q, L, edge;
     ExactCoef cf;
-    float2* y;               // [C][y_pitch]
+    float2* y;               // [C][y_pitch], layout y_index(n, y_sps, y_rows)
     int64_t y_pitch;
+    int32_t y_sps, y_rows;
     const int2* jobs;        // (carrier, mode), mode in {EX_LEFT, EX_RIGHT}
     int32_t n_jobs;
     double2* scr1;           // [n_jobs][w1] forward stage-1 output
@@ -483,7 +492,7 @@ __global__ void __launch_bounds__(EXT_THREADS) k_exact_edges(const EdgeArgs a) {
                 if (e - u >= f_stop) {
                     const double2 v = ba_step(bs, a.cf, g[u]);
                     const int64_t mm = e - u - EX_PAD2;
-                    if (mm >= o_lo && mm < o_hi) yc[mm] = make_float2((float)v.x, (float)v.y);
+                    if (mm >= o_lo && mm < o_hi) yc[y_index(mm, a.y_sps, a.y_rows)] = make_float2((float)v.x, (float)v.y);
                 }
             }
         }
@@ -745,7 +754,7 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
             [&](int s) { return s2[n2 - 1 - s]; },
             [&](int s, double2 v) {
                 const int64_t mm = f_hi - 1 - s - EX_PAD2;
-                if (mm >= o_lo && mm < o_hi) yc[mm] = make_float2((float)v.x, (float)v.y);
+                if (mm >= o_lo && mm < o_hi) yc[y_index(mm, a.y_sps, a.y_rows)] = make_float2((float)v.x, (float)v.y);
             });
     }
 }
@@ -758,8 +767,9 @@ constexpr int FIN_MAXPH = 32;
 constexpr int FIN_B = 8;                  // symbols per thread and batch in k_finalize
 
 struct FinArgs {
-    const float2* y;         // [C][y_pitch] filtered samples at the decimated rate
+    const float2* y;         // [C][y_pitch] filtered samples at the decimated rate, layout y_index(n, sps, y_rows)
     int64_t y_pitch;
+    int32_t y_rows;
     int32_t L;
     int32_t sps, step;       // samples per symbol, phase search step
     const double* partial;   // [C][n_seg][16] power sums of the bulk kernel (or null)
@@ -822,11 +832,11 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
             const int k_lo_end = has_bulk ? min(cnt, max(0, (a.bulk_lo - ph + sps - 1) / sps)) : cnt;
             const int k_hi_beg = has_bulk ? max(k_lo_end, (a.bulk_hi - ph + sps - 1) / sps) : cnt;
             for (int k = g; k < k_lo_end; k += G) {
-                const float2 v = y[ph + sps * k];
+                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
             for (int k = k_hi_beg + g; k < cnt; k += G) {
-                const float2 v = y[ph + sps * k];
+                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
         }
@@ -862,14 +872,16 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     float2* sym = a.symbols ? a.symbols + (int64_t)car * (a.cap + 1) : nullptr;
     const bool fuse = a.match != nullptr && nd <= FIN_DIB_SMEM;
     // symbols k = tid + 256 j, FIN_B of them per batch with all loads of a batch issued before any use
-    const float2* ys = y + best;
+    // symbol k is sample best + stride k: in the phase-major layout that is row `best`, contiguous in k
+    const float2* ys = a.y_rows > 0 ? y + (int64_t)best * a.y_rows : y + best;
+    const int64_t ks = a.y_rows > 0 ? 1 : stride;
     for (int k0 = tid; k0 < n_sym; k0 += FIN_B * FIN_THREADS) {
         float2 s1[FIN_B], s0[FIN_B];
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
             const int k = min(k0 + j * FIN_THREADS, n_sym - 1);
-            s1[j] = ys[(int64_t)stride * k];
-            s0[j] = ys[(int64_t)stride * max(k - 1, 0)];
+            s1[j] = ys[ks * k];
+            s0[j] = ys[ks * max(k - 1, 0)];
         }
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {

@@ -137,8 +137,9 @@ struct K1Args {
     int32_t n_seg;          // segments per carrier
     int32_t n_items;        // carriers * n_seg work items
     int32_t t_item;         // tiles per item = seg_len / 640 + 1 (pre-roll + post-roll)
-    float2* y;              // [C][y_pitch]
+    float2* y;              // [C][y_pitch], timing-phase major: y[(n % 13) * y_rows + n / 13]
     int64_t y_pitch;
+    int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x base/pitch allow 16-byte bulk copies
     // MODE 1 (freq_offset != 0) only
@@ -477,22 +478,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         o = ffma2(fadd2(v[r + TB_INT_K - 1 - k], v[r + TB_INT_K + k]), c_interp[k], o);
                     yv[2 * r + 1] = o;
                 }
+                // sample n goes to row n % 13, column n / 13 (kept incrementally over the ten outputs)
+                int col = n0 / K1_NPH, row = n0 - col * K1_NPH;
                 if (n0 >= y_lo && n0 + 10 <= y_hi) {        // the common case: all ten inside
 #pragma unroll
-                    for (int r = 0; r < 10; r += 2) {
-                        *reinterpret_cast<float4*>(yc + n0 + r) = make_float4(yv[r].x, yv[r].y, yv[r + 1].x, yv[r + 1].y);
+                    for (int r = 0; r < 10; ++r) {
+                        yc[(int64_t)row * a.y_rows + col] = yv[r];
+                        if (++row == K1_NPH) { row = 0; ++col; }
                         // |y|^2 in fp32 (y itself is fp32), accumulated in fp64; slot r <-> phase (n0 + r) % 13
                         pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
-                        pacc[r + 1] += (double)fmaf(yv[r + 1].x, yv[r + 1].x, yv[r + 1].y * yv[r + 1].y);
                     }
                 } else {
 #pragma unroll
                     for (int r = 0; r < 10; ++r) {
                         const int n = n0 + r;
                         if (n >= y_lo && n < y_hi) {
-                            yc[n] = yv[r];
+                            yc[(int64_t)row * a.y_rows + col] = yv[r];
                             pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
                         }
+                        if (++row == K1_NPH) { row = 0; ++col; }
                     }
                 }
             }
