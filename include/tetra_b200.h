@@ -72,6 +72,23 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int
                         float* symbols, int32_t* best_phase, uint8_t* ts_match, int32_t async);
 
 /*
+ * tetra_process_batch plus the frame-sync front end of TetraDecoder.decode (core/decoder.py:835-857) on the
+ * device: bit expansion, find_sync at 0.90 / 0.85 / 0.80 / adaptive with the reference's visiting order
+ * (jump +250 after a hit, max_corr over visited offsets only, in-function adaptive retry).
+ *   sync_pos  [C][max_positions] int32 bit offsets, ascending; host or device
+ *   n_sync    [C] int32 number of positions found (same residency as sync_pos)
+ * max_positions must be at least 2*cap/250 + 2. Frame start = position - 216 bits (decoder.py:865).
+ */
+int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int64_t n_samples,
+                             int64_t pitch, const double* freq_offset_hz,
+                             uint8_t* dibits, int64_t cap, int32_t* n_dibits,
+                             float* symbols, int32_t* best_phase, uint8_t* ts_match,
+                             int32_t* sync_pos, int32_t max_positions, int32_t* n_sync, int32_t async);
+/* The same cascade for dibit streams that are already there ([C][cap] uint8 + lengths; host or device). */
+int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits,
+                         int32_t n_carriers, int32_t* sync_pos, int32_t max_positions, int32_t* n_sync);
+
+/*
  * BASELINE config 3 -- C channels out of ONE wideband capture: for every channel centre f_c (Hz, relative
  * to the capture centre) the composition  process(frequency_shift(iq, f_c, sample_rate), 0)  of the
  * reference's own methods (signal/processor.py:85-100 and :221-273). The reference has no channelizer; its

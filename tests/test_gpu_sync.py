@@ -1,0 +1,82 @@
+"""GPU: TetraDecoder.find_sync + decode()'s threshold cascade on the device against the oracle,
+whose find_sync is pinned to the reference's own outputs by the golden fixtures (tests/test_oracle.py)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, golden_input
+from cases import CASES
+from oracle import ref_dsp
+from tetraear_b200 import sync
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits_to_dibits(bits):
+    bits = np.asarray(bits, dtype=np.uint8)
+    assert len(bits) % 2 == 0
+    return (bits[0::2] << 1 | bits[1::2]).astype(np.uint8)
+
+
+def _planted(rng, n_bits, plants):
+    """random bits with TS1/TS2 copies (pattern, bit offset, number of flipped bits) planted in"""
+    bits = rng.integers(0, 2, size=n_bits).astype(np.int64)
+    for pat, off, n_err in plants:
+        p = (ref_dsp.TS1 if pat == 1 else ref_dsp.TS2).copy()
+        if n_err:
+            p[rng.choice(22, size=n_err, replace=False)] ^= 1
+        bits[off:off + 22] = p
+    return bits
+
+
+def test_sync_positions_match_oracle_on_crafted_streams(gpu_processor):
+    sp = gpu_processor
+    rng = np.random.default_rng(5)
+    cases = [
+        [],                                                        # nothing planted: adaptive path on random bits
+        [(1, 20, 0)],                                              # the reference unit test's plant
+        [(1, 21, 0), (2, 600, 0), (1, 5001, 1)],                   # odd offsets, both patterns, 0.90 level
+        [(2, 100, 3)],                                             # 19/22: found at 0.85
+        [(1, 300, 4)],                                             # 18/22: found at 0.80
+        [(1, 1000, 5), (2, 4000, 5)],                              # 17/22: only the adaptive pass
+        [(1, 50, 0), (1, 200, 0), (2, 299, 0), (1, 300, 0)],       # closer than 250: skipped by the jump
+        [(1, 16130 - 22, 0)],                                      # last window
+        [(1, 10, 2), (2, 10 + 250, 2), (1, 10 + 499, 2), (2, 9000, 1)],
+    ]
+    n_bits = 16130
+    streams = np.stack([_bits_to_dibits(_planted(rng, n_bits, pl)) for pl in cases])
+    got = sp.sync_positions(streams)
+    for c, pl in enumerate(cases):
+        bits = ref_dsp.symbols_to_bits(streams[c])
+        assert got[c] == ref_dsp.sync_cascade(bits), (c, pl)
+
+
+def test_sync_positions_ragged_and_tiny(gpu_processor):
+    sp = gpu_processor
+    rng = np.random.default_rng(6)
+    cap = 4000
+    d = rng.integers(0, 4, size=(5, cap), dtype=np.uint8)
+    nd = np.array([4000, 0, 5, 11, 1234], dtype=np.int32)           # 0, 10 and 22 bits: nothing / one window
+    d[3, :11] = _bits_to_dibits(ref_dsp.TS2)
+    got = sp.sync_positions(d, nd)
+    for c in range(5):
+        bits = ref_dsp.symbols_to_bits(d[c, :nd[c]])
+        assert got[c] == ref_dsp.sync_cascade(bits), c
+    assert got[3] == [0]
+
+
+@pytest.mark.parametrize("name,gen,n,fs,fo", [c for c in CASES if c[2] >= 16384 and c[3] == 2.4e6], ids=lambda v: v if isinstance(v, str) else None)
+def test_process_batch_sync_matches_reference_cascade(gpu_processor, name, gen, n, fs, fo):
+    sp = gpu_processor
+    sp.sample_rate = fs
+    g = load_golden(name)
+    x = golden_input(g, **gen)
+    res = sp.process_batch(x[None, :], [fo], want_symbols=False, want_match=True, want_sync=True)
+    nd = int(res["n_dibits"][0])
+    bits = ref_dsp.symbols_to_bits(g["dibits"])
+    want = ref_dsp.sync_cascade(bits)
+    got = [int(p) for p in res["sync_pos"][0, : res["n_sync"][0]]]
+    assert got == want
+    # the device cascade and the host replay over the device's match counts agree
+    assert got == sync.sync_cascade(res["ts_match"][0], nd)
+    assert sync.burst_slices(got, nd) == [(p - 216) // 2 and ((p - 216) // 2, p - 216, (p - 216) // 510) for p in got
+                                          if p - 216 >= 0 and (p - 216) // 2 + 255 <= nd]

@@ -62,7 +62,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
@@ -336,7 +336,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -407,7 +407,16 @@ int tetra_last_phase_ms(tetra_ctx* ctx, double* out3) {
 int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                         uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
                         uint8_t* ts_match, int32_t async) {
+    return tetra_process_batch_sync(ctx, iq, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match,
+                                    nullptr, 0, nullptr, async);
+}
+
+int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                             uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                             uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async) {
     if (!ctx) return TETRA_E_INVALID;
+    if ((sync_pos != nullptr) != (n_sync != nullptr) || (sync_pos && max_pos <= 0))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_sync: sync_pos, n_sync and max_positions go together");
     if (C < 0 || N < 0 || (C > 0 && N > 0 && (!iq || pitch < N)) || !n_dibits || (cap > 0 && !dibits) || cap < 0)
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: bad arguments");
     if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: at most 65535 carriers per call");
@@ -417,8 +426,11 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     cudaStream_t st = ctx->stream;
     const bool d_in = is_device_ptr(iq), d_dib = is_device_ptr(dibits), d_nd = is_device_ptr(n_dibits);
     const bool d_sym = is_device_ptr(symbols), d_ph = is_device_ptr(best_phase), d_match = is_device_ptr(ts_match);
-    if (async && !(d_in && (d_dib || !dibits) && d_nd && (d_sym || !symbols) && (d_ph || !best_phase) && (d_match || !ts_match)))
+    const bool d_spos = is_device_ptr(sync_pos), d_nsync = is_device_ptr(n_sync);
+    if (async && !(d_in && (d_dib || !dibits) && d_nd && (d_sym || !symbols) && (d_ph || !best_phase) && (d_match || !ts_match) &&
+                   (!sync_pos || (d_spos && d_nsync))))
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: async needs device buffers");
+    if (sync_pos && d_spos != d_nsync) return fail(ctx, TETRA_E_INVALID, "sync_pos and n_sync must both be host or both device");
 
     const Plan pl = make_plan(ctx->sample_rate, N);
     const int64_t need_cap = tetra_dibit_capacity(ctx, N);
@@ -426,6 +438,7 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (N == 0 || pl.L <= 0) {      // processor.py:239-241: empty in -> empty out
         if (d_nd) CK(cudaMemsetAsync(n_dibits, 0, sizeof(int32_t) * C, st)); else memset(n_dibits, 0, sizeof(int32_t) * C);
         if (best_phase) { if (d_ph) CK(cudaMemsetAsync(best_phase, 0, sizeof(int32_t) * C, st)); else memset(best_phase, 0, sizeof(int32_t) * C); }
+        if (n_sync) { if (d_nsync) CK(cudaMemsetAsync(n_sync, 0, sizeof(int32_t) * C, st)); else memset(n_sync, 0, sizeof(int32_t) * C); }
         return TETRA_OK;
     }
     if (pl.sps > 1 && (pl.sps + pl.step - 1) / pl.step > FIN_MAXPH)
@@ -487,6 +500,17 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (symbols && !d_sym) { CK(ctx->sym.ensure((size_t)C * (cap + 1) * sizeof(float2))); k_sym = (float2*)ctx->sym.p; }
     if (best_phase && !d_ph) k_ph = (int32_t*)ctx->phase.p;
     if (ts_match && !d_match) { CK(ctx->match.ensure((size_t)C * cap * 4 + 16)); k_match = (uint8_t*)ctx->match.p; }
+    int32_t* k_spos = d_spos ? sync_pos : nullptr;
+    int32_t* k_nsync = d_nsync ? n_sync : nullptr;
+    if (sync_pos) {
+        // max_corr bookkeeping needs every position: the walk finds at most one per 250 bit offsets
+        if ((int64_t)max_pos < (2 * cap) / 250 + 2) return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
+        if (!d_spos) {
+            CK(ctx->spos.ensure((size_t)C * max_pos * sizeof(int32_t) + sizeof(int32_t) * C));
+            k_spos = (int32_t*)ctx->spos.p;
+            k_nsync = k_spos + (size_t)C * max_pos;
+        }
+    }
 
     ExactArgs ea;
     memset(&ea, 0, sizeof ea);
@@ -584,6 +608,9 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (ctx->timing && use_fast && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[2], st));
     const bool fused_match = ts_match && cap > 0 && cap <= FIN_DIB_SMEM;
     fa.match = fused_match ? k_match : nullptr;
+    const bool fused_sync = sync_pos && cap <= FIN_DIB_SMEM;
+    fa.sync_pos = fused_sync ? k_spos : nullptr; fa.max_pos = max_pos; fa.n_sync = k_nsync;
+    if (sync_pos && !fused_sync) return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
     k_finalize<<<C, FIN_THREADS, 0, st>>>(fa);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -601,6 +628,10 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (symbols && !d_sym) CK(cudaMemcpyAsync(symbols, k_sym, (size_t)C * (cap + 1) * sizeof(float2), cudaMemcpyDeviceToHost, st));
     if (best_phase && !d_ph) CK(cudaMemcpyAsync(best_phase, k_ph, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
     if (ts_match && !d_match) CK(cudaMemcpyAsync(ts_match, k_match, (size_t)C * cap * 4, cudaMemcpyDeviceToHost, st));
+    if (sync_pos && !d_spos) {
+        CK(cudaMemcpyAsync(sync_pos, k_spos, (size_t)C * max_pos * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(n_sync, k_nsync, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+    }
     if (!async) CK(cudaStreamSynchronize(st));
     return TETRA_OK;
 }
@@ -625,12 +656,52 @@ int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const dou
     CK(ctx->fo.ensure(sizeof(double) * C));
     CK(cudaMemcpyAsync(ctx->fo.p, channel_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
     CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
-    k_mix_wide<<<dim3((unsigned)std::min<int64_t>((N + 255) / 256, 1024), C), 256, 0, st>>>(dx, N, (const double*)ctx->fo.p,
+    k_mix_wide<<<dim3((unsigned)std::min<int64_t>((N + 256 * MIX_RUN - 1) / (256 * MIX_RUN), 1024), C), 256, 0, st>>>(dx, N, (const double*)ctx->fo.p,
                                                                                             ctx->sample_rate, (float2*)ctx->wide.p);
     ctx->launches++;
     CK(cudaGetLastError());
     // every channel is now an ordinary carrier at baseband: process(shifted, 0)
     return tetra_process_batch(ctx, (const float*)ctx->wide.p, C, N, N, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, 0);
+}
+
+int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits, int32_t C,
+                         int32_t* sync_pos, int32_t max_pos, int32_t* n_sync) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || cap < 0 || (C > 0 && (!dibits || !n_dibits || !sync_pos || !n_sync)) || max_pos <= 0)
+        return fail(ctx, TETRA_E_INVALID, "tetra_sync_positions: bad arguments");
+    if (C == 0) return TETRA_OK;
+    if (cap > FIN_DIB_SMEM) return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
+    if ((int64_t)max_pos < (2 * cap) / 250 + 2) return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool dev_in = is_device_ptr(dibits), dev_nd = is_device_ptr(n_dibits), dev_out = is_device_ptr(sync_pos);
+    if (dev_out != is_device_ptr(n_sync)) return fail(ctx, TETRA_E_INVALID, "sync_pos and n_sync must both be host or both device");
+    SyncPosArgs a;
+    a.dibits = dibits; a.cap = cap; a.n_dibits = n_dibits; a.sync_pos = sync_pos; a.max_pos = max_pos; a.n_sync = n_sync;
+    if (!dev_in) {
+        CK(ctx->dib.ensure((size_t)C * cap + 16));
+        CK(cudaMemcpyAsync(ctx->dib.p, dibits, (size_t)C * cap, cudaMemcpyHostToDevice, st));
+        a.dibits = (const uint8_t*)ctx->dib.p;
+    }
+    if (!dev_nd) {
+        CK(ctx->ndib.ensure(sizeof(int32_t) * C));
+        CK(cudaMemcpyAsync(ctx->ndib.p, n_dibits, sizeof(int32_t) * C, cudaMemcpyHostToDevice, st));
+        a.n_dibits = (const int32_t*)ctx->ndib.p;
+    }
+    if (!dev_out) {
+        CK(ctx->spos.ensure((size_t)C * max_pos * sizeof(int32_t) + sizeof(int32_t) * C));
+        a.sync_pos = (int32_t*)ctx->spos.p;
+        a.n_sync = a.sync_pos + (size_t)C * max_pos;
+    }
+    k_sync_positions<<<C, FIN_THREADS, 0, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (!dev_out) {
+        CK(cudaMemcpyAsync(sync_pos, a.sync_pos, (size_t)C * max_pos * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(n_sync, a.n_sync, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -782,6 +782,9 @@ struct FinArgs {
     int32_t* best_phase;     // [C] or null
     int32_t* phase_scratch;  // [C] always written (used by later kernels)
     uint8_t* match;          // [C][2*cap][2] or null: TS1/TS2 agreement counts, fused when cap <= FIN_DIB_SMEM
+    int32_t* sync_pos;       // [C][max_pos] or null: sync positions of decode()'s cascade (decoder.py:845-856)
+    int32_t max_pos;
+    int32_t* n_sync;         // [C]
 };
 
 constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22 (decoder.py:196-197)
@@ -807,11 +810,152 @@ __device__ __forceinline__ uint8_t slice_dqpsk(double re, double im) {
     return im <= kr ? 2 : 3;                 // ph >= -5pi/8  <=>  -im >= k |re|  <=>  im <= k re
 }
 
+// ----------------------------------------------------------------------------------------------
+// TetraDecoder.find_sync (core/decoder.py:171-295) and the threshold cascade of decode() (:845-856) for one
+// carrier, by all FIN_THREADS threads of a CTA, from the MSB-first packed bit stream in shared memory.
+// The reference walks every bit offset serially (jump +250 after a hit, max_corr over the visited offsets only,
+// adaptive retry when nothing was found). Here the hits of a pass become a bit mask in parallel, one thread walks
+// the mask (a handful of jumps), and the maximum over the visited offsets is a parallel reduction.
+// ----------------------------------------------------------------------------------------------
+struct SyncScratch {
+    uint32_t mask[FIN_DIB_SMEM / 16 + 2];   // one bit per window start
+    int n_pos, max_cnt;
+};
+
+__device__ __forceinline__ void ts_counts(const uint32_t* __restrict__ bits, int i, int& c1, int& c2) {
+    const uint64_t two = ((uint64_t)bits[i >> 5] << 32) | bits[(i >> 5) + 1];
+    const uint32_t win = (uint32_t)(two >> (64 - 22 - (i & 31))) & 0x3FFFFFu;
+    c1 = 22 - __popc(win ^ TS1_BITS);
+    c2 = 22 - __popc(win ^ TS2_BITS);
+}
+// smallest agreement count c with c / 22 >= threshold, in the reference's own float64 comparison (23: none)
+__device__ __forceinline__ int sync_min_count(double thr) {
+    int c = 0;
+    while (c <= 22 && !((double)c / 22.0 >= thr)) ++c;
+    return c;
+}
+// one thread: walk the hit mask like decoder.py:231-259 (record, jump 250) -> positions
+__device__ inline int sync_walk(const uint32_t* mask, int nw, int32_t* pos, int max_pos) {
+    int n = 0, i = 0;
+    while (i < nw) {
+        int wd = i >> 5;
+        uint32_t m = mask[wd] & (0xFFFFFFFFu << (i & 31));
+        const int n_words = (nw + 31) >> 5;
+        while (m == 0 && ++wd < n_words) m = mask[wd];
+        if (m == 0) break;
+        const int p = (wd << 5) + __ffs(m) - 1;
+        if (p >= nw) break;
+        if (n < max_pos) pos[n] = p;
+        ++n;
+        i = p + 250;
+    }
+    return n;
+}
+
+// find_sync(bits, threshold) -> number of positions (written to pos[], global or shared), *max_corr
+__device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double thr, int32_t* pos, int max_pos,
+                               SyncScratch& sc, double* max_corr) {
+    const int tid = threadIdx.x;
+    const int n_words = (nw + 31) >> 5;
+    const int cmin = sync_min_count(thr);
+    // pass 1: hits (TS1 is tried first, then TS2: decoder.py:237-259)
+    for (int wd = tid; wd < n_words; wd += FIN_THREADS) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int i = (wd << 5) + b;
+            if (i < nw) {
+                int c1, c2;
+                ts_counts(bits, i, c1, c2);
+                if (c1 >= cmin || c2 >= cmin) m |= 1u << b;
+            }
+        }
+        sc.mask[wd] = m;
+    }
+    if (tid == 0) sc.max_cnt = 0;
+    __syncthreads();
+    if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+    __syncthreads();
+    int n = sc.n_pos;
+    // max_corr over the VISITED offsets: everything except the 249 offsets skipped after each hit. At a visited
+    // offset TS2's correlation only counts when TS1 did not already hit.
+    const int n_known = min(n, max_pos);
+    int best = 0;
+    for (int i = tid; i < nw; i += FIN_THREADS) {
+        int lo = 0, hi = n_known;                       // last position <= i
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pos[mid] <= i) lo = mid + 1; else hi = mid; }
+        const bool skipped = lo > 0 && pos[lo - 1] < i && i < pos[lo - 1] + 250;
+        if (!skipped) {
+            int c1, c2;
+            ts_counts(bits, i, c1, c2);
+            best = max(best, c1 >= cmin ? c1 : max(c1, c2));
+        }
+    }
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) atomicMax(&sc.max_cnt, best);
+    __syncthreads();
+    const double mc = (double)sc.max_cnt / 22.0;
+    *max_corr = mc;
+    // adaptive retry inside find_sync (decoder.py:262-281)
+    if (n == 0 && mc > 0.75 && mc >= (thr - 0.15)) {
+        const double adaptive = fmax(0.75, mc - 0.02);
+        if (adaptive < thr) {
+            const int amin = sync_min_count(adaptive);
+            __syncthreads();
+            for (int wd = tid; wd < n_words; wd += FIN_THREADS) {
+                uint32_t m = 0;
+                for (int b = 0; b < 32; ++b) {
+                    const int i = (wd << 5) + b;
+                    if (i < nw) {
+                        int c1, c2;
+                        ts_counts(bits, i, c1, c2);
+                        if (max(c1, c2) >= amin) m |= 1u << b;      // no offset was skipped: best_here = max of both
+                    }
+                }
+                sc.mask[wd] = m;
+            }
+            __syncthreads();
+            // accepted offsets block +-250 around them; scanning upwards that is the same jump-250 walk
+            if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+            __syncthreads();
+            n = sc.n_pos;
+        }
+    }
+    __syncthreads();
+    return n;
+}
+
+// decode()'s cascade 0.90 -> 0.85 -> 0.80 -> adaptive (decoder.py:845-856)
+__device__ int block_sync_cascade(const uint32_t* __restrict__ bits, int nd, int32_t* pos, int max_pos, SyncScratch& sc) {
+    const int nw = 2 * nd - 22 + 1;
+    if (nw <= 0) return 0;                              // decoder.py:226-228: fewer than 22 bits
+    double mx = 0.0;
+    int n = block_find_sync(bits, nw, 0.90, pos, max_pos, sc, &mx);
+    if (n == 0) n = block_find_sync(bits, nw, 0.85, pos, max_pos, sc, &mx);
+    if (n == 0) n = block_find_sync(bits, nw, 0.80, pos, max_pos, sc, &mx);
+    if (n == 0 && mx >= 0.75) n = block_find_sync(bits, nw, fmax(0.75, mx - 0.02), pos, max_pos, sc, &mx);
+    return n;
+}
+
+// dibits in shared memory -> MSB-first packed bits (decoder.py:140-169), one zero word behind
+__device__ __forceinline__ void pack_dibits(const uint8_t* s_dib, int nd, uint32_t* s_bits) {
+    const int n_words = (nd + 15) / 16 + 1;
+    for (int j = threadIdx.x; j < n_words; j += blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int idx = 16 * j + m;
+            w = (w << 2) | (idx < nd ? (uint32_t)(s_dib[idx] & 3u) : 0u);
+        }
+        s_bits[j] = w;
+    }
+}
+
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     __shared__ double red[FIN_THREADS];
     __shared__ int s_best;
     __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
     __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
+    __shared__ SyncScratch s_sync;
     const int car = blockIdx.x, tid = threadIdx.x;
     const float2* __restrict__ y = a.y + (int64_t)car * a.y_pitch;
     const int L = a.L, sps = a.sps, step = a.step;
@@ -870,7 +1014,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     }
     uint8_t* dib = a.dibits + (int64_t)car * a.cap;
     float2* sym = a.symbols ? a.symbols + (int64_t)car * (a.cap + 1) : nullptr;
-    const bool fuse = a.match != nullptr && nd <= FIN_DIB_SMEM;
+    const bool fuse = (a.match != nullptr || a.sync_pos != nullptr) && nd <= FIN_DIB_SMEM;
     // symbols k = tid + 256 j, FIN_B of them per batch with all loads of a batch issued before any use
     // symbol k is sample best + stride k: in the phase-major layout that is row `best`, contiguous in k
     const float2* ys = a.y_rows > 0 ? y + (int64_t)best * a.y_rows : y + best;
@@ -900,35 +1044,52 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
         }
     }
     if (!fuse) return;
-    // ---- fused frame-sync correlator (decoder.py:140-169 bit expansion, :237-240 agreement counts) ----
+    // ---- fused frame-sync front end (decoder.py:140-169 bit expansion, :237-240 agreement counts, :171-295 + :845-856) ----
     __syncthreads();
-    const int n_words = (nd + 15) / 16 + 1;             // 16 dibits = 32 bits per word, first bit = MSB; one zero word behind
-    for (int j = tid; j < n_words; j += FIN_THREADS) {
-        uint32_t w = 0;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            const int idx = 16 * j + m;
-            w = (w << 2) | (idx < nd ? (uint32_t)(s_dib[idx] & 3u) : 0u);
-        }
-        s_bits[j] = w;
-    }
+    pack_dibits(s_dib, nd, s_bits);
     __syncthreads();
     const int nw = 2 * nd - 22 + 1;                     // window starts (decoder.py:232)
-    uint8_t* out = a.match + (int64_t)car * a.cap * 4;
-    for (int p = tid; 2 * p < nw; p += FIN_THREADS) {   // windows 2p and 2p+1 share their words
-        const int i = 2 * p;
-        const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
-        const int sh = i & 31;                          // even, <= 30: 23 bits starting at sh fit in 64
-        const uint32_t w0 = (uint32_t)(two >> (64 - 22 - sh)) & 0x3FFFFFu;
-        const uint32_t w1 = (uint32_t)(two >> (64 - 23 - sh)) & 0x3FFFFFu;
-        uchar4 o;
-        o.x = (uint8_t)(22 - __popc(w0 ^ TS1_BITS));
-        o.y = (uint8_t)(22 - __popc(w0 ^ TS2_BITS));
-        o.z = (uint8_t)(22 - __popc(w1 ^ TS1_BITS));
-        o.w = (uint8_t)(22 - __popc(w1 ^ TS2_BITS));
-        if (i + 1 < nw) *reinterpret_cast<uchar4*>(out + 2 * (int64_t)i) = o;
-        else { out[2 * (int64_t)i] = o.x; out[2 * (int64_t)i + 1] = o.y; }
+    if (a.match) {
+        uint8_t* out = a.match + (int64_t)car * a.cap * 4;
+        for (int p = tid; 2 * p < nw; p += FIN_THREADS) {   // windows 2p and 2p+1 share their words
+            const int i = 2 * p;
+            const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
+            const int sh = i & 31;                          // even, <= 30: 23 bits starting at sh fit in 64
+            const uint32_t w0 = (uint32_t)(two >> (64 - 22 - sh)) & 0x3FFFFFu;
+            const uint32_t w1 = (uint32_t)(two >> (64 - 23 - sh)) & 0x3FFFFFu;
+            uchar4 o;
+            o.x = (uint8_t)(22 - __popc(w0 ^ TS1_BITS));
+            o.y = (uint8_t)(22 - __popc(w0 ^ TS2_BITS));
+            o.z = (uint8_t)(22 - __popc(w1 ^ TS1_BITS));
+            o.w = (uint8_t)(22 - __popc(w1 ^ TS2_BITS));
+            if (i + 1 < nw) *reinterpret_cast<uchar4*>(out + 2 * (int64_t)i) = o;
+            else { out[2 * (int64_t)i] = o.x; out[2 * (int64_t)i + 1] = o.y; }
+        }
     }
+    if (a.sync_pos) {
+        const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
+        if (tid == 0) a.n_sync[car] = n;
+    }
+}
+
+// standalone: sync positions from dibit streams (the same device code; used when the streams come from elsewhere)
+struct SyncPosArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    int32_t* sync_pos; int32_t max_pos; int32_t* n_sync;
+};
+__global__ void __launch_bounds__(FIN_THREADS) k_sync_positions(const SyncPosArgs a) {
+    __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
+    __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
+    __shared__ SyncScratch s_sync;
+    const int car = blockIdx.x;
+    const int nd = min(a.n_dibits[car], FIN_DIB_SMEM);
+    const uint8_t* dib = a.dibits + (int64_t)car * a.cap;
+    for (int k = threadIdx.x; k < nd; k += FIN_THREADS) s_dib[k] = dib[k];
+    __syncthreads();
+    pack_dibits(s_dib, nd, s_bits);
+    __syncthreads();
+    const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
+    if (threadIdx.x == 0) a.n_sync[car] = n;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -112,17 +112,33 @@ __global__ void k_nco_c128(double2* x, int64_t n, double fo, double fs) {
 // Wideband channel selection (BASELINE config 3; the scanner's retune sweep, signal/scanner.py:383-445, done in
 // software): out[c][n] = x[n] * exp(-1j * 2 pi f_c * (n / fs)), i.e. frequency_shift (processor.py:97-100) of one
 // capture to C channel centres, with the reference's float64 phase and a complex64 result.
+constexpr int MIX_RUN = 16;               // samples per thread sharing one float64 sine/cosine (stride = block size)
 __global__ void __launch_bounds__(256) k_mix_wide(const float2* __restrict__ x, int64_t n, const double* __restrict__ freqs,
                                                     double fs, float2* __restrict__ out) {
     const int c = blockIdx.y;
     const double w = (2.0 * M_PI) * freqs[c];
     float2* oc = out + (int64_t)c * n;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const double t = (double)i / fs;
+    // Thread t of a block owns samples base + t + 256 u, u < MIX_RUN (coalesced). Its first phasor comes from the
+    // reference's own expression -(w * (i / fs)); the others by rotating with exp(-j w 256 / fs) in float64, so the
+    // recurrence error stays at a few ulp before the product is rounded to float32.
+    double s1, c1;
+    sincos(-(w * (256.0 / fs)), &s1, &c1);
+    const int64_t span = 256 * MIX_RUN;
+    for (int64_t base = blockIdx.x * span; base < n; base += (int64_t)gridDim.x * span) {
+        const int64_t i0 = base + threadIdx.x;
         double sn, cs;
-        sincos(-(w * t), &sn, &cs);
-        const float2 v = __ldg(x + i);
-        oc[i] = make_float2((float)((double)v.x * cs - (double)v.y * sn), (float)((double)v.x * sn + (double)v.y * cs));
+        sincos(-(w * ((double)i0 / fs)), &sn, &cs);
+#pragma unroll
+        for (int u = 0; u < MIX_RUN; ++u) {
+            const int64_t i = i0 + 256 * u;
+            if (i < n) {
+                const float2 v = __ldg(x + i);
+                oc[i] = make_float2((float)((double)v.x * cs - (double)v.y * sn), (float)((double)v.x * sn + (double)v.y * cs));
+            }
+            const double cn = cs * c1 - sn * s1;
+            sn = cs * s1 + sn * c1;
+            cs = cn;
+        }
     }
 }
 

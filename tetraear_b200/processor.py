@@ -148,11 +148,13 @@ class SignalProcessor:
         self.best_phase = int(res["best_phase"][0])
         return res["dibits"][0, :n].copy()
 
-    def process_batch(self, iq, freq_offsets=None, want_symbols=True, want_match=False):
+    def process_batch(self, iq, freq_offsets=None, want_symbols=True, want_match=False, want_sync=False):
         """Batched ``process``: iq complex64 [C, N] (numpy), freq_offsets [C] or None.
 
         Returns dict(dibits uint8 [C, cap], n_dibits int32 [C], n_symbols int32 [C], best_phase int32 [C],
-        symbols complex64 [C, cap+1] (if want_symbols), ts_match uint8 [C, 2*cap, 2] (if want_match)).
+        symbols complex64 [C, cap+1] (if want_symbols), ts_match uint8 [C, 2*cap, 2] (if want_match),
+        sync_pos int32 [C, max_pos] + n_sync int32 [C] (if want_sync: the positions TetraDecoder.decode's
+        threshold cascade finds, core/decoder.py:845-856, computed on the device)).
         """
         self._sync_rate()
         iq = np.ascontiguousarray(iq, dtype=np.complex64)
@@ -170,12 +172,20 @@ class SignalProcessor:
             fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
             if fo.shape != (n_car,):
                 raise ValueError("freq_offsets must have one entry per carrier")
-        self._check(self._lib.tetra_process_batch(
+        max_pos = (2 * cap) // 250 + 2
+        spos = np.zeros((n_car, max_pos), dtype=np.int32) if want_sync else None
+        nsync = np.zeros(n_car, dtype=np.int32) if want_sync else None
+        self._check(self._lib.tetra_process_batch_sync(
             self._ctx, iq.ctypes.data, n_car, n, n, fo.ctypes.data if fo is not None else None,
             dib.ctypes.data, cap, nd.ctypes.data, sym.ctypes.data if sym is not None else None, ph.ctypes.data,
-            mt.ctypes.data if mt is not None else None, 0), "process_batch")
+            mt.ctypes.data if mt is not None else None,
+            spos.ctypes.data if want_sync else None, max_pos if want_sync else 0, nsync.ctypes.data if want_sync else None,
+            0), "process_batch")
         n_sym = np.where(nd > 0, nd + 1, 0).astype(np.int32)
         out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=n_sym, best_phase=ph)
+        if want_sync:
+            out["sync_pos"] = spos
+            out["n_sync"] = nsync
         if sym is not None:
             out["symbols"] = sym
         if mt is not None:
@@ -225,6 +235,24 @@ class SignalProcessor:
             self._ctx, iq_ptr, n_carriers, n_samples, pitch, fo.ctypes.data if fo is not None else None,
             dibits_ptr, cap, n_dibits_ptr, symbols_ptr or None, best_phase_ptr or None, ts_match_ptr or None, 1),
             "process_batch(device)")
+
+    def sync_positions(self, dibits, n_dibits=None):
+        """decode()'s sync search (core/decoder.py:840-856) on the device for dibit streams [C, cap] (or one stream):
+        returns a list of position lists."""
+        d = np.ascontiguousarray(dibits, dtype=np.uint8)
+        one = d.ndim == 1
+        if one:
+            d = d[None, :]
+        n_car, cap = d.shape
+        nd = np.full(n_car, cap, dtype=np.int32) if n_dibits is None else np.ascontiguousarray(n_dibits, dtype=np.int32)
+        max_pos = (2 * cap) // 250 + 2
+        spos = np.zeros((n_car, max_pos), dtype=np.int32)
+        nsync = np.zeros(n_car, dtype=np.int32)
+        if cap > 0:
+            self._check(self._lib.tetra_sync_positions(self._ctx, d.ctypes.data, cap, nd.ctypes.data, n_car,
+                                                       spos.ctypes.data, max_pos, nsync.ctypes.data), "sync_positions")
+        res = [[int(p) for p in spos[c, : nsync[c]]] for c in range(n_car)]
+        return res[0] if one else res
 
     def dibit_capacity(self, n_samples: int) -> int:
         self._sync_rate()
