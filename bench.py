@@ -129,8 +129,9 @@ def cpu_baseline_sample(target_s=12.0):
     pool = mp.get_context("spawn").Pool(cores)
     try:
         pool.map(_cpu_worker, [(i, 0) for i in range(cores)])
-        _, _, dt1 = cpu_rate(1, cores, pool)                                # calibration pass
-        reps = int(max(2, min(256, round(target_s / max(dt1, 1e-3)))))
+        cpu_rate(1, cores, pool)                                            # first touch (caches, page faults)
+        _, _, dt4 = cpu_rate(4, cores, pool)                                # calibration pass
+        reps = int(max(4, min(512, round(4 * target_s / max(dt4, 1e-3)))))
         v, _, dt = cpu_rate(reps, cores, pool)
     finally:
         pool.close(); pool.join()
