@@ -89,6 +89,18 @@ int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, con
                          int32_t n_carriers, int32_t* sync_pos, int32_t max_positions, int32_t* n_sync);
 
 /*
+ * What TetraDecoder.decode does with each sync position up to the burst's CRC verdict (core/decoder.py:861-888,
+ * decode_frame :986-992, TetraProtocolParser.parse_burst core/protocol.py:192-347), for every (carrier, position):
+ *   burst_info [C][max_positions][4] int32 = (start_symbol or -1 when decode() drops the position,
+ *                                             frame_number = start_bit / 510, burst_type (2 normal downlink,
+ *                                             5 synchronization), crc_ok)
+ * All buffers host or all device.
+ */
+int tetra_parse_bursts(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits,
+                       int32_t n_carriers, const int32_t* sync_pos, int32_t max_positions,
+                       const int32_t* n_sync, int32_t* burst_info);
+
+/*
  * BASELINE config 3 -- C channels out of ONE wideband capture: for every channel centre f_c (Hz, relative
  * to the capture centre) the composition  process(frequency_shift(iq, f_c, sample_rate), 0)  of the
  * reference's own methods (signal/processor.py:85-100 and :221-273). The reference has no channelizer; its

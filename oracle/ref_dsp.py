@@ -198,6 +198,69 @@ def sync_cascade(bits: np.ndarray):
     return pos
 
 
+# protocol.py:162-163
+SYNC_CONTINUOUS_DOWNLINK = np.array([1, 1, 0, 1, 0, 0, 0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 1, 0, 0], dtype=np.int64)
+SYNC_DISCONTINUOUS_DOWNLINK = np.array([0, 0, 1, 1, 1, 0, 1, 0, 0, 1, 0, 0, 0, 0, 1, 1, 0, 1, 0, 0, 1, 1], dtype=np.int64)
+BURST_NORMAL_DOWNLINK, BURST_SYNCHRONIZATION = 2, 5        # protocol.py BurstType values
+
+
+def crc16_ccitt_bits(bits) -> int:
+    """protocol.py:332-347 -- bitwise CRC-16-CCITT (0x1021, init 0xFFFF), MSB first."""
+    crc = 0xFFFF
+    for bit in bits:
+        crc ^= (int(bit) << 15)
+        crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
+def check_crc(bits) -> bool:
+    """protocol.py:291-330 -- the reference's soft CRC check (<= 2 bit errors, forward or reversed payload)."""
+    bits = np.asarray(bits).astype(np.int64)
+    if len(bits) < 16:
+        return False
+    ones = int(bits.sum())
+    if ones == 0 or ones == len(bits):
+        return False
+    payload, recv = bits[:-16], bits[-16:]
+    recv_word = int("".join(str(int(b)) for b in recv), 2)
+    if bin(crc16_ccitt_bits(payload) ^ recv_word).count("1") <= 2:
+        return True
+    return bin(crc16_ccitt_bits(payload[::-1]) ^ recv_word).count("1") <= 2
+
+
+def parse_burst(symbols):
+    """protocol.py:192-289 for one 255-symbol slot -> (burst_type, crc_ok, data_bits)."""
+    sym = np.asarray(symbols[:255]).astype(np.int64)
+    bits = np.empty(510, dtype=np.int64)
+    bits[0::2] = (sym >> 1) & 1
+    bits[1::2] = sym & 1
+    w = bits[255:277]
+    m = max(int((w == SYNC_CONTINUOUS_DOWNLINK).sum()), int((w == SYNC_DISCONTINUOUS_DOWNLINK).sum())) / 22
+    if m > 0.8:
+        btype, data = BURST_SYNCHRONIZATION, bits
+    else:
+        btype, data = BURST_NORMAL_DOWNLINK, np.concatenate([bits[0:108], bits[122:230]])
+    return btype, check_crc(data), data
+
+
+def decode_bursts(dibits, positions):
+    """decoder.py:861-888 up to the parse_burst call inside decode_frame (:986-992): for every sync position the
+    (start_symbol, frame_number, burst_type, crc_ok) of its 255-symbol slot; positions without a complete slot
+    are dropped exactly like decode() drops them."""
+    out = []
+    d = np.asarray(dibits)
+    for pos in positions:
+        start = pos - 216
+        if start < 0:
+            continue
+        s0 = start // 2
+        if s0 + 255 > len(d):
+            continue
+        btype, crc_ok, _ = parse_burst(d[s0:s0 + 255])
+        out.append((s0, start // 510, btype, int(crc_ok)))
+    return out
+
+
 def spectrum_db(samples: np.ndarray, n_fft: int = 2048) -> np.ndarray:
     """modern.py:1924-1934 on the first n_fft samples."""
     w = np.hanning(n_fft)

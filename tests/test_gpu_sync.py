@@ -80,3 +80,30 @@ def test_process_batch_sync_matches_reference_cascade(gpu_processor, name, gen, 
     assert got == sync.sync_cascade(res["ts_match"][0], nd)
     assert sync.burst_slices(got, nd) == [(p - 216) // 2 and ((p - 216) // 2, p - 216, (p - 216) // 510) for p in got
                                           if p - 216 >= 0 and (p - 216) // 2 + 255 <= nd]
+
+
+def test_parse_bursts_matches_reference_golden(gpu_processor):
+    """Every golden slot (burst type and CRC verdict from the reference's own parse_burst) planted in a stream at the
+    position decode() would cut it from."""
+    sp = gpu_processor
+    g = load_golden("bursts")
+    frames = g["frames"]
+    n = len(frames)
+    rng = np.random.default_rng(8)
+    cap = 255 + 300
+    dib = rng.integers(0, 4, size=(n, cap), dtype=np.uint8)
+    nd = np.full(n, cap, dtype=np.int32)
+    spos = np.zeros((n, 6), dtype=np.int32)
+    ns = np.zeros(n, dtype=np.int32)
+    for c in range(n):
+        s0 = int(rng.integers(0, 300))
+        dib[c, s0:s0 + 255] = frames[c]
+        spos[c, 0] = 2 * s0 + 216 + (c % 2)            # odd positions floor to the same start symbol (decoder.py:869)
+        spos[c, 1] = 100                                # start < 0: dropped
+        spos[c, 2] = 2 * (cap - 200) + 216              # slot runs past the end: dropped
+        ns[c] = 3
+    got = sp.parse_bursts(dib, nd, spos, ns)
+    for c in range(n):
+        want = ref_dsp.decode_bursts(dib[c], [int(p) for p in spos[c, :3]])
+        assert got[c] == want, c
+        assert len(got[c]) == 1 and got[c][0][2:] == (int(g["burst_type"][c]), int(g["crc_ok"][c])), c

@@ -49,3 +49,13 @@ def test_stft_rows_shape():
     x = (np.random.default_rng(0).standard_normal(10000) + 0j).astype(np.complex64)
     assert ref_dsp.stft_db(x, 4096, 1024).shape == (6, 4096)
     assert ref_dsp.stft_db(x[:100], 4096, 1024).shape == (0, 4096)
+
+
+def test_burst_parse_matches_reference_golden():
+    """oracle parse_burst / check_crc vs TetraProtocolParser.parse_burst run on the same seeded slots."""
+    g = load_golden("bursts")
+    for f, bt, ok in zip(g["frames"], g["burst_type"], g["crc_ok"]):
+        btype, crc_ok, data = ref_dsp.parse_burst(f)
+        assert (btype, int(crc_ok)) == (int(bt), int(ok))
+        assert len(data) == (510 if btype == ref_dsp.BURST_SYNCHRONIZATION else 216)
+    assert g["crc_ok"].sum() > 10 and (g["burst_type"] == 5).sum() > 10

@@ -26,6 +26,8 @@ _SIGS = {
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "tetra_sync_positions": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p]),
+    "tetra_parse_bursts": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p]),
     "tetra_process_wideband": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),

@@ -704,6 +704,45 @@ int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, con
     return TETRA_OK;
 }
 
+int tetra_parse_bursts(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits, int32_t C,
+                       const int32_t* sync_pos, int32_t max_pos, const int32_t* n_sync, int32_t* burst_info) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || cap < 0 || max_pos <= 0 || (C > 0 && (!dibits || !n_dibits || !sync_pos || !n_sync || !burst_info)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_parse_bursts: bad arguments");
+    if (C == 0) return TETRA_OK;
+    if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_parse_bursts: at most 65535 carriers per call");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool dev = is_device_ptr(dibits);
+    if (dev != is_device_ptr(n_dibits) || dev != is_device_ptr(sync_pos) || dev != is_device_ptr(n_sync) || dev != is_device_ptr(burst_info))
+        return fail(ctx, TETRA_E_INVALID, "tetra_parse_bursts: all buffers must be host or all device");
+    BurstArgs a;
+    a.cap = cap; a.max_pos = max_pos;
+    if (dev) {
+        a.dibits = dibits; a.n_dibits = n_dibits; a.sync_pos = sync_pos; a.n_sync = n_sync; a.info = (int4*)burst_info;
+    } else {
+        const size_t b_dib = ((size_t)C * cap + 15) & ~(size_t)15, b_pos = (size_t)C * max_pos * sizeof(int32_t);
+        CK(ctx->tmp_a.ensure(b_dib + 2 * sizeof(int32_t) * C + b_pos + (size_t)C * max_pos * sizeof(int4) + 64));
+        uint8_t* base = (uint8_t*)ctx->tmp_a.p;
+        CK(cudaMemcpyAsync(base, dibits, (size_t)C * cap, cudaMemcpyHostToDevice, st));
+        int32_t* d_nd = (int32_t*)(base + b_dib);
+        int32_t* d_ns = d_nd + C;
+        int32_t* d_pos = d_ns + C;
+        CK(cudaMemcpyAsync(d_nd, n_dibits, sizeof(int32_t) * C, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_ns, n_sync, sizeof(int32_t) * C, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_pos, sync_pos, b_pos, cudaMemcpyHostToDevice, st));
+        size_t off = b_dib + 2 * sizeof(int32_t) * C + b_pos;
+        off = (off + 15) & ~(size_t)15;
+        a.dibits = base; a.n_dibits = d_nd; a.n_sync = d_ns; a.sync_pos = d_pos; a.info = (int4*)(base + off);
+    }
+    k_parse_bursts<<<dim3((max_pos + 3) / 4, C), 128, 0, st>>>(a);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (!dev) CK(cudaMemcpyAsync(burst_info, a.info, (size_t)C * max_pos * sizeof(int4), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // find_sync replay (host, integer-exact)
 // ------------------------------------------------------------------------------------------------

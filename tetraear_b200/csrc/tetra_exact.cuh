@@ -1093,6 +1093,72 @@ __global__ void __launch_bounds__(FIN_THREADS) k_sync_positions(const SyncPosArg
 }
 
 // ----------------------------------------------------------------------------------------------
+// k_parse_bursts: what TetraDecoder.decode does with each sync position up to the burst's CRC verdict
+// (core/decoder.py:861-888 -> decode_frame :986-992 -> TetraProtocolParser.parse_burst, core/protocol.py:192-347):
+// slot start = position - 216 bits, 255 symbols; burst type from the 22 bits at bit 255 (> 0.8 agreement with either
+// sync pattern); data bits (normal burst: bits 0-107 + 122-229, sync burst: all 510); the reference's soft CRC-16-CCITT
+// check (<= 2 differing CRC bits, forward or reversed payload). One warp per (carrier, position).
+// info[car][slot] = (start_symbol or -1 when decode() drops the position, frame_number, burst_type, crc_ok)
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t SYNC_CONT_BITS = 0x343A74u;    // 1101000011101001110100 (protocol.py:162), first bit = MSB of 22
+constexpr uint32_t SYNC_DISC_BITS = 0x0E90D3u;    // 0011101001000011010011 (protocol.py:163)
+
+struct BurstArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    const int32_t* sync_pos; int32_t max_pos; const int32_t* n_sync;
+    int4* info;              // [C][max_pos]
+};
+
+// bit j of the 510-bit slot (MSB-first expansion of the symbols in shared memory)
+__device__ __forceinline__ uint32_t burst_bit(const uint8_t* sym, int j) { return (sym[j >> 1] >> (1 - (j & 1))) & 1u; }
+
+__global__ void __launch_bounds__(128) k_parse_bursts(const BurstArgs a) {
+    __shared__ uint8_t s_sym[4][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + warp, car = blockIdx.y;
+    if (slot >= a.max_pos) return;
+    int4* out = a.info + (int64_t)car * a.max_pos + slot;
+    const int nd = a.n_dibits[car];
+    const int pos = slot < a.n_sync[car] ? a.sync_pos[(int64_t)car * a.max_pos + slot] : -1;
+    const int start = pos - 216;
+    const int s0 = start >> 1;                           // start >= 0 below
+    if (pos < 0 || start < 0 || s0 + 255 > nd) {
+        if (lane == 0) *out = make_int4(-1, 0, 0, 0);
+        return;
+    }
+    uint8_t* sym = s_sym[warp];
+    const uint8_t* dib = a.dibits + (int64_t)car * a.cap + s0;
+    for (int k = lane; k < 255; k += 32) sym[k] = dib[k] & 3u;
+    __syncwarp();
+    // burst type (protocol.py:244-266)
+    uint32_t win = 0;
+    for (int j = 0; j < 22; ++j) win = (win << 1) | burst_bit(sym, 255 + j);
+    const int m = max(22 - __popc(win ^ SYNC_CONT_BITS), 22 - __popc(win ^ SYNC_DISC_BITS));
+    const bool is_sync = (double)m / 22.0 > 0.8;
+    // data bit d of the burst (protocol.py:268-289)
+    const int n_data = is_sync ? 510 : 216;
+    auto data_bit = [&](int d) { return burst_bit(sym, is_sync ? d : (d < 108 ? d : d + 14)); };
+    int ones = 0;
+    for (int d = lane; d < n_data; d += 32) ones += data_bit(d);
+    for (int o = 16; o; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    // CRC-16-CCITT of the payload, MSB first, init 0xFFFF: lane 0 forward, lane 1 over the reversed payload
+    const int n_pay = n_data - 16;
+    uint32_t crc = 0xFFFFu;
+    if (lane < 2) {
+        for (int d = 0; d < n_pay; ++d) {
+            crc ^= data_bit(lane == 0 ? d : n_pay - 1 - d) << 15;
+            crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x1021u) & 0xFFFFu : (crc << 1) & 0xFFFFu;
+        }
+    }
+    uint32_t recv = 0;
+    for (int d = 0; d < 16; ++d) recv = (recv << 1) | data_bit(n_pay + d);
+    const int err = __popc((crc ^ recv) & 0xFFFFu);
+    const int err_fwd = __shfl_sync(0xffffffffu, err, 0), err_rev = __shfl_sync(0xffffffffu, err, 1);
+    const bool crc_ok = ones != 0 && ones != n_data && (err_fwd <= 2 || err_rev <= 2);
+    if (lane == 0) *out = make_int4(s0, start / 510, is_sync ? 5 : 2, crc_ok ? 1 : 0);
+}
+
+// ----------------------------------------------------------------------------------------------
 // K_sync: dibits -> bits (decoder.py:140-169) and 22-bit TS1/TS2 agreement at every bit offset
 // (decoder.py:237-240). One thread per window start.
 // ----------------------------------------------------------------------------------------------

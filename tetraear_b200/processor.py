@@ -254,6 +254,21 @@ class SignalProcessor:
         res = [[int(p) for p in spos[c, : nsync[c]]] for c in range(n_car)]
         return res[0] if one else res
 
+    def parse_bursts(self, dibits, n_dibits, sync_pos, n_sync):
+        """For every (carrier, sync position): (start_symbol, frame_number, burst_type, crc_ok) of its 255-symbol
+        slot as TetraDecoder.decode / parse_burst determine them (core/decoder.py:861-888, core/protocol.py:192-347);
+        positions decode() drops are left out. Returns one list of tuples per carrier."""
+        d = np.ascontiguousarray(dibits, dtype=np.uint8)
+        nd = np.ascontiguousarray(n_dibits, dtype=np.int32)
+        sp_ = np.ascontiguousarray(sync_pos, dtype=np.int32)
+        ns = np.ascontiguousarray(n_sync, dtype=np.int32)
+        n_car, cap = d.shape
+        max_pos = sp_.shape[1]
+        info = np.zeros((n_car, max_pos, 4), dtype=np.int32)
+        self._check(self._lib.tetra_parse_bursts(self._ctx, d.ctypes.data, cap, nd.ctypes.data, n_car, sp_.ctypes.data, max_pos,
+                                                 ns.ctypes.data, info.ctypes.data), "parse_bursts")
+        return [[tuple(int(v) for v in info[c, k]) for k in range(ns[c]) if info[c, k, 0] >= 0] for c in range(n_car)]
+
     def dibit_capacity(self, n_samples: int) -> int:
         self._sync_rate()
         return int(self._lib.tetra_dibit_capacity(self._ctx, int(n_samples)))
