@@ -313,6 +313,21 @@ def run_ours(a):
            "carriers_per_rank": ce, "timed": "host wall clock around SignalProcessor.process_batch, max over ranks",
            "note": "pinned host IQ -> tetra_process_batch -> host dibits; PCIe-bound"}
 
+    # ---- the same through the RTL-SDR byte format: 2 bytes per sample cross PCIe ----
+    scale = float(x[:ce].abs().max().item())
+    raw = torch.clamp(torch.round((x[:ce] / scale * 0.9 + 1.0) * 127.5), 0, 255).to(torch.uint8).cpu().pin_memory()
+    raw_np = raw.numpy()
+    sp.process_batch_u8(raw_np, None, want_symbols=False, want_match=False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        sp.process_batch_u8(raw_np, None, want_symbols=False, want_match=False)
+    dt8 = shard.max_over_ranks((time.perf_counter() - t0) / reps, dev)
+    e2e["u8_ingest"] = {"value": world * ce * N_SAMPLES / dt8 / 1e6, "unit": "MS/s", "h2d_bytes_per_step": int(ce * N_SAMPLES * 2),
+                        "note": "pinned host uint8 I/Q (RTL-SDR native) -> tetra_process_batch_u8 -> host dibits"}
+
     if rank == 0:
         peak, peak_src = measured_peak()
         k_avg = (k_total_ms / k_n) if k_n else None

@@ -101,6 +101,18 @@ int tetra_parse_bursts(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const
                        const int32_t* n_sync, int32_t* burst_info);
 
 /*
+ * tetra_process_batch_sync for RTL-SDR native samples: iq_u8 [C][pitch][2] interleaved unsigned 8-bit I, Q
+ * (host or device), converted on the device exactly like pyrtlsdr's packed_bytes_to_iq does before the
+ * reference sees them (RTLCapture.read_samples, signal/capture.py:143-158): (byte / 127.5) - 1.
+ * A quarter of the host-to-device bytes of the complex64 entry point. Synchronous.
+ */
+int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t n_carriers, int64_t n_samples,
+                           int64_t pitch, const double* freq_offset_hz,
+                           uint8_t* dibits, int64_t cap, int32_t* n_dibits,
+                           float* symbols, int32_t* best_phase, uint8_t* ts_match,
+                           int32_t* sync_pos, int32_t max_positions, int32_t* n_sync);
+
+/*
  * BASELINE config 3 -- C channels out of ONE wideband capture: for every channel centre f_c (Hz, relative
  * to the capture centre) the composition  process(frequency_shift(iq, f_c, sample_rate), 0)  of the
  * reference's own methods (signal/processor.py:85-100 and :221-273). The reference has no channelizer; its

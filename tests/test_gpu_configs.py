@@ -68,3 +68,26 @@ def test_spectrum_block_of_capture_thread(gpu_processor):
     assert np.array_equal(freqs, np.fft.fftshift(np.fft.fftfreq(2048, 1 / 2.4e6)) + 390.0e6)
     ref = ref_dsp.spectrum_db(x, 2048)
     assert power.dtype == np.float64 and np.abs(power - ref)[ref > -100].max() < 1e-2
+
+
+def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
+    """RTL-SDR bytes: the oracle gets what pyrtlsdr's read_samples hands the reference, complex128 (byte/127.5 - 1)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n = 1 << 17
+    xs = [synth.carrier_iq(n, 300 + c, snr_db=25.0, alphabet="centred" if c else "pi4") for c in range(2)]
+    raw = np.empty((2, n, 2), dtype=np.uint8)
+    for c in range(2):
+        z = xs[c] / np.abs(xs[c]).max() * 0.9                  # fill most of the ADC range
+        raw[c, :, 0] = np.clip(np.round((z.real + 1.0) * 127.5), 0, 255)
+        raw[c, :, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
+    res = sp.process_batch_u8(raw, [0.0, 777.0], want_symbols=True, want_sync=True)
+    for c, fo in enumerate((0.0, 777.0)):
+        x128 = (raw[c, :, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (raw[c, :, 1].astype(np.float64) / 127.5 - 1.0)
+        r = ref_dsp.process(x128, fo, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"]
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"])
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, err
+        assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))

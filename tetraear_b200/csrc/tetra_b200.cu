@@ -62,7 +62,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos, u8;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
@@ -336,7 +336,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos, &ctx->u8};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -634,6 +634,42 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     }
     if (!async) CK(cudaStreamSynchronize(st));
     return TETRA_OK;
+}
+
+int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t C, int64_t N, int64_t pitch,
+                           const double* fo_hz, uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols,
+                           int32_t* best_phase, uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || N < 0 || (C > 0 && N > 0 && (!iq_u8 || pitch < N)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_u8: bad arguments");
+    if (C == 0 || N == 0)
+        return tetra_process_batch_sync(ctx, nullptr, C, N, N, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match,
+                                        sync_pos, max_pos, n_sync, 0);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint8_t* d_in = iq_u8;
+    int64_t d_pitch = pitch;
+    if (!is_device_ptr(iq_u8)) {
+        CK(ctx->u8.ensure((size_t)C * N * 2));
+        if (pitch == N) CK(cudaMemcpyAsync(ctx->u8.p, iq_u8, (size_t)C * N * 2, cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpy2DAsync(ctx->u8.p, N * 2, iq_u8, pitch * 2, N * 2, C, cudaMemcpyHostToDevice, st));
+        d_in = (const uint8_t*)ctx->u8.p;
+        d_pitch = N;
+    }
+    CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
+    if (d_pitch == N) {
+        k_u8_to_c64<<<(unsigned)std::min<int64_t>(((int64_t)C * N / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(d_in, (int64_t)C * N, (float2*)ctx->wide.p);
+        ctx->launches++;
+    } else {
+        for (int c = 0; c < C; ++c) {
+            k_u8_to_c64<<<(unsigned)std::min<int64_t>((N / 8 + 255) / 256 + 1, 148 * 4), 256, 0, st>>>(d_in + (size_t)c * d_pitch * 2, N,
+                                                                                                  (float2*)ctx->wide.p + (size_t)c * N);
+            ctx->launches++;
+        }
+    }
+    CK(cudaGetLastError());
+    return tetra_process_batch_sync(ctx, (const float*)ctx->wide.p, C, N, N, fo_hz, dibits, cap, n_dibits, symbols, best_phase,
+                                    ts_match, sync_pos, max_pos, n_sync, 0);
 }
 
 int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const double* channel_hz, int32_t C,

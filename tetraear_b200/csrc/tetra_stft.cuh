@@ -109,6 +109,29 @@ __global__ void k_nco_c128(double2* x, int64_t n, double fo, double fs) {
     }
 }
 
+// RTL-SDR native samples (interleaved unsigned 8-bit I, Q) -> complex64, the conversion pyrtlsdr's
+// packed_bytes_to_iq applies before the reference ever sees the data (signal/capture.py:143-158 ->
+// RtlSdr.read_samples):  iq = (byte / 127.5) - 1   per component. 8 samples (16 bytes in, 64 bytes out) per thread step.
+__global__ void __launch_bounds__(256) k_u8_to_c64(const uint8_t* __restrict__ in, int64_t n_samples, float2* __restrict__ out) {
+    const int64_t n16 = n_samples / 8;
+    const uint4* in16 = reinterpret_cast<const uint4*>(in);
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    auto cv = [](uint32_t b) { return (float)((double)b / 127.5 - 1.0); };
+    if (aligned) {
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+            const uint4 v = __ldg(in16 + i);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+            float4* o = reinterpret_cast<float4*>(out + 8 * i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                o[k] = make_float4(cv(w[k] & 255u), cv((w[k] >> 8) & 255u), cv((w[k] >> 16) & 255u), cv(w[k] >> 24));
+        }
+    }
+    const int64_t done = aligned ? n16 * 8 : 0;
+    for (int64_t i = done + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_samples; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = make_float2(cv(in[2 * i]), cv(in[2 * i + 1]));
+}
+
 // Wideband channel selection (BASELINE config 3; the scanner's retune sweep, signal/scanner.py:383-445, done in
 // software): out[c][n] = x[n] * exp(-1j * 2 pi f_c * (n / fs)), i.e. frequency_shift (processor.py:97-100) of one
 // capture to C channel centres, with the reference's float64 phase and a complex64 result.

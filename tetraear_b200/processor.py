@@ -192,6 +192,43 @@ class SignalProcessor:
             out["ts_match"] = mt[:, : 2 * cap]
         return out
 
+    def process_batch_u8(self, iq_u8, freq_offsets=None, want_symbols=True, want_match=False, want_sync=False):
+        """``process_batch`` for raw RTL-SDR bytes: iq_u8 uint8 [C, N, 2] (interleaved I, Q as the dongle delivers
+        them). The conversion pyrtlsdr applies in ``read_samples`` -- (byte / 127.5) - 1 -- runs on the device, so
+        only 2 bytes per sample cross PCIe."""
+        self._sync_rate()
+        raw = np.ascontiguousarray(iq_u8, dtype=np.uint8)
+        if raw.ndim != 3 or raw.shape[2] != 2:
+            raise ValueError("iq_u8 must be [carriers, samples, 2]")
+        n_car, n = raw.shape[0], raw.shape[1]
+        cap = int(self._lib.tetra_dibit_capacity(self._ctx, n))
+        dib = np.zeros((n_car, max(cap, 1)), dtype=np.uint8)
+        nd = np.zeros(n_car, dtype=np.int32)
+        ph = np.zeros(n_car, dtype=np.int32)
+        sym = np.zeros((n_car, cap + 1), dtype=np.complex64) if want_symbols else None
+        mt = np.zeros((n_car, 2 * max(cap, 1), 2), dtype=np.uint8) if want_match else None
+        max_pos = (2 * cap) // 250 + 2
+        spos = np.zeros((n_car, max_pos), dtype=np.int32) if want_sync else None
+        nsync = np.zeros(n_car, dtype=np.int32) if want_sync else None
+        fo = None
+        if freq_offsets is not None:
+            fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
+        self._check(self._lib.tetra_process_batch_u8(
+            self._ctx, raw.ctypes.data, n_car, n, n, fo.ctypes.data if fo is not None else None,
+            dib.ctypes.data, cap, nd.ctypes.data, sym.ctypes.data if sym is not None else None, ph.ctypes.data,
+            mt.ctypes.data if mt is not None else None,
+            spos.ctypes.data if want_sync else None, max_pos if want_sync else 0, nsync.ctypes.data if want_sync else None),
+            "process_batch_u8")
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=np.where(nd > 0, nd + 1, 0).astype(np.int32), best_phase=ph)
+        if sym is not None:
+            out["symbols"] = sym
+        if mt is not None:
+            out["ts_match"] = mt[:, : 2 * cap]
+        if want_sync:
+            out["sync_pos"] = spos
+            out["n_sync"] = nsync
+        return out
+
     def process_wideband(self, samples, channel_freqs, want_symbols=True, want_match=False):
         """BASELINE config 3: every channel of one wideband capture, i.e. for each centre f_c the composition
         ``process(frequency_shift(samples, f_c), 0)`` of the reference's methods (processor.py:85-100, 221-273).
