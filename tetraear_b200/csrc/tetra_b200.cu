@@ -62,7 +62,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos, u8;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos, u8, stft_tab;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
@@ -336,7 +336,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos, &ctx->u8};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos, &ctx->u8, &ctx->stft_tab};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -984,7 +984,13 @@ int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n, int32_t nfft, int3
         dx = (const float2*)ctx->in.p;
     }
     if (!d_out) { CK(ctx->y.ensure((size_t)rows * nfft * sizeof(float))); dout = (float*)ctx->y.p; }
-    int rc = stft_launch(st, dx, n, nfft, hop, rows, dout);
+    if (nfft == 4096 && !ctx->stft_tab.p) {
+        CK(ctx->stft_tab.ensure(sizeof(S4kTables)));
+        k_stft4096_tables<<<S4K_N / 256, 256, 0, st>>>((S4kTables*)ctx->stft_tab.p);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    int rc = stft_launch(st, dx, n, nfft, hop, rows, dout, (const S4kTables*)ctx->stft_tab.p);
     ctx->launches++;
     if (rc) return fail(ctx, TETRA_E_CUDA, "tetra_stft_db: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CK(cudaGetLastError());

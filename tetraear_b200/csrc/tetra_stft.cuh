@@ -67,6 +67,144 @@ __global__ void __launch_bounds__(STFT_THREADS) k_stft_db(const float2* __restri
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// K3 for the waterfall size of BASELINE config 5 (4096 = 16^3): three radix-16 Stockham passes with the 16-point
+// DFTs in registers (two radix-4 stages), so a row costs 3 shared-memory exchanges instead of 12. 256 threads, one
+// (padded) row buffer, Hann window and the W_4096 table built once per persistent CTA; pass 1 reads the row from
+// global memory, pass 3 writes the fftshifted dB row. Two CTAs per SM.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }      // a * (-j)
+__device__ __forceinline__ float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }      // a * (+j)
+
+// a[q] *= w^q, q = 1..15, with the powers built by squaring and at most four products deep (a table lookup per power
+// would hit one shared-memory bank for all lanes)
+__device__ __forceinline__ void twiddle_powers(float2 (&a)[16], float2 w1) {
+    float2 w[16];
+    w[1] = w1;
+    w[2] = cmulf(w[1], w[1]);  w[3] = cmulf(w[2], w[1]);
+    w[4] = cmulf(w[2], w[2]);  w[5] = cmulf(w[4], w[1]);  w[6] = cmulf(w[4], w[2]);  w[7] = cmulf(w[4], w[3]);
+    w[8] = cmulf(w[4], w[4]);
+#pragma unroll
+    for (int q = 9; q < 16; ++q) w[q] = cmulf(w[8], w[q - 8]);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) a[q] = cmulf(a[q], w[q]);
+}
+
+// b[k] = sum_n a[n] exp(-2 pi j n k / 16), in place
+__device__ __forceinline__ void dft16(float2 (&a)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    const float2 w16[10] = {{1.f, 0.f}, {c1, -s1}, {h, -h}, {s1, -c1}, {0.f, -1.f}, {-s1, -c1}, {-h, -h}, {-c1, -s1}, {-1.f, 0.f}, {-c1, s1}};
+    float2 t[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 s02 = cadd(a[i], a[i + 8]), d02 = csub(a[i], a[i + 8]);
+        const float2 s13 = cadd(a[i + 4], a[i + 12]), d13 = csub(a[i + 4], a[i + 12]);
+        t[i][0] = cadd(s02, s13);
+        t[i][1] = cadd(d02, mul_mj(d13));
+        t[i][2] = csub(s02, s13);
+        t[i][3] = cadd(d02, mul_pj(d13));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) y[i] = (i * q == 0) ? t[i][q] : cmulf(t[i][q], w16[i * q]);   // i*q <= 9
+        const float2 s02 = cadd(y[0], y[2]), d02 = csub(y[0], y[2]);
+        const float2 s13 = cadd(y[1], y[3]), d13 = csub(y[1], y[3]);
+        a[q] = cadd(s02, s13);
+        a[q + 4] = cadd(d02, mul_mj(d13));
+        a[q + 8] = csub(s02, s13);
+        a[q + 12] = cadd(d02, mul_pj(d13));
+    }
+}
+
+constexpr int S4K_N = 4096, S4K_THREADS = 256;
+__device__ __forceinline__ int s4k_pad(int i) { return i + (i >> 4); }
+struct S4kSmem {
+    float2 buf[S4K_N + S4K_N / 16];
+    float2 tw[S4K_N];
+    float win[S4K_N];
+};
+
+// W_4096 and the symmetric Hann window (np.hanning), float64 trigonometry rounded to float32; built once per context
+struct S4kTables { float2 tw[S4K_N]; float win[S4K_N]; };
+__global__ void k_stft4096_tables(S4kTables* tab) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S4K_N) return;
+    double sn, cs;
+    sincospi(-2.0 * (double)t / (double)S4K_N, &sn, &cs);
+    tab->tw[t] = make_float2((float)cs, (float)sn);
+    tab->win[t] = (float)(0.5 - 0.5 * cospi(2.0 * (double)t / (double)(S4K_N - 1)));
+}
+
+__global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __restrict__ x, int hop, int64_t rows, float* __restrict__ out,
+                                                                const S4kTables* __restrict__ tab) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    S4kSmem& sm = *reinterpret_cast<S4kSmem*>(sm_raw);
+    const int j = threadIdx.x;
+    for (int t = j; t < S4K_N; t += S4K_THREADS) {
+        sm.tw[t] = __ldg(&tab->tw[t]);
+        sm.win[t] = __ldg(&tab->win[t]);
+    }
+    __syncthreads();
+    const float inv_n = 1.0f / (float)S4K_N;
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float2* xr = x + r * hop;
+        float2 a[16];
+        // pass 1 (sub-transform size 1): inputs j + 256 q straight from global memory, windowed
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float2 v = __ldg(xr + j + 256 * q);
+            const float w = sm.win[j + 256 * q];
+            a[q] = make_float2(v.x * w, v.y * w);
+        }
+        dft16(a);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sm.buf[s4k_pad(16 * j + q)] = a[q];
+        __syncthreads();
+        // pass 2 (sub-transform size 16): twiddle W_256^(q k), k = j mod 16
+        {
+            const int k = j & 15;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) a[q] = sm.buf[s4k_pad(j + 256 * q)];
+            const float2 w1 = sm.tw[16 * k];
+            __syncthreads();
+            twiddle_powers(a, w1);
+            dft16(a);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) sm.buf[s4k_pad((j - k) * 16 + k + 16 * q)] = a[q];
+            __syncthreads();
+        }
+        // pass 3 (sub-transform size 256): twiddle W_4096^(q j); outputs X[j + 256 q]
+#pragma unroll
+        for (int q = 0; q < 16; ++q) a[q] = sm.buf[s4k_pad(j + 256 * q)];
+        const float2 w1p3 = sm.tw[j];
+        __syncthreads();                                 // the buffer is free for the next row's pass 1
+        twiddle_powers(a, w1p3);
+        dft16(a);
+        float* orow = out + r * S4K_N;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int kk = j + 256 * q;                  // bin; fftshift puts it at (kk + N/2) mod N
+            const float mag = sqrtf(a[q].x * a[q].x + a[q].y * a[q].y) * inv_n + 1e-20f;
+            orow[(kk + S4K_N / 2) & (S4K_N - 1)] = 20.0f * log10f(mag);
+        }
+    }
+}
+
+static int stft4096_launch(cudaStream_t st, const float2* x, int hop, int64_t rows, float* out, const S4kTables* tab) {
+    if (cudaFuncSetAttribute(k_stft4096_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S4kSmem)) != cudaSuccess) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>(rows, (int64_t)sms * 2);
+    k_stft4096_db<<<grid, S4K_THREADS, sizeof(S4kSmem), st>>>(x, hop, rows, out, tab);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
 template <int NFFT>
 static int stft_launch_t(cudaStream_t st, const float2* x, int64_t n, int hop, int64_t rows, float* out) {
     const size_t smem = (size_t)NFFT * 8 * 2 + (size_t)NFFT / 2 * 8 + (size_t)NFFT * 4;
@@ -80,7 +218,7 @@ static int stft_launch_t(cudaStream_t st, const float2* x, int64_t n, int hop, i
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
 }
 
-static int stft_launch(cudaStream_t st, const float2* x, int64_t n, int nfft, int hop, int64_t rows, float* out) {
+static int stft_launch(cudaStream_t st, const float2* x, int64_t n, int nfft, int hop, int64_t rows, float* out, const S4kTables* tab4k) {
     switch (nfft) {
         case 64: return stft_launch_t<64>(st, x, n, hop, rows, out);
         case 128: return stft_launch_t<128>(st, x, n, hop, rows, out);
@@ -88,7 +226,7 @@ static int stft_launch(cudaStream_t st, const float2* x, int64_t n, int nfft, in
         case 512: return stft_launch_t<512>(st, x, n, hop, rows, out);
         case 1024: return stft_launch_t<1024>(st, x, n, hop, rows, out);
         case 2048: return stft_launch_t<2048>(st, x, n, hop, rows, out);
-        case 4096: return stft_launch_t<4096>(st, x, n, hop, rows, out);
+        case 4096: return stft4096_launch(st, x, hop, rows, out, tab4k);
         case 8192: return stft_launch_t<8192>(st, x, n, hop, rows, out);
     }
     return -1;

@@ -99,6 +99,17 @@ def main():
     out["config5_stft_4096_hop1024"] = {"ms_per_second_of_iq": ms, "rows_per_s": rows / (ms * 1e-3), "MS_per_s": ns / ms / 1e3,
                                         "x_real_time": 1e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
                                         "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak, "frames_at_60fps_rows": rows / 60.0}
+    # the same on 30 s of IQ in one call: the per-call launch + synchronise cost (tens of microseconds) no longer shows
+    reps30 = 30
+    xl = xs.repeat(reps30, 1)
+    nl = ns * reps30
+    rows_l = (nl - 4096) // 1024 + 1
+    ol = torch.zeros((rows_l, 4096), dtype=torch.float32, device=dev)
+    ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xl.data_ptr(), nl, 4096, 1024, ol.data_ptr(), C.byref(r64)), reps=10)
+    by = 24.0 * nl
+    out["config5_stft_4096_hop1024_30s"] = {"ms_per_call": ms, "rows_per_s": rows_l / (ms * 1e-3), "MS_per_s": nl / ms / 1e3,
+                                            "x_real_time": 30e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
+                                            "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak}
     print(json.dumps(out, indent=1))
     sp.close()
 
