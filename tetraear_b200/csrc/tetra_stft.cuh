@@ -79,20 +79,6 @@ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 mul_mj(float2 a) { return make_float2(a.y, -a.x); }      // a * (-j)
 __device__ __forceinline__ float2 mul_pj(float2 a) { return make_float2(-a.y, a.x); }      // a * (+j)
 
-// a[q] *= w^q, q = 1..15, with the powers built by squaring and at most four products deep (a table lookup per power
-// would hit one shared-memory bank for all lanes)
-__device__ __forceinline__ void twiddle_powers(float2 (&a)[16], float2 w1) {
-    float2 w[16];
-    w[1] = w1;
-    w[2] = cmulf(w[1], w[1]);  w[3] = cmulf(w[2], w[1]);
-    w[4] = cmulf(w[2], w[2]);  w[5] = cmulf(w[4], w[1]);  w[6] = cmulf(w[4], w[2]);  w[7] = cmulf(w[4], w[3]);
-    w[8] = cmulf(w[4], w[4]);
-#pragma unroll
-    for (int q = 9; q < 16; ++q) w[q] = cmulf(w[8], w[q - 8]);
-#pragma unroll
-    for (int q = 1; q < 16; ++q) a[q] = cmulf(a[q], w[q]);
-}
-
 // b[k] = sum_n a[n] exp(-2 pi j n k / 16), in place
 __device__ __forceinline__ void dft16(float2 (&a)[16]) {
     const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
@@ -123,21 +109,28 @@ __device__ __forceinline__ void dft16(float2 (&a)[16]) {
 
 constexpr int S4K_N = 4096, S4K_THREADS = 256;
 __device__ __forceinline__ int s4k_pad(int i) { return i + (i >> 4); }
+// twiddles laid out so that a warp reads consecutive shared-memory words: tw3[q][j] = W_4096^(q j) (pass 3, thread j),
+// tw2[q][k] = W_256^(q k) (pass 2, k = j mod 16); every entry is float64 trigonometry rounded once to float32
+struct S4kTables { float2 tw3[16][256]; float2 tw2[16][16]; float win[S4K_N]; };
 struct S4kSmem {
     float2 buf[S4K_N + S4K_N / 16];
-    float2 tw[S4K_N];
-    float win[S4K_N];
+    S4kTables tab;
 };
 
-// W_4096 and the symmetric Hann window (np.hanning), float64 trigonometry rounded to float32; built once per context
-struct S4kTables { float2 tw[S4K_N]; float win[S4K_N]; };
+// the tables are built once per context
 __global__ void k_stft4096_tables(S4kTables* tab) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= S4K_N) return;
     double sn, cs;
-    sincospi(-2.0 * (double)t / (double)S4K_N, &sn, &cs);
-    tab->tw[t] = make_float2((float)cs, (float)sn);
-    tab->win[t] = (float)(0.5 - 0.5 * cospi(2.0 * (double)t / (double)(S4K_N - 1)));
+    const int q = t >> 8, j = t & 255;
+    sincospi(-2.0 * (double)((q * j) & (S4K_N - 1)) / (double)S4K_N, &sn, &cs);
+    tab->tw3[q][j] = make_float2((float)cs, (float)sn);
+    if (t < 256) {
+        const int q2 = t >> 4, k = t & 15;
+        sincospi(-2.0 * (double)((q2 * k) & 255) / 256.0, &sn, &cs);
+        tab->tw2[q2][k] = make_float2((float)cs, (float)sn);
+    }
+    tab->win[t] = (float)(0.5 - 0.5 * cospi(2.0 * (double)t / (double)(S4K_N - 1)));   // np.hanning (symmetric)
 }
 
 __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __restrict__ x, int hop, int64_t rows, float* __restrict__ out,
@@ -145,9 +138,10 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
     extern __shared__ __align__(16) unsigned char sm_raw[];
     S4kSmem& sm = *reinterpret_cast<S4kSmem*>(sm_raw);
     const int j = threadIdx.x;
-    for (int t = j; t < S4K_N; t += S4K_THREADS) {
-        sm.tw[t] = __ldg(&tab->tw[t]);
-        sm.win[t] = __ldg(&tab->win[t]);
+    {
+        const float4* src = reinterpret_cast<const float4*>(tab);
+        float4* dst = reinterpret_cast<float4*>(&sm.tab);
+        for (int t = j; t < (int)(sizeof(S4kTables) / 16); t += S4K_THREADS) dst[t] = __ldg(src + t);
     }
     __syncthreads();
     const float inv_n = 1.0f / (float)S4K_N;
@@ -158,7 +152,7 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const float2 v = __ldg(xr + j + 256 * q);
-            const float w = sm.win[j + 256 * q];
+            const float w = sm.tab.win[j + 256 * q];
             a[q] = make_float2(v.x * w, v.y * w);
         }
         dft16(a);
@@ -169,10 +163,11 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
         {
             const int k = j & 15;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) a[q] = sm.buf[s4k_pad(j + 256 * q)];
-            const float2 w1 = sm.tw[16 * k];
+            for (int q = 0; q < 16; ++q) {
+                const float2 v = sm.buf[s4k_pad(j + 256 * q)];
+                a[q] = q == 0 ? v : cmulf(v, sm.tab.tw2[q][k]);
+            }
             __syncthreads();
-            twiddle_powers(a, w1);
             dft16(a);
 #pragma unroll
             for (int q = 0; q < 16; ++q) sm.buf[s4k_pad((j - k) * 16 + k + 16 * q)] = a[q];
@@ -180,10 +175,11 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
         }
         // pass 3 (sub-transform size 256): twiddle W_4096^(q j); outputs X[j + 256 q]
 #pragma unroll
-        for (int q = 0; q < 16; ++q) a[q] = sm.buf[s4k_pad(j + 256 * q)];
-        const float2 w1p3 = sm.tw[j];
+        for (int q = 0; q < 16; ++q) {
+            const float2 v = sm.buf[s4k_pad(j + 256 * q)];
+            a[q] = q == 0 ? v : cmulf(v, sm.tab.tw3[q][j]);
+        }
         __syncthreads();                                 // the buffer is free for the next row's pass 1
-        twiddle_powers(a, w1p3);
         dft16(a);
         float* orow = out + r * S4K_N;
 #pragma unroll
