@@ -22,6 +22,8 @@
 #include "filter_design.h"
 #include "tetra_kernels.cuh"
 #include "tetra_exact.cuh"
+#include "tetra_edges.cuh"
+#include "tetra_finalize.cuh"
 #include "tetra_stft.cuh"
 
 using namespace tetra;

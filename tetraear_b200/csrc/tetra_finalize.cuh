@@ -1,0 +1,440 @@
+// KF and what follows the dibits: timing pick + differential slicer (processor.py:168-219, 102-166), bit expansion and the
+// TS1/TS2 correlator (decoder.py:140-169, 231-259), find_sync + decode()'s cascade (decoder.py:171-295, 845-856) and the
+// burst verdicts of parse_burst (protocol.py:192-347).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "tetra_exact.cuh"
+
+namespace tetra {
+
+// ----------------------------------------------------------------------------------------------
+// K_finalize: timing pick (processor.py:189-215) + soft symbols + differential slicer (:129-163)
+// ----------------------------------------------------------------------------------------------
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_MAXPH = 32;
+constexpr int FIN_B = 8;                  // symbols per thread and batch in k_finalize
+
+struct FinArgs {
+    const float2* y;         // [C][y_pitch] filtered samples at the decimated rate, layout y_index(n, sps, y_rows)
+    int64_t y_pitch;
+    int32_t y_rows;
+    int32_t L;
+    int32_t sps, step;       // samples per symbol, phase search step
+    const double* partial;   // [C][n_seg][16] power sums of the bulk kernel (or null)
+    int32_t n_seg;
+    int32_t bulk_lo, bulk_hi;  // y range already covered by `partial` (empty if bulk_lo >= bulk_hi)
+    uint8_t* dibits;         // [C][cap]
+    int64_t cap;
+    int32_t* n_dibits;       // [C]
+    float2* symbols;         // [C][cap+1] or null
+    int32_t* best_phase;     // [C] or null
+    int32_t* phase_scratch;  // [C] always written (used by later kernels)
+    uint8_t* match;          // [C][2*cap][2] or null: TS1/TS2 agreement counts, fused when cap <= FIN_DIB_SMEM
+    int32_t* sync_pos;       // [C][max_pos] or null: sync positions of decode()'s cascade (decoder.py:845-856)
+    int32_t max_pos;
+    int32_t* n_sync;         // [C]
+};
+
+constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22 (decoder.py:196-197)
+constexpr uint32_t TS2_BITS = 0x1E90DCu;   // 0111101001000011011100                      (decoder.py:198-199)
+constexpr int FIN_DIB_SMEM = 12288;         // dibits of one carrier kept in shared memory for the fused correlator
+
+// processor.py:152-161 on the differential product d = s1 * conj(s0) without the arctangent:
+//   ph < -5pi/8 -> 3, < -3pi/8 -> 2, < 3pi/8 -> 0, < 5pi/8 -> 1, else 3,   ph = atan2(im, re) in (-pi, pi].
+// With k = tan(3pi/8) the four rays are im = +-k re (re > 0: +-3pi/8) and im = -+k re (re < 0: +-5pi/8).
+__device__ __forceinline__ uint8_t slice_dqpsk(double re, double im) {
+    const double k = 2.414213562373095048801688724209698;   // 1 + sqrt(2)
+    const double kr = k * re;
+    if (re > 0.0) {
+        if (im < -kr) return 2;              // ph < -3pi/8 (and > -pi/2)
+        return im < kr ? 0 : 1;              // [-3pi/8, 3pi/8) -> 0, [3pi/8, pi/2) -> 1
+    }
+    // re <= 0: ph in [pi/2, pi] (im >= 0) or [-pi, -pi/2] (im < 0); -kr >= 0
+    if (im > 0.0 || (im == 0.0 && re == 0.0)) {
+        if (re == 0.0 && im == 0.0) return 0;   // atan2(0, 0) = 0
+        return im > -kr ? 1 : 3;             // ph < 5pi/8  <=>  im > k |re|
+    }
+    if (im == 0.0) return 3;                 // ph = pi
+    return im <= kr ? 2 : 3;                 // ph >= -5pi/8  <=>  -im >= k |re|  <=>  im <= k re
+}
+
+// ----------------------------------------------------------------------------------------------
+// TetraDecoder.find_sync (core/decoder.py:171-295) and the threshold cascade of decode() (:845-856) for one
+// carrier, by all FIN_THREADS threads of a CTA, from the MSB-first packed bit stream in shared memory.
+// The reference walks every bit offset serially (jump +250 after a hit, max_corr over the visited offsets only,
+// adaptive retry when nothing was found). Here the hits of a pass become a bit mask in parallel, one thread walks
+// the mask (a handful of jumps), and the maximum over the visited offsets is a parallel reduction.
+// ----------------------------------------------------------------------------------------------
+struct SyncScratch {
+    uint32_t mask[FIN_DIB_SMEM / 16 + 2];   // one bit per window start
+    int n_pos, max_cnt;
+};
+
+__device__ __forceinline__ void ts_counts(const uint32_t* __restrict__ bits, int i, int& c1, int& c2) {
+    const uint64_t two = ((uint64_t)bits[i >> 5] << 32) | bits[(i >> 5) + 1];
+    const uint32_t win = (uint32_t)(two >> (64 - 22 - (i & 31))) & 0x3FFFFFu;
+    c1 = 22 - __popc(win ^ TS1_BITS);
+    c2 = 22 - __popc(win ^ TS2_BITS);
+}
+// smallest agreement count c with c / 22 >= threshold, in the reference's own float64 comparison (23: none)
+__device__ __forceinline__ int sync_min_count(double thr) {
+    int c = 0;
+    while (c <= 22 && !((double)c / 22.0 >= thr)) ++c;
+    return c;
+}
+// one thread: walk the hit mask like decoder.py:231-259 (record, jump 250) -> positions
+__device__ inline int sync_walk(const uint32_t* mask, int nw, int32_t* pos, int max_pos) {
+    int n = 0, i = 0;
+    while (i < nw) {
+        int wd = i >> 5;
+        uint32_t m = mask[wd] & (0xFFFFFFFFu << (i & 31));
+        const int n_words = (nw + 31) >> 5;
+        while (m == 0 && ++wd < n_words) m = mask[wd];
+        if (m == 0) break;
+        const int p = (wd << 5) + __ffs(m) - 1;
+        if (p >= nw) break;
+        if (n < max_pos) pos[n] = p;
+        ++n;
+        i = p + 250;
+    }
+    return n;
+}
+
+// find_sync(bits, threshold) -> number of positions (written to pos[], global or shared), *max_corr
+__device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double thr, int32_t* pos, int max_pos,
+                               SyncScratch& sc, double* max_corr) {
+    const int tid = threadIdx.x;
+    const int n_words = (nw + 31) >> 5;
+    const int cmin = sync_min_count(thr);
+    // pass 1: hits (TS1 is tried first, then TS2: decoder.py:237-259)
+    for (int wd = tid; wd < n_words; wd += FIN_THREADS) {
+        uint32_t m = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int i = (wd << 5) + b;
+            if (i < nw) {
+                int c1, c2;
+                ts_counts(bits, i, c1, c2);
+                if (c1 >= cmin || c2 >= cmin) m |= 1u << b;
+            }
+        }
+        sc.mask[wd] = m;
+    }
+    if (tid == 0) sc.max_cnt = 0;
+    __syncthreads();
+    if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+    __syncthreads();
+    int n = sc.n_pos;
+    // max_corr over the VISITED offsets: everything except the 249 offsets skipped after each hit. At a visited
+    // offset TS2's correlation only counts when TS1 did not already hit.
+    const int n_known = min(n, max_pos);
+    int best = 0;
+    for (int i = tid; i < nw; i += FIN_THREADS) {
+        int lo = 0, hi = n_known;                       // last position <= i
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pos[mid] <= i) lo = mid + 1; else hi = mid; }
+        const bool skipped = lo > 0 && pos[lo - 1] < i && i < pos[lo - 1] + 250;
+        if (!skipped) {
+            int c1, c2;
+            ts_counts(bits, i, c1, c2);
+            best = max(best, c1 >= cmin ? c1 : max(c1, c2));
+        }
+    }
+    for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((tid & 31) == 0) atomicMax(&sc.max_cnt, best);
+    __syncthreads();
+    const double mc = (double)sc.max_cnt / 22.0;
+    *max_corr = mc;
+    // adaptive retry inside find_sync (decoder.py:262-281)
+    if (n == 0 && mc > 0.75 && mc >= (thr - 0.15)) {
+        const double adaptive = fmax(0.75, mc - 0.02);
+        if (adaptive < thr) {
+            const int amin = sync_min_count(adaptive);
+            __syncthreads();
+            for (int wd = tid; wd < n_words; wd += FIN_THREADS) {
+                uint32_t m = 0;
+                for (int b = 0; b < 32; ++b) {
+                    const int i = (wd << 5) + b;
+                    if (i < nw) {
+                        int c1, c2;
+                        ts_counts(bits, i, c1, c2);
+                        if (max(c1, c2) >= amin) m |= 1u << b;      // no offset was skipped: best_here = max of both
+                    }
+                }
+                sc.mask[wd] = m;
+            }
+            __syncthreads();
+            // accepted offsets block +-250 around them; scanning upwards that is the same jump-250 walk
+            if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+            __syncthreads();
+            n = sc.n_pos;
+        }
+    }
+    __syncthreads();
+    return n;
+}
+
+// decode()'s cascade 0.90 -> 0.85 -> 0.80 -> adaptive (decoder.py:845-856)
+__device__ int block_sync_cascade(const uint32_t* __restrict__ bits, int nd, int32_t* pos, int max_pos, SyncScratch& sc) {
+    const int nw = 2 * nd - 22 + 1;
+    if (nw <= 0) return 0;                              // decoder.py:226-228: fewer than 22 bits
+    double mx = 0.0;
+    int n = block_find_sync(bits, nw, 0.90, pos, max_pos, sc, &mx);
+    if (n == 0) n = block_find_sync(bits, nw, 0.85, pos, max_pos, sc, &mx);
+    if (n == 0) n = block_find_sync(bits, nw, 0.80, pos, max_pos, sc, &mx);
+    if (n == 0 && mx >= 0.75) n = block_find_sync(bits, nw, fmax(0.75, mx - 0.02), pos, max_pos, sc, &mx);
+    return n;
+}
+
+// dibits in shared memory -> MSB-first packed bits (decoder.py:140-169), one zero word behind
+__device__ __forceinline__ void pack_dibits(const uint8_t* s_dib, int nd, uint32_t* s_bits) {
+    const int n_words = (nd + 15) / 16 + 1;
+    for (int j = threadIdx.x; j < n_words; j += blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int idx = 16 * j + m;
+            w = (w << 2) | (idx < nd ? (uint32_t)(s_dib[idx] & 3u) : 0u);
+        }
+        s_bits[j] = w;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
+    __shared__ double red[FIN_THREADS];
+    __shared__ int s_best;
+    __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
+    __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
+    __shared__ SyncScratch s_sync;
+    const int car = blockIdx.x, tid = threadIdx.x;
+    const float2* __restrict__ y = a.y + (int64_t)car * a.y_pitch;
+    const int L = a.L, sps = a.sps, step = a.step;
+    const int nph = (sps + step - 1) / step;            // phases tried: 0, step, 2 step, ... (<= FIN_MAXPH)
+    int best = 0;
+    if (sps > 1) {
+        // Power sum of phase ph over n = ph + sps*k, k < cnt = (L - ph) / sps. Thread (g, p) = (tid / nph, tid % nph)
+        // owns the symbols k = g (mod G) of phase p; samples inside [bulk_lo, bulk_hi) were already summed by the
+        // fused kernel and are skipped.
+        const int G = FIN_THREADS / nph;
+        const int g = tid / nph, p = tid % nph;
+        const bool has_bulk = a.bulk_lo < a.bulk_hi;
+        double acc = 0.0;
+        if (g < G) {
+            const int ph = p * step;
+            const int cnt = (L - ph) / sps;
+            // k < k_lo_end: below the bulk; k >= k_hi_beg: above it
+            const int k_lo_end = has_bulk ? min(cnt, max(0, (a.bulk_lo - ph + sps - 1) / sps)) : cnt;
+            const int k_hi_beg = has_bulk ? max(k_lo_end, (a.bulk_hi - ph + sps - 1) / sps) : cnt;
+            for (int k = g; k < k_lo_end; k += G) {
+                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
+                acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            }
+            for (int k = k_hi_beg + g; k < cnt; k += G) {
+                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
+                acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
+            }
+        }
+        red[tid] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double best_pow = -1.0;
+            for (int pp = 0; pp < nph; ++pp) {
+                const int ph = pp * step;
+                const int cnt = (L - ph) / sps;
+                if (cnt <= 0) continue;
+                double sum = 0.0;
+                for (int gg = 0; gg < G; ++gg) sum += red[gg * nph + pp];
+                if (a.partial && has_bulk)
+                    for (int sg = 0; sg < a.n_seg; ++sg) sum += a.partial[((int64_t)car * a.n_seg + sg) * 16 + ph];
+                const double mean = sum / (double)cnt;
+                if (mean > best_pow) { best_pow = mean; best = ph; }
+            }
+            s_best = best;
+        }
+        __syncthreads();
+        best = s_best;
+    }
+    const int stride = sps > 1 ? sps : 1;
+    const int n_sym = sps > 1 ? max(0, (L - best) / sps) : L;
+    const int nd = n_sym > 1 ? n_sym - 1 : 0;
+    if (tid == 0) {
+        a.n_dibits[car] = nd;
+        if (a.best_phase) a.best_phase[car] = best;
+        a.phase_scratch[car] = best;
+    }
+    uint8_t* dib = a.dibits + (int64_t)car * a.cap;
+    float2* sym = a.symbols ? a.symbols + (int64_t)car * (a.cap + 1) : nullptr;
+    const bool fuse = (a.match != nullptr || a.sync_pos != nullptr) && nd <= FIN_DIB_SMEM;
+    // symbols k = tid + 256 j, FIN_B of them per batch with all loads of a batch issued before any use
+    // symbol k is sample best + stride k: in the phase-major layout that is row `best`, contiguous in k
+    const float2* ys = a.y_rows > 0 ? y + (int64_t)best * a.y_rows : y + best;
+    const int64_t ks = a.y_rows > 0 ? 1 : stride;
+    for (int k0 = tid; k0 < n_sym; k0 += FIN_B * FIN_THREADS) {
+        float2 s1[FIN_B], s0[FIN_B];
+#pragma unroll
+        for (int j = 0; j < FIN_B; ++j) {
+            const int k = min(k0 + j * FIN_THREADS, n_sym - 1);
+            s1[j] = ys[ks * k];
+            s0[j] = ys[ks * max(k - 1, 0)];
+        }
+#pragma unroll
+        for (int j = 0; j < FIN_B; ++j) {
+            const int k = k0 + j * FIN_THREADS;
+            if (k < n_sym) {
+                if (sym) sym[k] = s1[j];
+                if (k >= 1) {
+                    // diff = s1 * conj(s0); the products of two floats are exact in double
+                    const double re = (double)s1[j].x * s0[j].x + (double)s1[j].y * s0[j].y;
+                    const double im = (double)s1[j].y * s0[j].x - (double)s1[j].x * s0[j].y;
+                    const uint8_t d = slice_dqpsk(re, im);
+                    dib[k - 1] = d;
+                    if (fuse) s_dib[k - 1] = d;
+                }
+            }
+        }
+    }
+    if (!fuse) return;
+    // ---- fused frame-sync front end (decoder.py:140-169 bit expansion, :237-240 agreement counts, :171-295 + :845-856) ----
+    __syncthreads();
+    pack_dibits(s_dib, nd, s_bits);
+    __syncthreads();
+    const int nw = 2 * nd - 22 + 1;                     // window starts (decoder.py:232)
+    if (a.match) {
+        uint8_t* out = a.match + (int64_t)car * a.cap * 4;
+        for (int p = tid; 2 * p < nw; p += FIN_THREADS) {   // windows 2p and 2p+1 share their words
+            const int i = 2 * p;
+            const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
+            const int sh = i & 31;                          // even, <= 30: 23 bits starting at sh fit in 64
+            const uint32_t w0 = (uint32_t)(two >> (64 - 22 - sh)) & 0x3FFFFFu;
+            const uint32_t w1 = (uint32_t)(two >> (64 - 23 - sh)) & 0x3FFFFFu;
+            uchar4 o;
+            o.x = (uint8_t)(22 - __popc(w0 ^ TS1_BITS));
+            o.y = (uint8_t)(22 - __popc(w0 ^ TS2_BITS));
+            o.z = (uint8_t)(22 - __popc(w1 ^ TS1_BITS));
+            o.w = (uint8_t)(22 - __popc(w1 ^ TS2_BITS));
+            if (i + 1 < nw) *reinterpret_cast<uchar4*>(out + 2 * (int64_t)i) = o;
+            else { out[2 * (int64_t)i] = o.x; out[2 * (int64_t)i + 1] = o.y; }
+        }
+    }
+    if (a.sync_pos) {
+        const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
+        if (tid == 0) a.n_sync[car] = n;
+    }
+}
+
+// standalone: sync positions from dibit streams (the same device code; used when the streams come from elsewhere)
+struct SyncPosArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    int32_t* sync_pos; int32_t max_pos; int32_t* n_sync;
+};
+__global__ void __launch_bounds__(FIN_THREADS) k_sync_positions(const SyncPosArgs a) {
+    __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
+    __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
+    __shared__ SyncScratch s_sync;
+    const int car = blockIdx.x;
+    const int nd = min(a.n_dibits[car], FIN_DIB_SMEM);
+    const uint8_t* dib = a.dibits + (int64_t)car * a.cap;
+    for (int k = threadIdx.x; k < nd; k += FIN_THREADS) s_dib[k] = dib[k];
+    __syncthreads();
+    pack_dibits(s_dib, nd, s_bits);
+    __syncthreads();
+    const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
+    if (threadIdx.x == 0) a.n_sync[car] = n;
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_parse_bursts: what TetraDecoder.decode does with each sync position up to the burst's CRC verdict
+// (core/decoder.py:861-888 -> decode_frame :986-992 -> TetraProtocolParser.parse_burst, core/protocol.py:192-347):
+// slot start = position - 216 bits, 255 symbols; burst type from the 22 bits at bit 255 (> 0.8 agreement with either
+// sync pattern); data bits (normal burst: bits 0-107 + 122-229, sync burst: all 510); the reference's soft CRC-16-CCITT
+// check (<= 2 differing CRC bits, forward or reversed payload). One warp per (carrier, position).
+// info[car][slot] = (start_symbol or -1 when decode() drops the position, frame_number, burst_type, crc_ok)
+// ----------------------------------------------------------------------------------------------
+constexpr uint32_t SYNC_CONT_BITS = 0x343A74u;    // 1101000011101001110100 (protocol.py:162), first bit = MSB of 22
+constexpr uint32_t SYNC_DISC_BITS = 0x0E90D3u;    // 0011101001000011010011 (protocol.py:163)
+
+struct BurstArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    const int32_t* sync_pos; int32_t max_pos; const int32_t* n_sync;
+    int4* info;              // [C][max_pos]
+};
+
+// bit j of the 510-bit slot (MSB-first expansion of the symbols in shared memory)
+__device__ __forceinline__ uint32_t burst_bit(const uint8_t* sym, int j) { return (sym[j >> 1] >> (1 - (j & 1))) & 1u; }
+
+__global__ void __launch_bounds__(128) k_parse_bursts(const BurstArgs a) {
+    __shared__ uint8_t s_sym[4][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = blockIdx.x * 4 + warp, car = blockIdx.y;
+    if (slot >= a.max_pos) return;
+    int4* out = a.info + (int64_t)car * a.max_pos + slot;
+    const int nd = a.n_dibits[car];
+    const int pos = slot < a.n_sync[car] ? a.sync_pos[(int64_t)car * a.max_pos + slot] : -1;
+    const int start = pos - 216;
+    const int s0 = start >> 1;                           // start >= 0 below
+    if (pos < 0 || start < 0 || s0 + 255 > nd) {
+        if (lane == 0) *out = make_int4(-1, 0, 0, 0);
+        return;
+    }
+    uint8_t* sym = s_sym[warp];
+    const uint8_t* dib = a.dibits + (int64_t)car * a.cap + s0;
+    for (int k = lane; k < 255; k += 32) sym[k] = dib[k] & 3u;
+    __syncwarp();
+    // burst type (protocol.py:244-266)
+    uint32_t win = 0;
+    for (int j = 0; j < 22; ++j) win = (win << 1) | burst_bit(sym, 255 + j);
+    const int m = max(22 - __popc(win ^ SYNC_CONT_BITS), 22 - __popc(win ^ SYNC_DISC_BITS));
+    const bool is_sync = (double)m / 22.0 > 0.8;
+    // data bit d of the burst (protocol.py:268-289)
+    const int n_data = is_sync ? 510 : 216;
+    auto data_bit = [&](int d) { return burst_bit(sym, is_sync ? d : (d < 108 ? d : d + 14)); };
+    int ones = 0;
+    for (int d = lane; d < n_data; d += 32) ones += data_bit(d);
+    for (int o = 16; o; o >>= 1) ones += __shfl_xor_sync(0xffffffffu, ones, o);
+    // CRC-16-CCITT of the payload, MSB first, init 0xFFFF: lane 0 forward, lane 1 over the reversed payload
+    const int n_pay = n_data - 16;
+    uint32_t crc = 0xFFFFu;
+    if (lane < 2) {
+        for (int d = 0; d < n_pay; ++d) {
+            crc ^= data_bit(lane == 0 ? d : n_pay - 1 - d) << 15;
+            crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x1021u) & 0xFFFFu : (crc << 1) & 0xFFFFu;
+        }
+    }
+    uint32_t recv = 0;
+    for (int d = 0; d < 16; ++d) recv = (recv << 1) | data_bit(n_pay + d);
+    const int err = __popc((crc ^ recv) & 0xFFFFu);
+    const int err_fwd = __shfl_sync(0xffffffffu, err, 0), err_rev = __shfl_sync(0xffffffffu, err, 1);
+    const bool crc_ok = ones != 0 && ones != n_data && (err_fwd <= 2 || err_rev <= 2);
+    if (lane == 0) *out = make_int4(s0, start / 510, is_sync ? 5 : 2, crc_ok ? 1 : 0);
+}
+
+// ----------------------------------------------------------------------------------------------
+// K_sync: dibits -> bits (decoder.py:140-169) and 22-bit TS1/TS2 agreement at every bit offset
+// (decoder.py:237-240). One thread per window start.
+// ----------------------------------------------------------------------------------------------
+struct SyncArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    uint8_t* match;          // [C][2*cap][2]
+};
+
+__global__ void __launch_bounds__(256) k_sync_match(const SyncArgs a) {
+    const int car = blockIdx.y;
+    const int nd = a.n_dibits[car];
+    const int nw = 2 * nd - 22 + 1;
+    const uint8_t* dib = a.dibits + (int64_t)car * a.cap;
+    uint8_t* out = a.match + (int64_t)car * a.cap * 4;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += gridDim.x * blockDim.x) {
+        const int d0 = i >> 1;
+        uint32_t bits = 0;                              // 24 bits: dibits d0 .. d0+11, first dibit highest
+#pragma unroll
+        for (int k = 0; k < 12; ++k) {
+            const int idx = d0 + k;
+            const uint32_t v = idx < nd ? (dib[idx] & 3u) : 0u;
+            bits = (bits << 2) | v;
+        }
+        const uint32_t win = (i & 1) ? (bits & 0x7FFFFEu) >> 1 : bits >> 2;   // 22 bits, first bit = MSB
+        out[2 * (int64_t)i] = (uint8_t)(22 - __popc((win ^ TS1_BITS) & 0x3FFFFFu));
+        out[2 * (int64_t)i + 1] = (uint8_t)(22 - __popc((win ^ TS2_BITS) & 0x3FFFFFu));
+    }
+}
+
+}  // namespace tetra
