@@ -133,7 +133,7 @@ int tetra_enable_kernel_timing(tetra_ctx* ctx, int on);
 double tetra_kernel_time_ms(tetra_ctx* ctx, int32_t* n_launches);
 /* Timeline of the most recent timed fast-path call, device ms between consecutive marks on the
  * context's stream: out3[0] call start -> fused kernel done and edge windows joined,
- * out3[1] (idle), out3[2] timing pick + slicer + TS correlator. */
+ * out3[1] span of the edge-window kernel on the side stream, out3[2] timing pick + slicer + TS correlator. */
 int tetra_last_phase_ms(tetra_ctx* ctx, double* out3);
 
 /*

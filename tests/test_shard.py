@@ -52,6 +52,13 @@ def _worker(rank, world, port, n_carriers, cap, ok):
         good = np.array_equal(d_all.numpy(), dib) and np.array_equal(n_all.numpy(), nd)
         t = shard.max_over_ranks(float(rank + 1))
         good = good and t == float(world)
+        if n_carriers % world == 0:                      # the single-collective variant
+            ps = shard.PackedStreams(n_carriers, cap)
+            ps.dibits[:, :cap] = torch.from_numpy(dib[first:first + count].copy())
+            ps.n_dibits[:] = torch.from_numpy(nd[first:first + count].copy())
+            d2, n2 = ps.gather()
+            good = good and np.array_equal(d2.reshape(n_carriers, -1).numpy()[:, :cap], dib)
+            good = good and np.array_equal(n2.reshape(-1).numpy(), nd)
         ok[rank] = 1 if good else 0
     finally:
         dist.destroy_process_group()

@@ -60,12 +60,14 @@ struct tetra_ctx {
     size_t ev_used = 0;
     bool timing = false;
     cudaEvent_t ph_ev[4] = {nullptr, nullptr, nullptr, nullptr};   // call start, edges joined, finalize done (debug timeline)
+    cudaEvent_t edge_ev[2] = {nullptr, nullptr};                   // around the edge kernel on the side stream
     bool ph_valid = false;
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos, u8, stft_tab;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
+    int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
     size_t max_scratch_bytes = (size_t)6 << 30;
 };
 
@@ -271,9 +273,11 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
     CK(ctx->scr2.ensure((size_t)(wz + 2 * EX_PAD2) * nj * sizeof(double2)));
     CK(ctx->jobs.ensure(nj * sizeof(int2)));
     CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
-    // transitions for the four (mode, direction) variants of each stage
-    ctx->edge_mats.assign(4 * 5 * 64 + 4 * 5 * 16, 0.0);
-    for (int m = EX_LEFT; m <= EX_RIGHT; ++m) {
+    // transitions for the four (mode, direction) variants of each stage (they depend on the block geometry only)
+    const bool mats_cached = ctx->mats_n == ea.n && ctx->mats_q == ea.q && ctx->mats_L == ea.L && ctx->mats.p &&
+                             ctx->edge_mats.size() == 4 * 5 * 64 + 4 * 5 * 16;
+    if (!mats_cached) ctx->edge_mats.assign(4 * 5 * 64 + 4 * 5 * 16, 0.0);
+    for (int m = EX_LEFT; m <= EX_RIGHT && !mats_cached; ++m) {
         const EdgeRange rg = edge_range(m, ea.n, ea.L, ea.q, ea.edge);
         const int var = m == EX_LEFT ? 0 : 2;
         const int nf = (int)(rg.e_hi - rg.e_lo), nb = (int)(rg.e_hi - rg.e_stop);
@@ -284,8 +288,11 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
         ba_transition_powers(ea.cf, (n2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 0) * 5 * 16);
         ba_transition_powers(ea.cf, (nb2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 1) * 5 * 16);
     }
-    CK(ctx->mats.ensure(ctx->edge_mats.size() * sizeof(double)));
-    CK(cudaMemcpyAsync(ctx->mats.p, ctx->edge_mats.data(), ctx->edge_mats.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (!mats_cached) {
+        CK(ctx->mats.ensure(ctx->edge_mats.size() * sizeof(double)));
+        CK(cudaMemcpyAsync(ctx->mats.p, ctx->edge_mats.data(), ctx->edge_mats.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        ctx->mats_n = ea.n; ctx->mats_q = ea.q; ctx->mats_L = ea.L;
+    }
     EdgeWarpArgs g;
     g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
     g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.y_sps = ea.y_sps; g.e.y_rows = ea.y_rows; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
@@ -343,6 +350,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int k = 0; k < 4; ++k) if (ctx->ph_ev[k]) cudaEventDestroy(ctx->ph_ev[k]);
+    for (int k = 0; k < 2; ++k) if (ctx->edge_ev[k]) cudaEventDestroy(ctx->edge_ev[k]);
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->side);
     delete ctx;
 }
@@ -402,6 +410,11 @@ int tetra_last_phase_ms(tetra_ctx* ctx, double* out3) {
         float ms = 0.f;
         CK(cudaEventElapsedTime(&ms, ctx->ph_ev[k], ctx->ph_ev[k + 1]));
         out3[k] = ms;
+    }
+    if (ctx->edge_ev[0]) {                              // slot 1 (an empty interval on the main stream): the edge kernel's span
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->edge_ev[0], ctx->edge_ev[1]) == cudaSuccess) out3[1] = ms;
+        else cudaGetLastError();
     }
     return TETRA_OK;
 }
@@ -569,19 +582,15 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
         }
         // edge windows run beside the bulk kernel on the side stream
         if (ctx->timing) {
-            if (!ctx->ph_ev[0]) for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&ctx->ph_ev[k]));
+            if (!ctx->ph_ev[0]) {
+                for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&ctx->ph_ev[k]));
+                for (int k = 0; k < 2; ++k) CK(cudaEventCreate(&ctx->edge_ev[k]));
+            }
             CK(cudaEventRecord(ctx->ph_ev[0], st));
         }
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
-        static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
-        // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
-        if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
-        else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
-        else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
-        if (rc) return rc;
-        CK(cudaEventRecord(ctx->ev_join, ctx->side));
+        // the fused kernel goes first: its persistent CTAs (one per SM) must not queue behind the edge blocks
         cudaEvent_t t0 = nullptr, t1 = nullptr;
         if (ctx->timing && ctx->ev_used < 4096) {
             if (ctx->ev_used == ctx->ev_pool.size()) {
@@ -598,6 +607,16 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
         ctx->launches++;
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));
+        // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
+        static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
+        if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
+        // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
+        if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
+        else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
+        if (rc) return rc;
+        if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
+        CK(cudaEventRecord(ctx->ev_join, ctx->side));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;

@@ -76,6 +76,37 @@ def gather_dibits(dibits: torch.Tensor, n_dibits: torch.Tensor, n_carriers: int,
     return out_dibits, out_n
 
 
+class PackedStreams:
+    """The dibit streams and their lengths of one rank in ONE buffer, so that the exchange is a single collective:
+    ``[n_local * cap]`` uint8 dibits followed by ``[n_local]`` int32 lengths (cap is rounded up to a multiple of 4 so
+    the lengths stay aligned). ``dibits`` / ``n_dibits`` are views the demodulator writes into; ``gather()`` all-gathers
+    the buffer and returns views over the received blocks."""
+
+    def __init__(self, n_carriers: int, cap: int, device=None, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        if n_carriers % self.world:
+            raise ValueError("PackedStreams needs an even partition; use gather_dibits for ragged ones")
+        self.n_carriers, self.n_local = n_carriers, n_carriers // self.world
+        self.cap = (cap + 3) & ~3
+        self.block = self.n_local * self.cap + 4 * self.n_local
+        self.local = torch.zeros(self.block, dtype=torch.uint8, device=device)
+        self.all = torch.zeros(self.block * self.world, dtype=torch.uint8, device=device) if self.world > 1 else self.local
+        self.dibits = self.local[: self.n_local * self.cap].view(self.n_local, self.cap)
+        self.n_dibits = self.local[self.n_local * self.cap:].view(torch.int32)
+
+    def gather(self):
+        """One all-gather. Returns views over the received blocks: dibits ``[world, n_local, cap]`` (carrier c is
+        ``[c // n_local, c % n_local]``) and lengths ``[world, n_local]`` -- no copy is made."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.all, self.local, group=self.group)
+        blocks = self.all.view(self.world, self.block)
+        d = blocks[:, : self.n_local * self.cap].unflatten(1, (self.n_local, self.cap))
+        n = blocks[:, self.n_local * self.cap:].view(torch.int32)
+        return d, n
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Max of a per-rank scalar (the timing rule: a multi-GPU step takes as long as its slowest rank)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
