@@ -29,8 +29,8 @@ N_SAMPLES = 1 << 20
 TOTAL_CARRIERS = 4096
 BYTES_PER_SAMPLE = 8.10      # 8 B read + (1 B dibit + 8 B soft symbol + ~4 B match) per 130 samples
 # dram__bytes_read.sum + dram__bytes_write.sum of k1_channelize_demod per input sample, from the committed
-# ncu --set full capture (profiles/r01_k1_ncu_full_summary.txt: 4.9672 GB + 0.4876 GB for 592 carriers x 2^20)
-NCU_TRAFFIC_BYTES_PER_SAMPLE = (4.967160e9 + 0.487606e9) / (592 * (1 << 20))
+# ncu --set full capture (profiles/r01_k1_ncu_full_summary.txt: 4.9671 GB + 0.4850 GB for 592 carriers x 2^20)
+NCU_TRAFFIC_BYTES_PER_SAMPLE = (4.967148e9 + 0.484972e9) / (592 * (1 << 20))
 METRIC = "IQ MS/s demodulated"
 WORKLOAD = "configs[3]: %d carriers x 2^20 complex64 samples @2.4 MS/s, sharded %d per GPU"
 
@@ -122,7 +122,7 @@ def cpu_rate(carriers_per_core=2, cores=None, pool=None):
     return total / dt / 1e6, cores, dt
 
 
-def cpu_baseline_sample(target_s=12.0):
+def cpu_baseline_sample(target_s=20.0):
     """One bounded sample (about target_s seconds of wall time on all host cores) of the same workload."""
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
