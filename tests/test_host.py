@@ -94,3 +94,22 @@ def test_fir_tables_reproduce_reference_interior():
     y = df.simulate(x, taps, np.float32)
     err = np.abs(y - ref) / np.abs(ref).max()
     assert err[160:-160].max() < 2e-6
+
+
+def test_find_sync_replay_on_crafted_streams():
+    """Host replay (tetra_find_sync / tetra_sync_cascade) over oracle match counts on streams that reach every level of
+    decode()'s cascade: planted TS1/TS2 with 0..5 bit errors, hits closer than the 250-bit jump, noise only."""
+    rng = np.random.default_rng(11)
+    plants = [[], [(1, 20, 0)], [(2, 100, 3)], [(1, 300, 4)], [(1, 1000, 5), (2, 4000, 5)],
+              [(1, 50, 0), (1, 200, 0), (2, 299, 0), (1, 300, 0)], [(1, 6000 - 22, 1)]]
+    for pl in plants:
+        bits = rng.integers(0, 2, size=6000).astype(np.int64)
+        for pat, off, n_err in pl:
+            p = (ref_dsp.TS1 if pat == 1 else ref_dsp.TS2).copy()
+            if n_err:
+                p[rng.choice(22, size=n_err, replace=False)] ^= 1
+            bits[off:off + 22] = p
+        mc = ref_dsp.match_counts(bits).astype(np.uint8)
+        assert sync.sync_cascade(mc, len(bits) // 2) == ref_dsp.sync_cascade(bits), pl
+        for th in (0.9, 0.85, 0.8, 0.76):
+            assert sync.find_sync(mc, len(bits) // 2, th, True) == ref_dsp.find_sync(bits, th), (pl, th)
