@@ -101,6 +101,17 @@ int tetra_parse_bursts(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const
                        const int32_t* n_sync, int32_t* burst_info);
 
 /*
+ * The per-sample part of TetraSignalDetector.analyze_signal (signal/scanner.py:42-147, 204-231) for C captures
+ * (e.g. the channels of a wideband survey): calculate_power, detect_tetra_modulation, detect_sync_pattern and
+ * check_power_stability in float64.  iq [C][pitch] complex64 host or device;
+ *   out6 [C][6] float64 = (power_db, modulation_confidence, sync_correlation, power_stable (0/1),
+ *                          modulation_matches, number of phase differences); host or device.
+ * The decision thresholds stay with the caller (confidence > 0.4, correlation > 0.75, scanner.py:94, 145).
+ */
+int tetra_analyze_signal(tetra_ctx* ctx, const float* iq, int32_t n_captures, int64_t n_samples, int64_t pitch,
+                         double* out6);
+
+/*
  * tetra_process_batch_sync for RTL-SDR native samples: iq_u8 [C][pitch][2] interleaved unsigned 8-bit I, Q
  * (host or device), converted on the device exactly like pyrtlsdr's packed_bytes_to_iq does before the
  * reference sees them (RTLCapture.read_samples, signal/capture.py:143-158): (byte / 127.5) - 1.

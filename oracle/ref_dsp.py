@@ -261,6 +261,59 @@ def decode_bursts(dibits, positions):
     return out
 
 
+# scanner.py:133-134
+SCANNER_SYNC_PATTERN = np.array([0, 1, 0, 1, 1, 0, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0,
+                                 1, 0, 1, 1, 0, 0, 1, 1, 1, 0, 0, 0, 1, 0, 0], dtype=np.int64)
+
+
+def _wrapped_phase_diffs(x):
+    """diff(angle(x)) folded into [-pi, pi) exactly as scanner.py:74-75 / :113-114 do."""
+    pd = np.diff(np.angle(x))
+    return (pd + np.pi) % (2 * np.pi) - np.pi
+
+
+def analyze_signal(samples, sample_rate: float = 2.4e6, symbol_rate: float = 18000.0):
+    """The per-sample part of TetraSignalDetector.analyze_signal (signal/scanner.py:42-147, 204-231), vectorised:
+    calculate_power, detect_tetra_modulation, detect_sync_pattern, check_power_stability."""
+    x = np.asarray(samples).astype(np.complex128)
+    out = {}
+    # calculate_power (:42-55)
+    out["power_db"] = float(10 * np.log10(np.mean(np.abs(x) ** 2) + 1e-10)) if x.size else -120.0
+    # detect_tetra_modulation (:57-96)
+    if len(x) < 1000:
+        out["modulation_matches"], out["modulation_confidence"] = 0, 0.0
+    else:
+        xn = x / (np.abs(x).max() + 1e-10)
+        pd = _wrapped_phase_diffs(xn)
+        expected = np.array([-np.pi, -3 * np.pi / 4, -np.pi / 2, -np.pi / 4, 0, np.pi / 4, np.pi / 2, 3 * np.pi / 4])
+        dist = np.abs(expected[None, :] - pd[:, None]).min(axis=1)
+        m = int((dist < np.pi / 8).sum())
+        out["modulation_matches"], out["modulation_confidence"] = m, m / len(pd)
+    out["is_tetra_modulation"] = out["modulation_confidence"] > 0.4
+    # detect_sync_pattern (:98-147)
+    ds = max(1, int(sample_rate / symbol_rate / 10))
+    sym = x[::ds]
+    corr = 0.0
+    if len(sym) >= 100:
+        pd = _wrapped_phase_diffs(sym)
+        q = np.round(pd / (np.pi / 4)) * (np.pi / 4)
+        bits = (np.abs(q) < np.pi / 8).astype(np.int64)
+        if len(bits) >= 31:
+            n_win = len(bits) - 31
+            if n_win > 0:
+                win = np.lib.stride_tricks.sliding_window_view(bits, 31)[:n_win]
+                corr = float((win == SCANNER_SYNC_PATTERN).sum(axis=1).max() / 31)
+    out["sync_correlation"], out["sync_detected"] = corr, corr > 0.75
+    # check_power_stability (:204-231)
+    if len(x) < 5 * 1000:
+        out["power_stable"] = False
+    else:
+        w = len(x) // 5
+        pw = [10 * np.log10(np.mean(np.abs(x[i * w:(i + 1) * w]) ** 2) + 1e-10) for i in range(5)]
+        out["power_stable"] = bool(np.std(pw) < 10.0)
+    return out
+
+
 def spectrum_db(samples: np.ndarray, n_fft: int = 2048) -> np.ndarray:
     """modern.py:1924-1934 on the first n_fft samples."""
     w = np.hanning(n_fft)

@@ -91,3 +91,27 @@ def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
         err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
         assert err <= SOFT_TOL, err
         assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
+
+
+def test_scanner_analysis_matches_reference_golden(gpu_processor):
+    """TetraSignalDetector's per-sample analysis on the device vs the reference's own numbers."""
+    import os, sys
+    from conftest import load_golden
+    from oracle.make_golden_scanner import captures
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    g = load_golden("scanner")
+    caps = captures()
+    for name, x in caps:
+        r = sp.analyze_signal(x)
+        want = g[name]
+        assert abs(r["power_db"] - want[0]) < 1e-6, name
+        n_pd = max(len(x) - 1, 1)
+        assert abs(r["modulation_confidence"] - want[1]) <= 2.0 / n_pd, name      # decisions can differ on a boundary ulp
+        assert float(r["is_tetra_modulation"]) == want[2], name
+        assert abs(r["sync_correlation"] - want[3]) < 1e-12 and float(r["sync_detected"]) == want[4], name
+        assert float(r["power_stable"]) == want[5], name
+    same = [x for _, x in caps if len(x) == len(caps[0][1])]
+    batch = sp.analyze_signal(np.stack(same))                      # several captures in one launch
+    for r, (name, x) in zip(batch, [c for c in caps if len(c[1]) == len(caps[0][1])]):
+        assert abs(r["power_db"] - g[name][0]) < 1e-6 and abs(r["sync_correlation"] - g[name][3]) < 1e-12

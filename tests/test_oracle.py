@@ -59,3 +59,18 @@ def test_burst_parse_matches_reference_golden():
         assert (btype, int(crc_ok)) == (int(bt), int(ok))
         assert len(data) == (510 if btype == ref_dsp.BURST_SYNCHRONIZATION else 216)
     assert g["crc_ok"].sum() > 10 and (g["burst_type"] == 5).sum() > 10
+
+
+def test_scanner_analysis_matches_reference_golden():
+    """oracle analyze_signal vs TetraSignalDetector's own methods on the same seeded captures."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "oracle"))
+    from oracle.make_golden_scanner import captures
+    g = load_golden("scanner")
+    for name, x in captures():
+        r = ref_dsp.analyze_signal(x.astype(np.complex128))
+        want = g[name]
+        assert abs(r["power_db"] - want[0]) < 1e-9, name
+        assert r["modulation_confidence"] == want[1] and float(r["is_tetra_modulation"]) == want[2], name
+        assert r["sync_correlation"] == want[3] and float(r["sync_detected"]) == want[4], name
+        assert float(r["power_stable"]) == want[5], name

@@ -26,6 +26,7 @@ _SIGS = {
                                            C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]),
     "tetra_sync_positions": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p]),
+    "tetra_analyze_signal": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
     "tetra_process_batch_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p]),

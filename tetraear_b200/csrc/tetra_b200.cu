@@ -657,6 +657,38 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     return TETRA_OK;
 }
 
+int tetra_analyze_signal(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, double* out6) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || N < 0 || (C > 0 && (!out6 || (N > 0 && (!iq || pitch < N)))))
+        return fail(ctx, TETRA_E_INVALID, "tetra_analyze_signal: bad arguments");
+    if (C == 0) return TETRA_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int ds = std::max(1, (int)(ctx->sample_rate / 18000.0 / 10.0));      // scanner.py:108
+    const int64_t n_bits = (N + ds - 1) / ds;
+    if (n_bits > ANA_MAXBITS) return fail(ctx, TETRA_E_UNSUPPORTED, "tetra_analyze_signal: capture too long (%lld crude bits > %d)", (long long)n_bits, ANA_MAXBITS);
+    const float2* dx = (const float2*)iq;
+    int64_t dpitch = pitch;
+    if (N > 0 && !is_device_ptr(iq)) {
+        CK(ctx->in.ensure((size_t)C * N * sizeof(float2)));
+        if (pitch == N) CK(cudaMemcpyAsync(ctx->in.p, iq, (size_t)C * N * sizeof(float2), cudaMemcpyHostToDevice, st));
+        else CK(cudaMemcpy2DAsync(ctx->in.p, N * sizeof(float2), iq, pitch * sizeof(float2), N * sizeof(float2), C, cudaMemcpyHostToDevice, st));
+        dx = (const float2*)ctx->in.p;
+        dpitch = N;
+    }
+    const bool d_out = is_device_ptr(out6);
+    double* dout = out6;
+    if (!d_out) { CK(ctx->tmp_c.ensure(sizeof(double) * 6 * C)); dout = (double*)ctx->tmp_c.p; }
+    const size_t smem = ((size_t)(n_bits + 31) / 32 + 2) * sizeof(uint32_t);
+    CK(cudaFuncSetAttribute(k_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_analyze<<<C, ANA_THREADS, smem, st>>>(dx, dpitch, N, ds, dout);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (!d_out) CK(cudaMemcpyAsync(out6, dout, sizeof(double) * 6 * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
 int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t C, int64_t N, int64_t pitch,
                            const double* fo_hz, uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols,
                            int32_t* best_phase, uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync) {

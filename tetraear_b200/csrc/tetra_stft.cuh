@@ -243,6 +243,114 @@ __global__ void k_nco_c128(double2* x, int64_t n, double fo, double fs) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// k_analyze: the per-sample part of TetraSignalDetector.analyze_signal (signal/scanner.py:42-147, 204-231) for C captures
+// at once: power, the pi/4 phase-step clustering score, the 31-bit sync pattern correlation on crude bits, and the
+// power-stability verdict. float64 throughout (the reference works on complex128). One CTA per capture.
+//   out[c] = (power_db, modulation_confidence, sync_correlation, power_stable, modulation_matches, n_phase_diffs)
+// ----------------------------------------------------------------------------------------------
+constexpr int ANA_THREADS = 512;
+constexpr int ANA_MAXBITS = 1 << 20;                   // crude bits kept bit-packed in shared memory (128 KB)
+constexpr uint32_t ANA_PATTERN = 0x2CE259C4u;          // 0101100111000100101100111000100 (scanner.py:133-134), first bit = MSB of 31
+
+__device__ __forceinline__ double ana_wrap(double d) {  // (d + pi) % (2 pi) - pi with Python's modulo
+    const double t = d + M_PI;
+    return (t - (2.0 * M_PI) * floor(t / (2.0 * M_PI))) - M_PI;
+}
+__device__ __forceinline__ double ana_block_sum(double v, double* red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < ANA_THREADS / 32; ++w) t += red[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restrict__ x, int64_t pitch, int64_t n, int ds, double* __restrict__ out) {
+    extern __shared__ uint32_t s_bits[];                // ceil(nbits / 32) + 2 words
+    __shared__ double red[ANA_THREADS / 32];
+    __shared__ unsigned long long s_max;
+    __shared__ int s_best;
+    const int tid = threadIdx.x;
+    const float2* xc = x + (int64_t)blockIdx.x * pitch;
+    double* o = out + 6 * (int64_t)blockIdx.x;
+    if (tid == 0) { s_max = 0ull; s_best = 0; }
+    __syncthreads();
+    // ---- power (scanner.py:42-55), per-window powers (:204-231) and max |x| (:72) ----
+    const int64_t wlen = n / 5;
+    double tot = 0.0, win[5] = {0, 0, 0, 0, 0}, mx = 0.0;
+    for (int64_t i = tid; i < n; i += ANA_THREADS) {
+        const float2 v = __ldg(xc + i);
+        const double p = (double)v.x * v.x + (double)v.y * v.y;
+        tot += p;
+        mx = fmax(mx, hypot((double)v.x, (double)v.y));
+        if (wlen > 0) {
+            const int64_t w = i / wlen;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) if (w == k) win[k] += p;
+        }
+    }
+    tot = ana_block_sum(tot, red);
+    double wsum[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) wsum[k] = ana_block_sum(win[k], red);
+    atomicMax(&s_max, (unsigned long long)__double_as_longlong(mx));
+    __syncthreads();
+    const double scale = __longlong_as_double((long long)s_max) + 1e-10;
+    // ---- detect_tetra_modulation (:57-96) ----
+    double matches = 0.0;
+    if (n >= 1000) {
+        for (int64_t i = 1 + tid; i < n; i += ANA_THREADS) {
+            const float2 a = __ldg(xc + i), b = __ldg(xc + i - 1);
+            const double d = ana_wrap(atan2((double)a.y / scale, (double)a.x / scale) - atan2((double)b.y / scale, (double)b.x / scale));
+            double best = 1e9;
+#pragma unroll
+            for (int k = -4; k < 4; ++k) best = fmin(best, fabs((double)k * (M_PI / 4.0) - d));
+            matches += best < M_PI / 8.0 ? 1.0 : 0.0;
+        }
+    }
+    matches = ana_block_sum(matches, red);
+    // ---- detect_sync_pattern (:98-147): every ds-th sample, bit = 1 where the phase step rounds to 0 ----
+    const int64_t n_sym = (n + ds - 1) / ds;
+    const int64_t n_bits = n_sym >= 100 ? n_sym - 1 : 0;
+    const int n_words = (int)((n_bits + 31) / 32) + 2;
+    for (int w = tid; w < n_words; w += ANA_THREADS) s_bits[w] = 0u;
+    __syncthreads();
+    for (int64_t j = tid; j < n_bits; j += ANA_THREADS) {
+        const float2 a = __ldg(xc + (j + 1) * ds), b = __ldg(xc + j * ds);
+        const double d = ana_wrap(atan2((double)a.y, (double)a.x) - atan2((double)b.y, (double)b.x));
+        const double q = rint(d / (M_PI / 4.0)) * (M_PI / 4.0);     // numpy round: half to even
+        if (fabs(q) < M_PI / 8.0) atomicOr(&s_bits[j >> 5], 0x80000000u >> (j & 31));
+    }
+    __syncthreads();
+    int best = 0;
+    for (int64_t i = tid; i < n_bits - 31; i += ANA_THREADS) {        // range(len(bits) - 31): the last window is not tried
+        const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
+        const uint32_t w31 = (uint32_t)(two >> (64 - 31 - (i & 31))) & 0x7FFFFFFFu;
+        best = max(best, 31 - __popc(w31 ^ ANA_PATTERN));
+    }
+    for (int of = 16; of; of >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, of));
+    if ((tid & 31) == 0) atomicMax(&s_best, best);
+    __syncthreads();
+    if (tid == 0) {
+        o[0] = n > 0 ? 10.0 * log10(tot / (double)n + 1e-10) : -120.0;
+        o[1] = n >= 1000 ? matches / (double)(n - 1) : 0.0;
+        o[2] = (double)s_best / 31.0;
+        double stable = 0.0;
+        if (n >= 5 * 1000) {
+            double p[5], mean = 0.0, var = 0.0;
+            for (int k = 0; k < 5; ++k) { p[k] = 10.0 * log10(wsum[k] / (double)wlen + 1e-10); mean += p[k]; }
+            mean /= 5.0;
+            for (int k = 0; k < 5; ++k) var += (p[k] - mean) * (p[k] - mean);
+            stable = sqrt(var / 5.0) < 10.0 ? 1.0 : 0.0;
+        }
+        o[3] = stable;
+        o[4] = matches;
+        o[5] = n >= 1000 ? (double)(n - 1) : 0.0;
+    }
+}
+
 // RTL-SDR native samples (interleaved unsigned 8-bit I, Q) -> complex64, the conversion pyrtlsdr's
 // packed_bytes_to_iq applies before the reference ever sees the data (signal/capture.py:143-158 ->
 // RtlSdr.read_samples):  iq = (byte / 127.5) - 1   per component. 8 samples (16 bytes in, 64 bytes out) per thread step.

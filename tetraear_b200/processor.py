@@ -306,6 +306,23 @@ class SignalProcessor:
                                                  ns.ctypes.data, info.ctypes.data), "parse_bursts")
         return [[tuple(int(v) for v in info[c, k]) for k in range(ns[c]) if info[c, k, 0] >= 0] for c in range(n_car)]
 
+    def analyze_signal(self, captures):
+        """The per-sample part of ``TetraSignalDetector.analyze_signal`` (signal/scanner.py:42-147, 204-231) for one
+        capture [N] or several [C, N]: a dict (or list of dicts) with power_db, modulation_confidence,
+        is_tetra_modulation (> 0.4), sync_correlation, sync_detected (> 0.75) and power_stable."""
+        self._sync_rate()
+        x = np.ascontiguousarray(captures, dtype=np.complex64)
+        one = x.ndim == 1
+        if one:
+            x = x[None, :]
+        n_cap, n = x.shape
+        out = np.zeros((n_cap, 6), dtype=np.float64)
+        self._check(self._lib.tetra_analyze_signal(self._ctx, x.ctypes.data, n_cap, n, n, out.ctypes.data), "analyze_signal")
+        res = [dict(power_db=float(r[0]), modulation_confidence=float(r[1]), is_tetra_modulation=bool(r[1] > 0.4),
+                    sync_correlation=float(r[2]), sync_detected=bool(r[2] > 0.75), power_stable=bool(r[3] > 0.5),
+                    modulation_matches=int(r[4])) for r in out]
+        return res[0] if one else res
+
     def dibit_capacity(self, n_samples: int) -> int:
         self._sync_rate()
         return int(self._lib.tetra_dibit_capacity(self._ctx, int(n_samples)))
