@@ -102,6 +102,33 @@ def test_freq_offset_outside_fused_range_uses_exact_path(gpu_processor):
     assert np.abs(sp.symbols - r["symbols"]).max() / np.abs(r["symbols"]).max() <= SOFT_TOL
 
 
+def test_full_size_batch_of_64_carriers_bit_exact(gpu_processor):
+    """BASELINE size: 64 carriers x 2^20 samples (SNR 15..35 dB, both alphabets, as bench.py builds them) in one call,
+    every one of them against the oracle: dibits identical, timing phase identical, soft symbols within 1e-5, sync
+    positions of the device cascade identical (SURVEY 8d, config 4 subset)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n, n_car, n_base = 1 << 20, 64, 8
+    base = [synth.carrier_iq(n, 500 + s, snr_db=40.0, alphabet="centred" if s % 2 else "pi4") for s in range(n_base)]
+    rng = np.random.default_rng(64)
+    snr = rng.uniform(15.0, 35.0, size=n_car)
+    xs = np.empty((n_car, n), dtype=np.complex64)
+    for c in range(n_car):
+        sigma = np.sqrt(10.0 ** (-snr[c] / 10.0) / 2.0)
+        xs[c] = base[c % n_base] + (sigma * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    res = sp.process_batch(xs, None, want_symbols=True, want_sync=True)
+    for c in range(n_car):
+        r = ref_dsp.process(xs[c].astype(np.complex128), 0.0, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]), c
+        assert int(res["best_phase"][c]) == r["best_phase"], c
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), c
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, err)
+        want = ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
+        assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == want, c
+
+
 def test_full_size_properties(gpu_processor):
     """BASELINE size (2^20): structural checks that do not need the oracle."""
     sp = gpu_processor
