@@ -124,6 +124,7 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_interp, TB_INTERP_TAPS, sizeof(float) * TB_INT_K));
     CK(cudaFuncSetAttribute(k1_channelize_demod<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     ctx->tables_uploaded = true;
     return 0;
 }
@@ -426,9 +427,24 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
                                     nullptr, 0, nullptr, async);
 }
 
+// chan_hz == nullptr: C carriers [C][pitch]. chan_hz != nullptr (config 3): iq is ONE capture of N samples and carrier c is
+// its channel at offset chan_hz[c], i.e. process(frequency_shift(iq, chan_hz[c]), 0); needs the fused path's conditions.
+static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                        uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                        uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async,
+                        const double* chan_hz);
+
 int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                              uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
                              uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async) {
+    return process_impl(ctx, iq, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, sync_pos, max_pos,
+                        n_sync, async, nullptr);
+}
+
+static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                        uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                        uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async,
+                        const double* chan_hz) {
     if (!ctx) return TETRA_E_INVALID;
     if ((sync_pos != nullptr) != (n_sync != nullptr) || (sync_pos && max_pos <= 0))
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_sync: sync_pos, n_sync and max_positions go together");
@@ -464,7 +480,15 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     // ---- input on device ----
     const float2* d_x;
     int64_t x_pitch = pitch;
-    if (d_in) d_x = (const float2*)iq;
+    if (chan_hz) {
+        if (d_in) d_x = (const float2*)iq;
+        else {
+            CK(ctx->tmp_a.ensure((size_t)N * sizeof(float2)));
+            CK(cudaMemcpyAsync(ctx->tmp_a.p, iq, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, st));
+            d_x = (const float2*)ctx->tmp_a.p;
+        }
+        x_pitch = 0;                                   // every channel reads the same capture
+    } else if (d_in) d_x = (const float2*)iq;
     else {
         CK(ctx->in.ensure((size_t)C * N * sizeof(float2)));
         if (pitch == N) CK(cudaMemcpyAsync(ctx->in.p, iq, (size_t)C * N * sizeof(float2), cudaMemcpyHostToDevice, st));
@@ -485,6 +509,7 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     // The fused path covers freq_offset = 0 (MODE 0) and, with per-carrier complex taps, |freq_offset| <= 12.5 kHz
     // (MODE 1: the GUI's AFC range, ui/modern.py:1949-1967); anything else runs the exact recursion over the block.
     const bool use_fast = fast_ok && (!any_fo || fo_in_range);
+    if (chan_hz && (!use_fast || any_fo)) return fail(ctx, TETRA_E_UNSUPPORTED, "wideband channels need the fused path (fs 2.4 MS/s, >= 16384 samples)");
     for (int c = 0; c < C; ++c) {
         if (use_fast) edge_jobs.push_back(make_int2(c, EX_LEFT));
         else full_jobs.push_back(make_int2(c, EX_FULL));
@@ -492,9 +517,9 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     // LEFT jobs first, then RIGHT: the two window shapes differ in length, keep warps homogeneous
     for (size_t k = 0, n_left = edge_jobs.size(); k < n_left; ++k) edge_jobs.push_back(make_int2(edge_jobs[k].x, EX_RIGHT));
     const double* d_fo = nullptr;
-    if (any_fo) {
+    if (any_fo || chan_hz) {
         CK(ctx->fo.ensure(sizeof(double) * C));
-        CK(cudaMemcpyAsync(ctx->fo.p, fo_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ctx->fo.p, chan_hz ? chan_hz : fo_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
         d_fo = (const double*)ctx->fo.p;
     }
 
@@ -532,7 +557,20 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
     ea.x32 = d_x; ea.pitch = x_pitch; ea.n = N; ea.q = pl.q; ea.L = (int32_t)pl.L;
     ea.has_s1 = pl.has_s1; ea.has_s2 = pl.has_s2;
     fill_coef(ea.cf, pl.has_s1 ? pl.q : 1, pl.wn);
-    ea.fo = d_fo; ea.fs_dec = pl.rate;
+    ea.fo = chan_hz ? nullptr : d_fo; ea.fs_dec = pl.rate;
+    if (chan_hz) {
+        // the exact edge kernels take each channel's shifted stream; only the block-end windows they read are formed
+        CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
+        int64_t w1 = 0, wz = 0, w1r = 0;
+        exact_extents(EX_LEFT, N, pl.L, pl.q, K1_EDGE, true, &w1, &wz);
+        exact_extents(EX_RIGHT, N, pl.L, pl.q, K1_EDGE, true, &w1r, &wz);
+        const int64_t len0 = std::min<int64_t>(N, w1 + 64), len1 = std::min<int64_t>(N, w1r + 64);
+        k_mix_wide_ranges<<<dim3((unsigned)((len0 + len1 + 255) / 256), C), 256, 0, st>>>(d_x, N, d_fo, ctx->sample_rate, (float2*)ctx->wide.p,
+                                                                                         0, len0, N - len1, len1);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        ea.x32 = (const float2*)ctx->wide.p; ea.pitch = N;
+    }
     ea.y32 = (float2*)ctx->y.p; ea.y_pitch = y_pitch; ea.y_sps = y_sps; ea.y_rows = y_rows; ea.edge = K1_EDGE;
 
     FinArgs fa;
@@ -568,7 +606,7 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
         ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg; ka.n_items = n_items; ka.t_item = std::max(seg_len / K1_W + 1, K1_MIN_T_ITEM);
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.y_rows = y_rows; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
-        ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate;
+        ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
         if (any_fo) {
             // this batch's complex fir120 tables, designed on the device from the same IIR coefficients
             CK(ctx->ctaps.ensure((size_t)C * 128 * sizeof(float2)));
@@ -602,7 +640,8 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
             ctx->ev_used++;
             CK(cudaEventRecord(t0, st));
         }
-        if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+        if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+        else if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
         ctx->launches++;
         CK(cudaGetLastError());
@@ -736,6 +775,15 @@ int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const dou
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     if (N == 0) return tetra_process_batch(ctx, nullptr, C, 0, 0, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, 0);
+    // fused: the capture is read as is, each channel's shift is folded into stage A of the fused kernel (MODE 2)
+    {
+        const Plan pl = make_plan(ctx->sample_rate, N);
+        const bool fast_ok = ctx->sample_rate == 2.4e6 && pl.q == 10 && pl.has_s1 && pl.has_s2 && N >= 16384 && pl.sps == K1_NPH;
+        if (fast_ok)
+            return process_impl(ctx, iq, C, N, N, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, nullptr, 0, nullptr, 0,
+                                channel_hz);
+    }
+    // otherwise: expand the capture to C baseband streams and run them as ordinary carriers
     const float2* dx = (const float2*)iq;
     if (!is_device_ptr(iq)) {
         CK(ctx->tmp_a.ensure((size_t)N * sizeof(float2)));

@@ -121,6 +121,7 @@ struct K1SmemFo {
     K1Smem base;
     float2 ph[2][K1_W];
     float2 ctap[2][128];
+    float2 ptap[2][48];     // MODE 2: this channel's modulated proto taps
 };
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
@@ -146,6 +147,7 @@ struct K1Args {
     const double* fo;       // [C] Hz
     const float2* ctaps;    // [C][128] complex fir120 taps for each carrier's offset (k_design_fo_taps)
     double fs_dec;          // 240000
+    double fs;              // 2.4e6 (MODE 2: the rate the channel offsets refer to)
 };
 
 // one quarter (taps 32 q .. 32 q + 31 of the 128-entry table c_fir) of ten consecutive fir120 outputs;
@@ -260,9 +262,20 @@ __device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a,
     }
 }
 
+// modulated proto taps of a channel at offset f: q[d] = c_proto[d] exp(-j 2 pi f (d - 20) / fs). With them and the w rotation
+// exp(-j 2 pi f 10 m / fs) stage A computes proto(x[n] exp(-j 2 pi f n / fs)) without ever forming the shifted stream.
+__device__ __forceinline__ float2 k1_modulated_tap(int d, double f, double fs) {
+    double sn, cs;
+    const double turns = f * (double)(d - TB_PROTO_H) / fs;
+    sincospi(-2.0 * (turns - rint(turns)), &sn, &cs);
+    return make_float2((float)((double)c_proto[d] * cs), (float)((double)c_proto[d] * sn));
+}
+
 // MODE 0: freq_offset == 0 (real fir120 taps from constant memory). MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w
 // samples are rotated by the NCO phasor (stage B's warps prepare them one iteration ahead) and stage C applies the
-// carrier's complex taps  B2(f) C2(f + f_off) / (HB(f) P(f + f_off)).
+// carrier's complex taps  B2(f) C2(f + f_off) / (HB(f) P(f + f_off)). MODE 2 (config 3): every "carrier" is a channel of ONE
+// shared wideband capture (pitch 0) at offset fo[c]: process(frequency_shift(x, f_c), 0) with the shift folded into
+// stage A (modulated proto taps + w rotation), so the capture is read as is and never expanded.
 template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Args a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -287,9 +300,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
-    if (MODE == 1) {
+    if (MODE >= 1) {
         const K1Slot s0 = k1_slot(a, 0);
-        if (tid < 128) sf.ctap[0][tid] = a.ctaps[(int64_t)s0.car * 128 + tid];
+        if (MODE == 1 && tid < 128) sf.ctap[0][tid] = a.ctaps[(int64_t)s0.car * 128 + tid];
+        if (MODE == 2 && tid < 2 * TB_PROTO_H + 1) sf.ptap[0][tid] = k1_modulated_tap(tid, a.fo[s0.car], a.fs);
         if (tid >= 256 && tid < 320)                      // phasors of iteration 0: w [A0, A0 + 640) of slot 0
             k1_phasors10(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &sf.ph[0][10 * (tid - 256)]);
     }
@@ -314,6 +328,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
                 const int L5 = tid;                            // 0..127
                 const int64_t gx0 = slot_gx + (int64_t)t * K1_TILE;
+                const int q_now = q;                           // slot of the tile being filtered
                 if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
                 mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
                 if (gx0 < a.n && gx0 + K1_TILE > 0) {          // tiles entirely outside the block carry nothing
@@ -329,15 +344,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         for (int h = 0; h < 2; ++h) {
                             const int tt = 2 * t2 + h;
                             const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
+                            const float2 xs = make_float2(-xv.y, xv.x);      // j * x (MODE 2)
 #pragma unroll
                             for (int g = 0; g < 5; ++g) {
                                 const int d = tt - 10 * g;
-                                if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                                if (d >= 0 && d <= 40) {
+                                    if (MODE == 2) {
+                                        const float2 tp = sf.ptap[q_now & 1][d];
+                                        acc[g] = ffma2(xv, tp.x, acc[g]);
+                                        acc[g] = ffma2(xs, tp.y, acc[g]);
+                                    } else {
+                                        acc[g] = ffma2(xv, c_proto[d], acc[g]);
+                                    }
+                                }
                             }
                         }
                     }
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
-                    if (MODE == 1) {                        // frequency_shift at the decimated rate (processor.py:259-261)
+                    if (MODE >= 1) {                        // MODE 1: frequency_shift at the decimated rate (processor.py:259-261)
 #pragma unroll
                         for (int g = 0; g < 5; ++g) {
                             const float2 p = sf.ph[i & 1][5 * L5 + g];
@@ -408,14 +432,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
 #pragma unroll
             for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
-            if (MODE == 1 && i + 1 < n_load) {
+            if (MODE >= 1 && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
                 k1_phasors10(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_W * tn + K1_A0 + 10 * lb, &sf.ph[(i + 1) & 1][10 * lb]);
-                if (tn == 0) {
+                if (tn == 0 && MODE == 1) {
                     sf.ctap[qn & 1][2 * lb] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb];
                     sf.ctap[qn & 1][2 * lb + 1] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb + 1];
                 }
+                if (tn == 0 && MODE == 2 && lb < 2 * TB_PROTO_H + 1) sf.ptap[qn & 1][lb] = k1_modulated_tap(lb, a.fo[sn.car], a.fs);
                 if (++tn == a.t_item) { tn = 0; ++qn; if (qn < n_my) sn = k1_slot(a, qn); }
             }
             k1_bar_sync();

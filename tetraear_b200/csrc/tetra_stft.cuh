@@ -407,6 +407,24 @@ __global__ void __launch_bounds__(256) k_mix_wide(const float2* __restrict__ x, 
     }
 }
 
+// the same for two index ranges [lo0, lo0 + len0) and [lo1, lo1 + len1) only: the block-end windows the exact edge
+// kernels read when the fused kernel takes the capture as is (MODE 2)
+__global__ void __launch_bounds__(256) k_mix_wide_ranges(const float2* __restrict__ x, int64_t n, const double* __restrict__ freqs,
+                                                           double fs, float2* __restrict__ out, int64_t lo0, int64_t len0,
+                                                           int64_t lo1, int64_t len1) {
+    const int c = blockIdx.y;
+    const double w = (2.0 * M_PI) * freqs[c];
+    float2* oc = out + (int64_t)c * n;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < len0 + len1; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t < len0 ? lo0 + t : lo1 + (t - len0);
+        if (i < 0 || i >= n) continue;
+        double sn, cs;
+        sincos(-(w * ((double)i / fs)), &sn, &cs);
+        const float2 v = __ldg(x + i);
+        oc[i] = make_float2((float)((double)v.x * cs - (double)v.y * sn), (float)((double)v.x * sn + (double)v.y * cs));
+    }
+}
+
 // extract_symbols (processor.py:179-219) on complex128: res[0] = n_symbols, res[1] = best phase
 __global__ void __launch_bounds__(256) k_extract_c128(const double2* x, int64_t n, int sps, int step, double2* out, int64_t* res) {
     __shared__ double red[8];
