@@ -198,20 +198,24 @@ __device__ __forceinline__ void k1_fir_quarter_cplx(const float2* __restrict__ u
 
 __device__ __forceinline__ void k1_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
-// NCO phasors exp(-j 2 pi f m / fs_dec) of ten consecutive w samples starting at global index m0 (float64 phase,
-// reduced to one turn before the sine/cosine: processor.py:97-100 evaluated at the decimated rate)
-__device__ __forceinline__ void k1_phasors10(double fo, double fs_dec, int64_t m0, float2* dst) {
-    const double turns = fo * (double)m0 / fs_dec;
-    double sn, cs, sr, cr;
-    sincospi(-2.0 * (turns - rint(turns)), &sn, &cs);
-    const double step = fo / fs_dec;
-    sincospi(-2.0 * step, &sr, &cr);
+// NCO phasors exp(-j 2 pi f m / fs_dec) (processor.py:97-100 evaluated at the decimated rate). The float64 phase is reduced
+// to one turn before the sine/cosine. One out-of-line copy: it runs once per slot and thread, not once per tile.
+struct K1Phasor { double c, s; };
+__device__ __noinline__ void k1_phasor_setup(double fo, double fs_dec, int64_t m0, K1Phasor* base, K1Phasor* step1, K1Phasor* step_tile) {
+    double turns = fo * (double)m0 / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &base->s, &base->c);
+    turns = fo / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &step1->s, &step1->c);
+    turns = fo * (double)K1_W / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &step_tile->s, &step_tile->c);
+}
+__device__ __forceinline__ K1Phasor k1_rot(K1Phasor p, K1Phasor r) { return K1Phasor{p.c * r.c - p.s * r.s, p.c * r.s + p.s * r.c}; }
+// ten consecutive phasors starting at `base`, rounded to float32
+__device__ __forceinline__ void k1_phasors10(K1Phasor base, K1Phasor step1, float2* dst) {
 #pragma unroll
     for (int g = 0; g < 10; ++g) {
-        dst[g] = make_float2((float)cs, (float)sn);
-        const double c2 = cs * cr - sn * sr;
-        sn = cs * sr + sn * cr;
-        cs = c2;
+        dst[g] = make_float2((float)base.c, (float)base.s);
+        base = k1_rot(base, step1);
     }
 }
 
@@ -304,8 +308,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         const K1Slot s0 = k1_slot(a, 0);
         if (MODE == 1 && tid < 128) sf.ctap[0][tid] = a.ctaps[(int64_t)s0.car * 128 + tid];
         if (MODE == 2 && tid < 2 * TB_PROTO_H + 1) sf.ptap[0][tid] = k1_modulated_tap(tid, a.fo[s0.car], a.fs);
-        if (tid >= 256 && tid < 320)                      // phasors of iteration 0: w [A0, A0 + 640) of slot 0
-            k1_phasors10(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &sf.ph[0][10 * (tid - 256)]);
+        if (tid >= 256 && tid < 320) {                    // phasors of iteration 0: w [A0, A0 + 640) of slot 0
+            K1Phasor b0, r1, rt;
+            k1_phasor_setup(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &b0, &r1, &rt);
+            k1_phasors10(b0, r1, &sf.ph[0][10 * (tid - 256)]);
+        }
     }
     __syncthreads();
     if (warp == 0) {
@@ -414,6 +421,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         const int lb = tid - 256;                           // 0..63
         int qn = 1 / a.t_item, tn = 1 % a.t_item;           // (slot, tile) of the tile stage A filters next iteration
         K1Slot sn = k1_slot(a, qn);
+        // MODE >= 1: phasor of this thread's first w sample of that tile, advanced by one tile per iteration inside a slot
+        // (float64 rotations: ~1e-16 per step over the <= 170 tiles of a slot) and set up afresh when a slot opens
+        K1Phasor pbase = {1.0, 0.0}, pstep1 = {1.0, 0.0}, pstep_tile = {1.0, 0.0};
+        if (MODE >= 1 && qn < n_my)
+            k1_phasor_setup(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_W * tn + K1_A0 + 10 * lb, &pbase, &pstep1, &pstep_tile);
         for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
             float2 acc[5];
@@ -435,13 +447,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (MODE >= 1 && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
-                k1_phasors10(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_W * tn + K1_A0 + 10 * lb, &sf.ph[(i + 1) & 1][10 * lb]);
+                k1_phasors10(pbase, pstep1, &sf.ph[(i + 1) & 1][10 * lb]);
                 if (tn == 0 && MODE == 1) {
                     sf.ctap[qn & 1][2 * lb] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb];
                     sf.ctap[qn & 1][2 * lb + 1] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb + 1];
                 }
                 if (tn == 0 && MODE == 2 && lb < 2 * TB_PROTO_H + 1) sf.ptap[qn & 1][lb] = k1_modulated_tap(lb, a.fo[sn.car], a.fs);
-                if (++tn == a.t_item) { tn = 0; ++qn; if (qn < n_my) sn = k1_slot(a, qn); }
+                if (++tn == a.t_item) {
+                    tn = 0; ++qn;
+                    if (qn < n_my) {
+                        sn = k1_slot(a, qn);
+                        k1_phasor_setup(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_A0 + 10 * lb, &pbase, &pstep1, &pstep_tile);
+                    }
+                } else {
+                    pbase = k1_rot(pbase, pstep_tile);
+                }
             }
             k1_bar_sync();
         }
