@@ -102,6 +102,25 @@ def test_freq_offset_outside_fused_range_uses_exact_path(gpu_processor):
     assert np.abs(sp.symbols - r["symbols"]).max() / np.abs(r["symbols"]).max() <= SOFT_TOL
 
 
+def test_unaligned_batches_and_small_blocks(gpu_processor):
+    """Carriers whose rows are not 16-byte aligned (odd block length: the fused kernel copies tiles by hand instead of
+    bulk copies) and the smallest block the fused path takes, several carriers per call, with and without freq_offset."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    for n, fos in ((100003, [0.0, 0.0, 0.0]), (50001, [0.0, 2500.0, -800.0]), (16384, [0.0] * 5), (16385, [1000.0] * 4)):
+        xs = np.stack([synth.carrier_iq(n, 700 + c, snr_db=22.0, alphabet="centred" if c % 2 else "pi4") for c in range(len(fos))])
+        res = sp.process_batch(xs, fos, want_symbols=True, want_sync=True)
+        for c, fo in enumerate(fos):
+            r = ref_dsp.process(xs[c].astype(np.complex128), fo, 2.4e6)
+            nd = int(res["n_dibits"][c])
+            assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], (n, c)
+            assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), (n, c)
+            err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+            assert err <= SOFT_TOL, (n, c, err)
+            want = ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
+            assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == want, (n, c)
+
+
 def test_full_size_batch_of_64_carriers_bit_exact(gpu_processor):
     """BASELINE size: 64 carriers x 2^20 samples (SNR 15..35 dB, both alphabets, as bench.py builds them) in one call,
     every one of them against the oracle: dibits identical, timing phase identical, soft symbols within 1e-5, sync
