@@ -107,3 +107,25 @@ def test_parse_bursts_matches_reference_golden(gpu_processor):
         want = ref_dsp.decode_bursts(dib[c], [int(p) for p in spos[c, :3]])
         assert got[c] == want, c
         assert len(got[c]) == 1 and got[c][0][2:] == (int(g["burst_type"][c]), int(g["crc_ok"][c])), c
+
+
+def test_sync_positions_random_streams_property(gpu_processor):
+    """128 random dibit streams of ragged length with random plants (0-6 bit errors): device cascade == oracle."""
+    sp = gpu_processor
+    rng = np.random.default_rng(4242)
+    n_car, cap = 128, 3000
+    d = rng.integers(0, 4, size=(n_car, cap), dtype=np.uint8)
+    nd = rng.integers(11, cap + 1, size=n_car).astype(np.int32)
+    for c in range(n_car):
+        bits = ref_dsp.symbols_to_bits(d[c, :nd[c]])
+        for _ in range(int(rng.integers(0, 7))):
+            off = int(rng.integers(0, len(bits) - 22 + 1))
+            p = (ref_dsp.TS1 if rng.integers(0, 2) else ref_dsp.TS2).copy()
+            n_err = int(rng.integers(0, 7))
+            if n_err:
+                p[rng.choice(22, size=n_err, replace=False)] ^= 1
+            bits[off:off + 22] = p
+        d[c, :nd[c]] = _bits_to_dibits(bits)
+    got = sp.sync_positions(d, nd)
+    for c in range(n_car):
+        assert got[c] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(d[c, :nd[c]])), c

@@ -113,3 +113,30 @@ def test_find_sync_replay_on_crafted_streams():
         assert sync.sync_cascade(mc, len(bits) // 2) == ref_dsp.sync_cascade(bits), pl
         for th in (0.9, 0.85, 0.8, 0.76):
             assert sync.find_sync(mc, len(bits) // 2, th, True) == ref_dsp.find_sync(bits, th), (pl, th)
+
+
+def test_sync_replay_and_c_oracle_agree_on_random_streams():
+    """Property check over 60 random bit streams (random length, 0-6 planted training sequences with 0-6 bit errors):
+    host replay of device-style match counts == numpy oracle == C oracle, for the cascade and for single thresholds."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(2025)
+    for trial in range(60):
+        n_bits = int(rng.integers(22, 5000))
+        bits = rng.integers(0, 2, size=n_bits).astype(np.int64)
+        for _ in range(int(rng.integers(0, 7))):
+            if n_bits <= 22:
+                break
+            off = int(rng.integers(0, n_bits - 22 + 1))
+            p = (ref_dsp.TS1 if rng.integers(0, 2) else ref_dsp.TS2).copy()
+            n_err = int(rng.integers(0, 7))
+            if n_err:
+                p[rng.choice(22, size=n_err, replace=False)] ^= 1
+            bits[off:off + 22] = p
+        want = ref_dsp.sync_cascade(bits)
+        assert c_oracle.sync_cascade(bits.astype(np.uint8)) == want, trial
+        if n_bits % 2 == 0:
+            mc = ref_dsp.match_counts(bits).astype(np.uint8)
+            assert sync.sync_cascade(mc, n_bits // 2) == want, trial
+            th = float(rng.choice([0.9, 0.85, 0.8, 0.77]))
+            assert sync.find_sync(mc, n_bits // 2, th, True) == ref_dsp.find_sync(bits, th), (trial, th)
+            assert c_oracle.find_sync(bits.astype(np.uint8), th) == ref_dsp.find_sync(bits, th), (trial, th)
