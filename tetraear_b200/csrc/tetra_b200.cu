@@ -2,10 +2,11 @@
 //
 // Mirrors the control flow of the reference's SignalProcessor.process
 // (tetraear/signal/processor.py:221-273) for a batch of carriers, choosing between
-//   * the fused FIR-cascade kernel (k1_channelize_demod) + exact edge windows, when the block is
-//     long, fs = 2.4 MS/s and freq_offset = 0, and
+//   * the fused FIR-cascade kernel (k1_channelize_demod<MODE>, persistent) + exact edge windows on a second stream, when
+//     fs = 2.4 MS/s, the block has >= 16384 samples and |freq_offset| <= 12.5 kHz (MODE 1 when any offset is non-zero,
+//     MODE 2 for the channels of one wideband capture), and
 //   * the exact-recursion kernel over the whole block otherwise,
-// then the timing pick / slicer kernel and the training-sequence correlator.
+// then the timing pick / slicer / TS correlator / sync cascade kernel.
 // There is no CPU fallback: without a CUDA device every compute entry point fails.
 #include <cuda_runtime.h>
 #include <stdint.h>

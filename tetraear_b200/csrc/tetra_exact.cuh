@@ -1,9 +1,10 @@
 // Exact-recursion kernels: the reference's zero-phase IIR chain evaluated literally (fp64,
 // SciPy's sosfiltfilt / filtfilt padding and initial-condition rules) on a window of a block.
 //
-// Used (a) for the block edges of the fast path, where filtfilt is not shift-invariant
-// (SURVEY.md 7.3 H3), (b) as the complete path for short blocks, other sample rates and
-// non-zero freq_offset, (c) by the public helper entry points (filter_signal, ...).
+// k_exact_chain here is (a) the complete path for short blocks, other sample rates and freq_offset
+// beyond the fused kernel's range, (b) the engine of the public helper entry points (filter_signal, ...).
+// The block ends of the fused path, where filtfilt is not shift-invariant, have their
+// own kernels in tetra_edges.cuh; the shared pieces (padding, initial conditions, y layout) live here.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -62,16 +62,16 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 }
 
 // ----------------------------------------------------------------------------------------------
-// K1  channelize_demod_fused  (fast path, fs = 2.4 MS/s, freq_offset = 0)
+// K1  channelize_demod_fused  (fused path, fs = 2.4 MS/s)
 // ----------------------------------------------------------------------------------------------
-// One CTA streams one (carrier, segment) through the four FIR stages
-//   A proto /10 -> B half-band /2 -> C fir120 (129 taps) -> D x2 interp + store + |y|^2 phase sums
+// A persistent CTA streams its (carrier, segment) items back to back through the four FIR stages
+//   A proto /10 -> B half-band /2 -> C fir120 (127 taps) -> D x2 interp + store + |y|^2 phase sums
 // with every stage working, in the same iteration, on data produced in earlier iterations, so a
-// single __syncthreads per 6400-sample tile is the only block-wide barrier. IQ tiles arrive by
+// single bar.sync per 6400-sample tile is the only block-wide barrier. IQ tiles arrive by
 // 1-D TMA bulk copies into a 3-deep ring, two tiles ahead of the compute.
 //
 // Stage C keeps its accumulators in registers across four iterations: each of its four warps owns
-// every fourth group of 320 outputs and adds one quarter of the 129 taps per iteration (oldest
+// every fourth group of 320 outputs and adds one quarter of the taps per iteration (oldest
 // inputs first), so no partial sums ever go through shared memory.
 constexpr int K1_TILE = 6400;             // input samples per iteration
 constexpr int K1_HDR = 40;                // samples of the previous tile kept in front of each buffer
