@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const int kk = j + 256 * q;                  // bin; fftshift puts it at (kk + N/2) mod N
-            const float mag = sqrtf(a[q].x * a[q].x + a[q].y * a[q].y) * inv_n + 1e-20f;
-            orow[(kk + S4K_N / 2) & (S4K_N - 1)] = 20.0f * log10f(mag);
+            // 20 log10(m) = 6.0206 log2(m) through the hardware log2 (absolute error ~2e-7 in log2, i.e. ~1e-6 dB)
+            const float mag = __fsqrt_rn(a[q].x * a[q].x + a[q].y * a[q].y) * inv_n + 1e-20f;
+            orow[(kk + S4K_N / 2) & (S4K_N - 1)] = 6.020599913f * __log2f(mag);
         }
     }
 }
