@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(STFT_THREADS) k_stft_db(const float2* __restri
         float* orow = out + r * NFFT;
         for (int k = tid; k < NFFT; k += STFT_THREADS) {
             const float2 v = src[(k + NFFT / 2) & (NFFT - 1)];   // fftshift
-            const float mag = sqrtf(v.x * v.x + v.y * v.y) * inv_n + 1e-20f;
-            orow[k] = 20.0f * log10f(mag);
+            const float mag = __fsqrt_rn(v.x * v.x + v.y * v.y) * inv_n + 1e-20f;
+            orow[k] = 6.020599913f * __log2f(mag);          // 20 log10(m) through the hardware log2 (~1e-6 dB)
         }
         __syncthreads();
     }
