@@ -5,7 +5,7 @@
 //   scipy.signal.cheby1(8, 0.05, 0.8/q, 'sos')      inside scipy.signal.decimate, processor.py:254
 // This is an independent implementation of the published method (analog prototype ->
 // frequency pre-warp -> bilinear transform -> polynomial / second-order sections), so that the
-// library needs no Python at run time. tests/test_design.py checks it against SciPy.
+// library needs no Python at run time. tests/test_host.py checks it against SciPy.
 #pragma once
 #include <cmath>
 #include <complex>
