@@ -66,7 +66,7 @@ struct tetra_ctx {
     int64_t launches = 0;
     std::string err;
     bool tables_uploaded = false;
-    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, ctaps, spos, u8, stft_tab;
+    DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
     size_t max_scratch_bytes = (size_t)6 << 30;
@@ -123,6 +123,7 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaMemcpyToSymbol(c_hb, TB_HB_TAPS, sizeof(float) * (2 * TB_HB_H + 1)));
     CK(cudaMemcpyToSymbol(c_fir, fir, sizeof fir));
     CK(cudaMemcpyToSymbol(c_interp, TB_INTERP_TAPS, sizeof(float) * TB_INT_K));
+    CK(cudaMemcpyToSymbol(c_req, TB_REQ_CHEB, sizeof TB_REQ_CHEB));
     CK(cudaFuncSetAttribute(k1_channelize_demod<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
@@ -347,7 +348,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->ctaps, &ctx->spos, &ctx->u8, &ctx->stft_tab};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -607,18 +608,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg; ka.n_items = n_items; ka.t_item = std::max(seg_len / K1_W + 1, K1_MIN_T_ITEM);
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.y_rows = y_rows; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
-        ka.fo = d_fo; ka.ctaps = nullptr; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
-        if (any_fo) {
-            // this batch's complex fir120 tables, designed on the device from the same IIR coefficients
-            CK(ctx->ctaps.ensure((size_t)C * 128 * sizeof(float2)));
-            FoDesignArgs fd;
-            fd.fo = d_fo; fd.fs = ctx->sample_rate; fd.fs_dec = pl.rate; fd.ctaps = (float2*)ctx->ctaps.p;
-            memcpy(fd.sos, ea.cf.sos, sizeof fd.sos); memcpy(fd.b, ea.cf.b, sizeof fd.b); memcpy(fd.a, ea.cf.a, sizeof fd.a);
-            k_design_fo_taps<<<C, 128, 0, st>>>(fd);
-            ctx->launches++;
-            CK(cudaGetLastError());
-            ka.ctaps = (const float2*)ctx->ctaps.p;
-        }
+        ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
         // edge windows run beside the bulk kernel on the side stream
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {

@@ -79,25 +79,29 @@ constexpr int K1_W = K1_TILE / 10;        // 640 w (240 kS/s) samples per iterat
 constexpr int K1_U = K1_TILE / 20;        // 320 u/v (120 kS/s) samples per iteration
 constexpr int K1_NBUF = 3;
 constexpr int K1_WRING = 2048, K1_URING = 2048, K1_VRING = 1024;
+constexpr int K1_RRING = 512;             // MODE 1: ring of half-band outputs waiting for the equaliser
 constexpr int K1_THREADS = 384;           // warps 0-3: A, 4-7: C, 8-9: B, 10-11: D
 constexpr int K1_DLANES = 64;
 constexpr int K1_CQ = 4;                  // tap quarters = iterations a C group stays in registers
 // local (stream-origin relative) index ranges produced in iteration i
 constexpr int K1_A0 = -2;                 // w: [640 i + A0, +640)
-constexpr int K1_B0 = -326;               // u: [320 i + B0, +320)
-constexpr int K1_C0 = -614;               // v group g: [320 g + C0, +320), finished in iteration g + 3
-constexpr int K1_D0 = -1902;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
+constexpr int K1_B0 = -326;               // u: [320 i + B0, +320) (MODE 1: the half-band output before the equaliser)
+constexpr int K1_R0 = K1_B0 - 8;          // MODE 1: equalised u [320 i + R0, +320), from the same iteration's half-band output
+constexpr int K1_C0 = -622;               // v group g: [320 g + C0, +320), finished in iteration g + 3
+constexpr int K1_D0 = -1910;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
 constexpr int K1_PREROLL = 320;           // pre-roll and post-roll of a slot in w samples (> the cascade's reach of 157)
 constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
 constexpr int K1_NPH = 13;
 constexpr int K1_MIN_T_ITEM = 6;           // a slot outlasts stage C's lag behind stage A (two tap buffers suffice)
 constexpr double K1_FO_MAX_HZ = 12500.0;  // freq_offset range of the fused path (the proto's alias nulls cover +-60 kHz +- this)
 
-static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K == 8, "tables changed: re-derive lags");
+static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K == 8 && TB_REQ_K == 5, "tables changed: re-derive lags");
 // dependency checks (each stage only reads what earlier iterations produced)
 static_assert(2 * (K1_B0 + K1_U - 1) + TB_HB_H <= K1_A0 - 1, "B reads w of a later iteration");
 // quarter q of group g runs in iteration g + q and reads u up to 320 g + C0 + 319 - 64 + 32 q + 31 (+1 for the 129th tap)
-static_assert((K1_C0 + K1_U - 1) - 64 + 31 <= K1_B0 - 1, "C quarter 0 reads u of a later iteration");
+static_assert((K1_C0 + K1_U - 1) - 64 + 31 <= K1_R0 - 1, "C quarter 0 reads u of a later iteration");
+static_assert(K1_R0 + K1_U - 1 + TB_REQ_K <= K1_B0 + K1_U - 1, "the equaliser reads half-band output of a later iteration");
+static_assert(K1_U + 8 + 2 * TB_REQ_K <= K1_RRING, "equaliser ring too small");
 static_assert((K1_C0 + K1_U - 1) - 64 + 32 * 3 + 31 <= 2 * K1_U + K1_B0 + K1_U - 1, "C quarter 3 reads u of a later iteration");
 // D in iteration i reads v up to 320 i + D0 + 319 + 8; finished groups then: g <= i - 4
 static_assert((K1_D0 + K1_U - 1) + TB_INT_K <= -K1_CQ * K1_U + K1_C0 + K1_U - 1, "D reads v of an unfinished group");
@@ -105,6 +109,7 @@ static_assert((K1_A0 + K1_W) - (2 * K1_B0 - TB_HB_H) <= K1_WRING, "w ring too sm
 static_assert((3 * K1_U + K1_B0 + K1_U) - (K1_C0 - 64 + 32 * 3) <= K1_URING, "u ring too small");
 static_assert((-3 * K1_U + K1_C0 + K1_U) - (K1_D0 - TB_INT_K) <= K1_VRING, "v ring too small");
 static_assert((K1_C0 % 2) == 0 && (K1_D0 % 2) == 0 && (K1_PREROLL % 2) == 0, "16-byte aligned ring reads need even offsets");
+static_assert(TB_FIR_H + TB_REQ_K + 2 * TB_HB_H + 2 < K1_PREROLL, "pre-roll shorter than the cascade's reach");
 static_assert((2 * K1_D0) % 2 == 0, "y pairs must start on even samples");
 
 struct K1Smem {
@@ -115,19 +120,23 @@ struct K1Smem {
     double bins[K1_NPH][K1_DLANES];
     uint64_t full[K1_NBUF];
 };
-// freq_offset != 0 variant: the NCO phasors of the w samples of the current / next iteration and this
-// carrier's complex fir120 taps
+// freq_offset != 0 variant: the NCO phasors of the w samples of the current / next iteration, the half-band
+// output ring and this carrier's equaliser taps
 struct K1SmemFo {
     K1Smem base;
     float2 ph[2][K1_W];
-    float2 ctap[2][128];
+    float2 ur[K1_RRING];    // MODE 1: half-band output before the equaliser
+    float2 rtap[2][16];     // MODE 1: equaliser taps r[-5..5] of the slot (by slot parity)
     float2 ptap[2][48];     // MODE 2: this channel's modulated proto taps
 };
+
+static_assert(sizeof(K1SmemFo) <= 227 * 1024, "K1 shared memory exceeds the 227 KB a CTA may use");
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
 __constant__ float c_hb[2 * TB_HB_H + 1];
 __constant__ float c_fir[128];                    // c_fir[0] = 0, c_fir[1 + k] = fir120 tap k (127 taps): v[n] = sum_k c_fir[k] u[n - 64 + k]
 __constant__ float c_interp[TB_INT_K];
+__constant__ double c_req[(TB_REQ_DEG + 1) * (2 * TB_REQ_K + 1) * 2];   // Chebyshev series of the equaliser taps (taps_generated.h)
 
 struct K1Args {
     const float2* x;        // [C][pitch]
@@ -143,9 +152,8 @@ struct K1Args {
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x base/pitch allow 16-byte bulk copies
-    // MODE 1 (freq_offset != 0) only
-    const double* fo;       // [C] Hz
-    const float2* ctaps;    // [C][128] complex fir120 taps for each carrier's offset (k_design_fo_taps)
+    // MODE >= 1 only
+    const double* fo;       // [C] Hz: freq_offset (MODE 1) / channel offset (MODE 2)
     double fs_dec;          // 240000
     double fs;              // 2.4e6 (MODE 2: the rate the channel offsets refer to)
 };
@@ -170,53 +178,37 @@ __device__ __forceinline__ void k1_fir_quarter(const float2* __restrict__ u, int
     }
 }
 
-// the same with this carrier's complex taps (freq_offset != 0): acc += x * (tr + j ti)
-__device__ __forceinline__ void k1_fir_quarter_cplx(const float2* __restrict__ u, int s0, const float2* __restrict__ taps,
-                                                    float2 (&acc)[10]) {
-    float2 tp[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) tp[k] = taps[k];         // broadcast shared-memory loads
-#pragma unroll
-    for (int t2 = 0; t2 < 21; ++t2) {
-        const float4 v = *reinterpret_cast<const float4*>(&u[(s0 + 2 * t2) & (K1_URING - 1)]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int t = 2 * t2 + h;
-            const float2 xv = h ? make_float2(v.z, v.w) : make_float2(v.x, v.y);
-            const float2 xs = make_float2(-xv.y, xv.x);    // j * x
-#pragma unroll
-            for (int r = 0; r < 10; ++r) {
-                const int k = t - r;
-                if (k >= 0 && k < 32) {
-                    acc[r] = ffma2(xv, tp[k].x, acc[r]);
-                    acc[r] = ffma2(xs, tp[k].y, acc[r]);
-                }
-            }
-        }
-    }
-}
-
 __device__ __forceinline__ void k1_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
 
 // NCO phasors exp(-j 2 pi f m / fs_dec) (processor.py:97-100 evaluated at the decimated rate). The float64 phase is reduced
 // to one turn before the sine/cosine. One out-of-line copy: it runs once per slot and thread, not once per tile.
 struct K1Phasor { double c, s; };
-__device__ __noinline__ void k1_phasor_setup(double fo, double fs_dec, int64_t m0, K1Phasor* base, K1Phasor* step1, K1Phasor* step_tile) {
-    double turns = fo * (double)m0 / fs_dec;
-    sincospi(-2.0 * (turns - rint(turns)), &base->s, &base->c);
-    turns = fo / fs_dec;
-    sincospi(-2.0 * (turns - rint(turns)), &step1->s, &step1->c);
-    turns = fo * (double)K1_W / fs_dec;
-    sincospi(-2.0 * (turns - rint(turns)), &step_tile->s, &step_tile->c);
-}
+struct K1PhasorSet {
+    K1Phasor base, step_tile;   // phasor of sample m0; rotation over one tile (640 samples)
+    float2 pw[10];              // rotation over g = 0..9 samples, rounded to float32
+};
 __device__ __forceinline__ K1Phasor k1_rot(K1Phasor p, K1Phasor r) { return K1Phasor{p.c * r.c - p.s * r.s, p.c * r.s + p.s * r.c}; }
-// ten consecutive phasors starting at `base`, rounded to float32
-__device__ __forceinline__ void k1_phasors10(K1Phasor base, K1Phasor step1, float2* dst) {
+__device__ __noinline__ void k1_phasor_setup(double fo, double fs_dec, int64_t m0, K1PhasorSet* out) {
+    double turns = fo * (double)m0 / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &out->base.s, &out->base.c);
+    turns = fo * (double)K1_W / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &out->step_tile.s, &out->step_tile.c);
+    K1Phasor step1, p = {1.0, 0.0};
+    turns = fo / fs_dec;
+    sincospi(-2.0 * (turns - rint(turns)), &step1.s, &step1.c);
 #pragma unroll
     for (int g = 0; g < 10; ++g) {
-        dst[g] = make_float2((float)base.c, (float)base.s);
-        base = k1_rot(base, step1);
+        out->pw[g] = make_float2((float)p.c, (float)p.s);
+        p = k1_rot(p, step1);
     }
+}
+// ten consecutive phasors starting at `base`: the float64 base rounded once, times the float32 short rotations
+// (|error| < 2e-7, no serial chain)
+__device__ __forceinline__ void k1_phasors10(K1Phasor base, const float2 (&pw)[10], float2* dst) {
+    const float bc = (float)base.c, bs = (float)base.s;
+#pragma unroll
+    for (int g = 0; g < 10; ++g)
+        dst[g] = make_float2(fmaf(bc, pw[g].x, -bs * pw[g].y), fmaf(bc, pw[g].y, bs * pw[g].x));
 }
 
 // Work items and slots. An item is one (carrier, segment); CTA b of a grid of G persistent CTAs owns items
@@ -275,9 +267,23 @@ __device__ __forceinline__ float2 k1_modulated_tap(int d, double f, double fs) {
     return make_float2((float)((double)c_proto[d] * cs), (float)((double)c_proto[d] * sn));
 }
 
-// MODE 0: freq_offset == 0 (real fir120 taps from constant memory). MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w
-// samples are rotated by the NCO phasor (stage B's warps prepare them one iteration ahead) and stage C applies the
-// carrier's complex taps  B2(f) C2(f + f_off) / (HB(f) P(f + f_off)). MODE 2 (config 3): every "carrier" is a channel of ONE
+// tap k (0..10 <-> lag -5..5) of the freq_offset equaliser: Clenshaw sum of its Chebyshev series in f_off / 12.5 kHz
+__device__ __forceinline__ float2 k1_req_tap(int k, double fo) {
+    const double x = fo * (1.0 / TB_REQ_FOMAX), x2 = 2.0 * x;
+    double br1 = 0.0, br2 = 0.0, bi1 = 0.0, bi2 = 0.0;
+#pragma unroll 1
+    for (int j = TB_REQ_DEG; j >= 1; --j) {
+        const double* c = c_req + (j * (2 * TB_REQ_K + 1) + k) * 2;
+        const double tr = x2 * br1 - br2 + c[0], ti = x2 * bi1 - bi2 + c[1];
+        br2 = br1; br1 = tr; bi2 = bi1; bi1 = ti;
+    }
+    return make_float2((float)(x * br1 - br2 + c_req[2 * k]), (float)(x * bi1 - bi2 + c_req[2 * k + 1]));
+}
+
+// MODE 0: freq_offset == 0. MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w samples are rotated by the NCO phasor (stage
+// B's warps prepare them one iteration ahead), which leaves proto and the Chebyshev response acting at f + f_off; stage B
+// makes up the difference R(f) = [C2(f+f_off)/P(f+f_off)] / [C2(f)/P(f)] with an 11-tap complex equaliser on its half-band
+// output (taps: k1_req_tap), and stage C runs the same real fir120 as MODE 0. MODE 2 (config 3): every "carrier" is a channel of ONE
 // shared wideband capture (pitch 0) at offset fo[c]: process(frequency_shift(x, f_c), 0) with the shift folded into
 // stage A (modulated proto taps + w rotation), so the capture is read as is and never expanded.
 template <int MODE>
@@ -306,12 +312,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
     if (MODE >= 1) {
         const K1Slot s0 = k1_slot(a, 0);
-        if (MODE == 1 && tid < 128) sf.ctap[0][tid] = a.ctaps[(int64_t)s0.car * 128 + tid];
+        if (MODE == 1 && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
+        if (MODE == 1) for (int i = tid; i < K1_RRING; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
         if (MODE == 2 && tid < 2 * TB_PROTO_H + 1) sf.ptap[0][tid] = k1_modulated_tap(tid, a.fo[s0.car], a.fs);
         if (tid >= 256 && tid < 320) {                    // phasors of iteration 0: w [A0, A0 + 640) of slot 0
-            K1Phasor b0, r1, rt;
-            k1_phasor_setup(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &b0, &r1, &rt);
-            k1_phasors10(b0, r1, &sf.ph[0][10 * (tid - 256)]);
+            K1PhasorSet ps;
+            k1_phasor_setup(a.fo[s0.car], a.fs_dec, (int64_t)s0.O + K1_A0 + 10 * (tid - 256), &ps);
+            k1_phasors10(ps.base, ps.pw, &sf.ph[0][10 * (tid - 256)]);
         }
     }
     __syncthreads();
@@ -388,8 +395,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         float2 cacc[10];                                    // outputs of the group in flight
 #pragma unroll
         for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
-        // slot of stream coordinate 640 i + 2 C0 + PREROLL (the kept outputs of group i), kept incrementally (MODE 1)
-        int qc = k1_floordiv(2 * K1_C0 + K1_PREROLL, S), rc = 2 * K1_C0 + K1_PREROLL - qc * S;
         for (int i = 0; i < n_iter; ++i) {
             const int q = (i - (warp - 4)) & 3;             // this warp's group is g = i - q
             const int nu0 = K1_U * (i - q) + K1_C0 + 10 * lane;   // first output (stream v index), even
@@ -398,16 +403,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                 for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
             }
-            if (MODE == 1) {
-                // taps of the slot this group's kept outputs belong to (two slots can be in flight in stage C)
-                // group g = i - q lies q iterations back: at most one slot back (a slot is >= 6 iterations long)
-                const int qs = min(max(rc - K1_W * q < 0 ? qc - 1 : qc, 0), n_my - 1);
-                k1_fir_quarter_cplx(s.u, s0, sf.ctap[qs & 1] + 32 * q, cacc);
-                rc += K1_W;
-                if (rc >= S) { rc -= S; ++qc; }
-            } else {
-                k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
-            }
+            k1_fir_quarter(s.u, s0, c_fir + 32 * q, cacc);
             if (q == 3) {
 #pragma unroll
                 for (int r = 0; r < 10; r += 2)
@@ -421,11 +417,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         const int lb = tid - 256;                           // 0..63
         int qn = 1 / a.t_item, tn = 1 % a.t_item;           // (slot, tile) of the tile stage A filters next iteration
         K1Slot sn = k1_slot(a, qn);
-        // MODE >= 1: phasor of this thread's first w sample of that tile, advanced by one tile per iteration inside a slot
-        // (float64 rotations: ~1e-16 per step over the <= 170 tiles of a slot) and set up afresh when a slot opens
-        K1Phasor pbase = {1.0, 0.0}, pstep1 = {1.0, 0.0}, pstep_tile = {1.0, 0.0};
+        // MODE >= 1: phasor of this thread's first w sample of that tile (float64), advanced by one tile per iteration inside
+        // a slot (~1e-16 per step over the <= 170 tiles of a slot) and set up afresh when a slot opens
+        K1Phasor pbase = {1.0, 0.0}, pstep_tile = {1.0, 0.0};
+        float2 pw[10];
+#pragma unroll
+        for (int g = 0; g < 10; ++g) pw[g] = make_float2(1.f, 0.f);
+        // the out-of-line setup writes through memory; the loop keeps plain register copies
+        auto open_slot = [&](const K1Slot& sl, int tile) {
+            K1PhasorSet ps;
+            k1_phasor_setup(a.fo[sl.car], a.fs_dec, (int64_t)sl.O + K1_W * tile + K1_A0 + 10 * lb, &ps);
+            pbase = ps.base; pstep_tile = ps.step_tile;
+#pragma unroll
+            for (int g = 0; g < 10; ++g) pw[g] = ps.pw[g];
+        };
+        // MODE 1: slot of stream coordinate 640 i + 2 R0 + PREROLL (the kept outputs of the equalised range), kept incrementally
+        int qr = k1_floordiv(2 * K1_R0 + K1_PREROLL, S), rr = 2 * K1_R0 + K1_PREROLL - qr * S;
         if (MODE >= 1 && qn < n_my)
-            k1_phasor_setup(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_W * tn + K1_A0 + 10 * lb, &pbase, &pstep1, &pstep_tile);
+            open_slot(sn, tn);
         for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
             float2 acc[5];
@@ -442,22 +451,50 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         acc[r] = ffma2(xv, c_hb[d], acc[r]);
                 }
             }
+            if (MODE == 1) {
+                // half-band output -> ring, then the carrier's equaliser over this and earlier iterations' entries
 #pragma unroll
-            for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
+                for (int r = 0; r < 5; ++r) sf.ur[(nu0 + r) & (K1_RRING - 1)] = acc[r];
+                asm volatile("bar.sync 1, 64;" ::: "memory");
+                // taps of the slot the kept outputs of this range belong to (kept outputs lie PREROLL inside their slot)
+                const float2* tp = sf.rtap[min(max(qr, 0), n_my - 1) & 1];
+                const int ne0 = K1_U * i + K1_R0 + 5 * lb;
+                float2 e[5];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) e[r] = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 5 + 2 * TB_REQ_K; ++t) {          // ur[ne0 - 5 + t]
+                    const float2 xv = sf.ur[(ne0 - TB_REQ_K + t) & (K1_RRING - 1)];
+                    const float2 xs = make_float2(-xv.y, xv.x);      // j * x
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        const int k = r + TB_REQ_K - (t - TB_REQ_K);    // out[n] += r_lag u[n - lag], lag = r - (t - 5) ... index lag + 5
+                        if (k >= 0 && k <= 2 * TB_REQ_K) {
+                            const float2 c = tp[k];
+                            e[r] = ffma2(xv, c.x, e[r]);
+                            e[r] = ffma2(xs, c.y, e[r]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 5; ++r) s.u[(ne0 + r) & (K1_URING - 1)] = e[r];
+                rr += K1_W;
+                if (rr >= S) { rr -= S; ++qr; }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
+            }
             if (MODE >= 1 && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
-                k1_phasors10(pbase, pstep1, &sf.ph[(i + 1) & 1][10 * lb]);
-                if (tn == 0 && MODE == 1) {
-                    sf.ctap[qn & 1][2 * lb] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb];
-                    sf.ctap[qn & 1][2 * lb + 1] = a.ctaps[(int64_t)sn.car * 128 + 2 * lb + 1];
-                }
+                k1_phasors10(pbase, pw, &sf.ph[(i + 1) & 1][10 * lb]);
+                if (tn == 0 && MODE == 1 && lb < 2 * TB_REQ_K + 1) sf.rtap[qn & 1][lb] = k1_req_tap(lb, a.fo[sn.car]);
                 if (tn == 0 && MODE == 2 && lb < 2 * TB_PROTO_H + 1) sf.ptap[qn & 1][lb] = k1_modulated_tap(lb, a.fo[sn.car], a.fs);
                 if (++tn == a.t_item) {
                     tn = 0; ++qn;
                     if (qn < n_my) {
                         sn = k1_slot(a, qn);
-                        k1_phasor_setup(a.fo[sn.car], a.fs_dec, (int64_t)sn.O + K1_A0 + 10 * lb, &pbase, &pstep1, &pstep_tile);
+                        open_slot(sn, 0);
                     }
                 } else {
                     pbase = k1_rot(pbase, pstep_tile);
@@ -557,70 +594,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             k1_bar_sync();
         }
         if (q_cur >= 0 && q_cur < n_my) flush(n_iter);
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// k_design_fo_taps: the complex fir120 table of one carrier with freq_offset f_off,
-//   Gc(f) = B2(f) C2(f + f_off) / (HB(f) P(f + f_off))   on |f| < 60 kHz at 120 kS/s,
-// by frequency sampling (FO_NG points) and an inverse DFT truncated to 127 taps -- the same recipe
-// tools/design_filters.py uses for the real table. Everything in float64; one CTA per carrier.
-// Layout as c_fir: ctaps[0] = 0, ctaps[k] = g[lag = 64 - k]  (v[n] = sum_k ctaps[k] u[n - 64 + k]).
-// ----------------------------------------------------------------------------------------------
-constexpr int FO_NG = 1024;
-struct FoDesignArgs {
-    const double* fo;        // [C] Hz
-    double sos[4][6];        // cheby1(8, 0.05, 0.08) sections at fs
-    double b[5], a[5];       // butter(4, 12.5k / 120k) at fs_dec
-    double fs, fs_dec;
-    float2* ctaps;           // [C][128]
-};
-
-__global__ void __launch_bounds__(128) k_design_fo_taps(const FoDesignArgs g) {
-    __shared__ double T[FO_NG];
-    __shared__ double2 tw[FO_NG];
-    const int car = blockIdx.x, tid = threadIdx.x;
-    const double fo = g.fo[car];
-    for (int i = tid; i < FO_NG; i += 128) {
-        const double f = (double)(i < FO_NG / 2 ? i : i - FO_NG) * (0.5 * g.fs_dec / FO_NG);
-        // |H_butter|^2 at f (rate fs_dec)
-        double s1, c1;
-        double nr = 0, ni = 0, dr = 0, di = 0;
-        for (int k = 0; k < 5; ++k) {
-            sincospi(-2.0 * f * k / g.fs_dec, &s1, &c1);
-            nr += g.b[k] * c1; ni += g.b[k] * s1; dr += g.a[k] * c1; di += g.a[k] * s1;
-        }
-        const double B2 = (nr * nr + ni * ni) / (dr * dr + di * di);
-        // |H_cheby|^2 at f + fo (rate fs)
-        double C2 = 1.0;
-        for (int sct = 0; sct < 4; ++sct) {
-            double n_r = 0, n_i = 0, d_r = 0, d_i = 0;
-            for (int k = 0; k < 3; ++k) {
-                sincospi(-2.0 * (f + fo) * k / g.fs, &s1, &c1);
-                n_r += g.sos[sct][k] * c1; n_i += g.sos[sct][k] * s1;
-                d_r += g.sos[sct][3 + k] * c1; d_i += g.sos[sct][3 + k] * s1;
-            }
-            C2 *= (n_r * n_r + n_i * n_i) / (d_r * d_r + d_i * d_i);
-        }
-        double hbv = c_hb[TB_HB_H], pv = c_proto[TB_PROTO_H];
-        for (int k = 1; k <= TB_HB_H; ++k) hbv += 2.0 * (double)c_hb[TB_HB_H + k] * cospi(2.0 * f * k / g.fs_dec);
-        for (int k = 1; k <= TB_PROTO_H; ++k) pv += 2.0 * (double)c_proto[TB_PROTO_H + k] * cospi(2.0 * (f + fo) * k / g.fs);
-        T[i] = B2 * C2 / (hbv * pv);
-        sincospi(2.0 * (double)i / FO_NG, &s1, &c1);
-        tw[i] = make_double2(c1, s1);
-    }
-    __syncthreads();
-    float2* out = g.ctaps + (int64_t)car * 128;
-    if (tid == 0) out[0] = make_float2(0.f, 0.f);
-    if (tid >= 1) {
-        const int lag = 64 - tid;                        // 63 .. -63
-        double ar = 0.0, ai = 0.0;
-        for (int i = 0; i < FO_NG; ++i) {
-            const int idx = (((i * lag) % FO_NG) + FO_NG) % FO_NG;
-            ar += T[i] * tw[idx].x;
-            ai += T[i] * tw[idx].y;
-        }
-        out[tid] = make_float2((float)(ar / FO_NG), (float)(ai / FO_NG));
     }
 }
 

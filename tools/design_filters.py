@@ -13,6 +13,13 @@ response can be realised as a multirate FIR cascade (all real, symmetric taps):
     interp : 120 kS/s -> 240 kS/s, even outputs are the fir120 samples themselves, odd outputs a
              half-sample fractional-delay FIR
 
+freq_offset != 0 (processor.py:259-261 mixes BETWEEN the two filters): the w samples are rotated by the
+NCO, so proto and the Chebyshev response act at f + f_off while hb, B2 and fir120 act at f. The chain
+above then misses the factor  R(f) = [C2(f+f_off) / P(f+f_off)] / [C2(f) / P(f)]  -- smooth and within
+about 1 % of one where B2 is not negligible -- which an 11-tap complex FIR at 120 kS/s supplies
+(least squares weighted by the response the signal still meets). Its taps are smooth in f_off and are
+stored as Chebyshev series on |f_off| <= 12.5 kHz.
+
 Coefficients of the two IIRs come from SciPy (the reference's own dependency) at design time
 only; the result is written to tetraear_b200/csrc/taps_generated.h and committed.
 Run:  python tools/design_filters.py [--write]
@@ -33,6 +40,9 @@ HB_K = 6          # hb: true half-band, centre 0.5 + HB_K odd taps each side (le
 HB_H = 2 * HB_K - 1
 FIR_H = 63        # fir120 taps -63..63 at 120k (127; the kernel pads to 128 = 4 quarters of 32)
 INT_K = 8         # interp: 2*INT_K taps at half-sample offsets
+REQ_K = 5         # freq_offset equaliser: complex taps -5..5 at 120k
+REQ_DEG = 12      # ... each a Chebyshev series in f_off / REQ_FOMAX
+REQ_FOMAX = 12500.0
 
 
 def C2(f):
@@ -124,6 +134,31 @@ def design():
     sol, *_ = np.linalg.lstsq(A * W[:, None], W, rcond=None)
     out["interp_half"] = sol                     # taps at +-(k+1/2)
     out["interp_err"] = np.abs((A @ sol - 1) * B2(f)).max()
+    # --- req: equaliser taps of the freq_offset path as Chebyshev series in f_off ---
+    fq = np.linspace(-60e3, 60e3, 1024, endpoint=False)
+    kk = np.arange(-REQ_K, REQ_K + 1)
+    E = np.exp(-2j * np.pi * np.outer(fq, kk) / FS2)
+    Pq = lambda ff: cosmat(ff, PROTO_H, FS) @ p
+    Gq = (np.exp(-2j * np.pi * np.outer(fq, np.arange(-FIR_H, FIR_H + 1)) / FS2) @ g).real
+    HBq = cosmat(fq, HB_H, FS1) @ h
+
+    def req_taps(fo):
+        R = (C2(fq + fo) / Pq(fq + fo)) / (C2(fq) / Pq(fq))
+        W = np.abs(Gq * HBq * Pq(fq + fo))
+        sol, *_ = np.linalg.lstsq(E * W[:, None], R * W, rcond=None)
+        return sol
+
+    def req_err(fo, taps):
+        return np.abs((E @ taps) * Gq * HBq * Pq(fq + fo) - B2(fq) * C2(fq + fo)).max()
+
+    nn = 48
+    nodes = REQ_FOMAX * np.cos(np.pi * (np.arange(nn) + 0.5) / nn)
+    T = np.array([req_taps(fo) for fo in nodes])
+    V = np.polynomial.chebyshev.chebvander(nodes / REQ_FOMAX, REQ_DEG)
+    coef, *_ = np.linalg.lstsq(V, T, rcond=None)                    # [DEG+1][2K+1] complex
+    out["req_cheb"] = coef
+    test = np.linspace(-REQ_FOMAX, REQ_FOMAX, 51)
+    out["req_err"] = max(req_err(fo, np.polynomial.chebyshev.chebvander(np.array([fo / REQ_FOMAX]), REQ_DEG)[0] @ coef) for fo in test)
     return out
 
 
@@ -166,12 +201,18 @@ def write_header(taps, path):
         fh.write(arr("TB_HB_TAPS", taps["hb"]))
         fh.write(arr("TB_FIR120_TAPS", taps["fir120"]))
         fh.write(arr("TB_INTERP_TAPS", taps["interp_half"]))
+        # freq_offset equaliser: tap k (0..2K <-> -K..K) = sum_j T_j(f_off / FOMAX) (COEF[j][k][0] + i COEF[j][k][1])
+        c = taps["req_cheb"]
+        fh.write("#define TB_REQ_K %d\n#define TB_REQ_DEG %d\n#define TB_REQ_FOMAX %.1f\n" % (REQ_K, REQ_DEG, REQ_FOMAX))
+        flat = np.stack([c.real, c.imag], axis=-1).reshape(-1)
+        body = ",\n    ".join(", ".join("%.17e" % v for v in flat[i:i + 4]) for i in range(0, len(flat), 4))
+        fh.write("static const double TB_REQ_CHEB[%d] = {\n    %s\n};\n" % (len(flat), body))
 
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser(); ap.add_argument("--write", action="store_true"); a = ap.parse_args()
     t = design()
-    for k in ("proto_leak", "hb_leak", "fir120_trunc", "interp_err"):
+    for k in ("proto_leak", "hb_leak", "fir120_trunc", "interp_err", "req_err"):
         print(k, "%.3e" % t[k])
     print("lens", len(t["proto"]), len(t["hb"]), len(t["fir120"]), 2 * len(t["interp_half"]))
     here = os.path.dirname(os.path.abspath(__file__))
