@@ -79,16 +79,16 @@ constexpr int K1_W = K1_TILE / 10;        // 640 w (240 kS/s) samples per iterat
 constexpr int K1_U = K1_TILE / 20;        // 320 u/v (120 kS/s) samples per iteration
 constexpr int K1_NBUF = 3;
 constexpr int K1_WRING = 2048, K1_URING = 2048, K1_VRING = 1024;
-constexpr int K1_RRING = 512;             // MODE 1: ring of half-band outputs waiting for the equaliser
+constexpr int K1_RRING = 1024;            // MODE 1: ring of half-band outputs waiting for the equaliser
 constexpr int K1_THREADS = 384;           // warps 0-3: A, 4-7: C, 8-9: B, 10-11: D
 constexpr int K1_DLANES = 64;
 constexpr int K1_CQ = 4;                  // tap quarters = iterations a C group stays in registers
 // local (stream-origin relative) index ranges produced in iteration i
 constexpr int K1_A0 = -2;                 // w: [640 i + A0, +640)
 constexpr int K1_B0 = -326;               // u: [320 i + B0, +320) (MODE 1: the half-band output before the equaliser)
-constexpr int K1_R0 = K1_B0 - 8;          // MODE 1: equalised u [320 i + R0, +320), from the same iteration's half-band output
-constexpr int K1_C0 = -622;               // v group g: [320 g + C0, +320), finished in iteration g + 3
-constexpr int K1_D0 = -1910;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
+constexpr int K1_R0 = K1_B0 - 326;        // MODE 1: equalised u [320 i + R0, +320), from earlier iterations' half-band output
+constexpr int K1_C0 = -942;               // v group g: [320 g + C0, +320), finished in iteration g + 3
+constexpr int K1_D0 = -2230;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
 constexpr int K1_PREROLL = 320;           // pre-roll and post-roll of a slot in w samples (> the cascade's reach of 157)
 constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
 constexpr int K1_NPH = 13;
@@ -100,8 +100,8 @@ static_assert(TB_PROTO_H == 20 && TB_HB_H == 11 && TB_FIR_H == 63 && TB_INT_K ==
 static_assert(2 * (K1_B0 + K1_U - 1) + TB_HB_H <= K1_A0 - 1, "B reads w of a later iteration");
 // quarter q of group g runs in iteration g + q and reads u up to 320 g + C0 + 319 - 64 + 32 q + 31 (+1 for the 129th tap)
 static_assert((K1_C0 + K1_U - 1) - 64 + 31 <= K1_R0 - 1, "C quarter 0 reads u of a later iteration");
-static_assert(K1_R0 + K1_U - 1 + TB_REQ_K <= K1_B0 + K1_U - 1, "the equaliser reads half-band output of a later iteration");
-static_assert(K1_U + 8 + 2 * TB_REQ_K <= K1_RRING, "equaliser ring too small");
+static_assert(K1_R0 + K1_U - 1 + TB_REQ_K <= K1_B0 - 1, "the equaliser reads half-band output of this or a later iteration");
+static_assert((K1_B0 + K1_U) - (K1_R0 - TB_REQ_K) <= K1_RRING, "equaliser ring too small");
 static_assert((K1_C0 + K1_U - 1) - 64 + 32 * 3 + 31 <= 2 * K1_U + K1_B0 + K1_U - 1, "C quarter 3 reads u of a later iteration");
 // D in iteration i reads v up to 320 i + D0 + 319 + 8; finished groups then: g <= i - 4
 static_assert((K1_D0 + K1_U - 1) + TB_INT_K <= -K1_CQ * K1_U + K1_C0 + K1_U - 1, "D reads v of an unfinished group");
@@ -452,10 +452,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 }
             }
             if (MODE == 1) {
-                // half-band output -> ring, then the carrier's equaliser over this and earlier iterations' entries
+                // half-band output -> ring; the carrier's equaliser runs over earlier iterations' entries (no barrier in between)
 #pragma unroll
                 for (int r = 0; r < 5; ++r) sf.ur[(nu0 + r) & (K1_RRING - 1)] = acc[r];
-                asm volatile("bar.sync 1, 64;" ::: "memory");
                 // taps of the slot the kept outputs of this range belong to (kept outputs lie PREROLL inside their slot)
                 const float2* tp = sf.rtap[min(max(qr, 0), n_my - 1) & 1];
                 const int ne0 = K1_U * i + K1_R0 + 5 * lb;
