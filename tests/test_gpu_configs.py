@@ -93,6 +93,33 @@ def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
         assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
 
 
+@pytest.mark.parametrize("n", [1 << 17, (1 << 17) + 1235, 16384 + 8])
+def test_u8_ingest_fused_path(gpu_processor, n):
+    """freq_offset 0 at 2.4 MS/s: the fused kernel reads the bytes itself (bulk copies when the rows are 16-byte
+    aligned, plain loads otherwise) and only the block-end windows are expanded for the exact edge kernels."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n_car = 3
+    raw = np.empty((n_car, n, 2), dtype=np.uint8)
+    for c in range(n_car):
+        x = synth.carrier_iq(n, 500 + c, snr_db=20.0 + 5 * c, alphabet="centred" if c & 1 else "pi4")
+        z = x / np.abs(x).max() * 0.95
+        raw[c, :, 0] = np.clip(np.round((z.real + 1.0) * 127.5), 0, 255)
+        raw[c, :, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
+    before = sp.launch_count()
+    res = sp.process_batch_u8(raw, None, want_symbols=True, want_sync=True)
+    assert sp.launch_count() - before == 4                     # windows, fused kernel, edges, finalize: no expansion pass
+    for c in range(n_car):
+        x128 = (raw[c, :, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (raw[c, :, 1].astype(np.float64) / 127.5 - 1.0)
+        r = ref_dsp.process(x128, 0.0, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"]
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"])
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, err
+        assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
+
+
 def test_scanner_analysis_matches_reference_golden(gpu_processor):
     """TetraSignalDetector's per-sample analysis on the device vs the reference's own numbers."""
     import os, sys

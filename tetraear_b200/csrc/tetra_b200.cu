@@ -127,6 +127,7 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
     ctx->tables_uploaded = true;
     return 0;
 }
@@ -205,7 +206,7 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
     CK(ctx->jobs.ensure(nj * sizeof(int2)));
     CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
     EdgeArgs g;
-    g.x = ea.x32; g.pitch = ea.pitch; g.n = ea.n; g.q = ea.q; g.L = ea.L; g.edge = ea.edge; g.cf = ea.cf;
+    g.x = ea.x32; g.pitch = ea.pitch; g.right_shift = ea.x_right_shift; g.n = ea.n; g.q = ea.q; g.L = ea.L; g.edge = ea.edge; g.cf = ea.cf;
     g.y = ea.y32; g.y_pitch = ea.y_pitch; g.y_sps = ea.y_sps; g.y_rows = ea.y_rows; g.jobs = (const int2*)ctx->jobs.p; g.n_jobs = (int32_t)nj;
     g.scr1 = (double2*)ctx->scr1.p; g.scrz = (double2*)ctx->scrz.p; g.scr2 = (double2*)ctx->scr2.p;
     g.w1 = w1; g.wz = wz; g.fo = ea.fo; g.fs_dec = ea.fs_dec;
@@ -297,7 +298,7 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
         ctx->mats_n = ea.n; ctx->mats_q = ea.q; ctx->mats_L = ea.L;
     }
     EdgeWarpArgs g;
-    g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
+    g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.right_shift = ea.x_right_shift; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
     g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.y_sps = ea.y_sps; g.e.y_rows = ea.y_rows; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
     g.e.scr1 = (double2*)ctx->scr1.p; g.e.scrz = (double2*)ctx->scrz.p; g.e.scr2 = (double2*)ctx->scr2.p;
     g.e.w1 = w1; g.e.wz = wz; g.e.fo = ea.fo; g.e.fs_dec = ea.fs_dec;
@@ -434,7 +435,7 @@ int tetra_process_batch(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
 static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                         uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
                         uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async,
-                        const double* chan_hz);
+                        const double* chan_hz, const uint8_t* u8 = nullptr, int64_t u8_pitch = 0);
 
 int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                              uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
@@ -446,18 +447,20 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t
 static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                         uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
                         uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async,
-                        const double* chan_hz) {
+                        const double* chan_hz, const uint8_t* u8, int64_t u8_pitch) {
+    // u8 != null: the input is [C][u8_pitch][2] unsigned bytes on the device (RTL-SDR format) and `iq` is unused
     if (!ctx) return TETRA_E_INVALID;
+    static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;   // debug switch, see DESIGN.md §5
     if ((sync_pos != nullptr) != (n_sync != nullptr) || (sync_pos && max_pos <= 0))
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_sync: sync_pos, n_sync and max_positions go together");
-    if (C < 0 || N < 0 || (C > 0 && N > 0 && (!iq || pitch < N)) || !n_dibits || (cap > 0 && !dibits) || cap < 0)
+    if (C < 0 || N < 0 || (C > 0 && N > 0 && (u8 ? u8_pitch < N : (!iq || pitch < N))) || !n_dibits || (cap > 0 && !dibits) || cap < 0)
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: bad arguments");
     if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: at most 65535 carriers per call");
     if (N > ((int64_t)1 << 30)) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch: block too long");
     CK(cudaSetDevice(ctx->device));
     if (C == 0) return TETRA_OK;
     cudaStream_t st = ctx->stream;
-    const bool d_in = is_device_ptr(iq), d_dib = is_device_ptr(dibits), d_nd = is_device_ptr(n_dibits);
+    const bool d_in = u8 ? true : is_device_ptr(iq), d_dib = is_device_ptr(dibits), d_nd = is_device_ptr(n_dibits);
     const bool d_sym = is_device_ptr(symbols), d_ph = is_device_ptr(best_phase), d_match = is_device_ptr(ts_match);
     const bool d_spos = is_device_ptr(sync_pos), d_nsync = is_device_ptr(n_sync);
     if (async && !(d_in && (d_dib || !dibits) && d_nd && (d_sym || !symbols) && (d_ph || !best_phase) && (d_match || !ts_match) &&
@@ -480,9 +483,11 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     if (rc) return rc;
 
     // ---- input on device ----
-    const float2* d_x;
+    const float2* d_x = nullptr;
     int64_t x_pitch = pitch;
-    if (chan_hz) {
+    if (u8) {
+        // decided below: the fused kernel reads the bytes itself, every other path gets them expanded first
+    } else if (chan_hz) {
         if (d_in) d_x = (const float2*)iq;
         else {
             CK(ctx->tmp_a.ensure((size_t)N * sizeof(float2)));
@@ -511,6 +516,23 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     // The fused path covers freq_offset = 0 (MODE 0) and, with per-carrier complex taps, |freq_offset| <= 12.5 kHz
     // (MODE 1: the GUI's AFC range, ui/modern.py:1949-1967); anything else runs the exact recursion over the block.
     const bool use_fast = fast_ok && (!any_fo || fo_in_range);
+    const bool u8_fused = u8 && use_fast && !any_fo && edge_mode != 2;
+    if (u8 && !u8_fused) {
+        CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
+        if (u8_pitch == N) {
+            k_u8_to_c64<<<(unsigned)std::min<int64_t>(((int64_t)C * N / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(u8, (int64_t)C * N, (float2*)ctx->wide.p);
+            ctx->launches++;
+        } else {
+            for (int c = 0; c < C; ++c) {
+                k_u8_to_c64<<<(unsigned)std::min<int64_t>((N / 8 + 255) / 256 + 1, 148 * 4), 256, 0, st>>>(u8 + (size_t)c * u8_pitch * 2, N,
+                                                                                                      (float2*)ctx->wide.p + (size_t)c * N);
+                ctx->launches++;
+            }
+        }
+        CK(cudaGetLastError());
+        d_x = (const float2*)ctx->wide.p;
+        x_pitch = N;
+    }
     if (chan_hz && (!use_fast || any_fo)) return fail(ctx, TETRA_E_UNSUPPORTED, "wideband channels need the fused path (fs 2.4 MS/s, >= 16384 samples)");
     for (int c = 0; c < C; ++c) {
         if (use_fast) edge_jobs.push_back(make_int2(c, EX_LEFT));
@@ -573,6 +595,17 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(cudaGetLastError());
         ea.x32 = (const float2*)ctx->wide.p; ea.pitch = N;
     }
+    if (u8_fused) {
+        // the exact edge kernels read complex64: expand the two end windows of every block, compactly
+        const EdgeRange rl = edge_range(EX_LEFT, N, (int)pl.L, pl.q, K1_EDGE), rr = edge_range(EX_RIGHT, N, (int)pl.L, pl.q, K1_EDGE);
+        const int64_t wl = std::min<int64_t>(N, ((rl.e_hi - EX_PAD1) + 7) & ~(int64_t)7);
+        const int64_t wr = std::min<int64_t>(N, (N - std::max<int64_t>(0, rr.e_lo - EX_PAD1) + 7) & ~(int64_t)7);
+        CK(ctx->wide.ensure((size_t)C * (wl + wr) * sizeof(float2)));
+        k_u8_edge_windows<<<dim3((unsigned)((wl + wr + 255) / 256), C), 256, 0, st>>>(u8, u8_pitch, N, (int32_t)wl, (int32_t)wr, (float2*)ctx->wide.p);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        ea.x32 = (const float2*)ctx->wide.p; ea.pitch = wl + wr; ea.x_right_shift = wl - (N - wr);
+    }
     ea.y32 = (float2*)ctx->y.p; ea.y_pitch = y_pitch; ea.y_sps = y_sps; ea.y_rows = y_rows; ea.edge = K1_EDGE;
 
     FinArgs fa;
@@ -608,6 +641,11 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         ka.x = d_x; ka.pitch = x_pitch; ka.n = N; ka.L = (int32_t)pl.L; ka.seg_len = seg_len; ka.n_seg = n_seg; ka.n_items = n_items; ka.t_item = std::max(seg_len / K1_W + 1, K1_MIN_T_ITEM);
         ka.y = (float2*)ctx->y.p; ka.y_pitch = y_pitch; ka.y_rows = y_rows; ka.partial = (double*)ctx->partial.p;
         ka.aligned = ((reinterpret_cast<uintptr_t>(d_x) & 15) == 0) && ((x_pitch & 1) == 0);
+        ka.x8 = nullptr;
+        if (u8_fused) {
+            ka.x8 = u8; ka.pitch = u8_pitch;
+            ka.aligned = ((reinterpret_cast<uintptr_t>(u8) & 15) == 0) && ((u8_pitch & 7) == 0);
+        }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
         // edge windows run beside the bulk kernel on the side stream
         if (ctx->timing) {
@@ -631,14 +669,14 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ctx->ev_used++;
             CK(cudaEventRecord(t0, st));
         }
-        if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+        if (u8_fused) k1_channelize_demod<3><<<k1_grid, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
+        else if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
         ctx->launches++;
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));
         // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
-        static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;
         if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
         // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
         if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
@@ -739,20 +777,9 @@ int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t C, int6
         d_in = (const uint8_t*)ctx->u8.p;
         d_pitch = N;
     }
-    CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
-    if (d_pitch == N) {
-        k_u8_to_c64<<<(unsigned)std::min<int64_t>(((int64_t)C * N / 8 + 255) / 256 + 1, 148 * 16), 256, 0, st>>>(d_in, (int64_t)C * N, (float2*)ctx->wide.p);
-        ctx->launches++;
-    } else {
-        for (int c = 0; c < C; ++c) {
-            k_u8_to_c64<<<(unsigned)std::min<int64_t>((N / 8 + 255) / 256 + 1, 148 * 4), 256, 0, st>>>(d_in + (size_t)c * d_pitch * 2, N,
-                                                                                                  (float2*)ctx->wide.p + (size_t)c * N);
-            ctx->launches++;
-        }
-    }
-    CK(cudaGetLastError());
-    return tetra_process_batch_sync(ctx, (const float*)ctx->wide.p, C, N, N, fo_hz, dibits, cap, n_dibits, symbols, best_phase,
-                                    ts_match, sync_pos, max_pos, n_sync, 0);
+    // the fused path reads the bytes as they are (2 bytes per sample); other sample rates / offsets expand them first
+    return process_impl(ctx, nullptr, C, N, N, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, sync_pos, max_pos, n_sync, 0,
+                        nullptr, d_in, d_pitch);
 }
 
 int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const double* channel_hz, int32_t C,

@@ -23,6 +23,8 @@ constexpr int EXT_BB = 8;                 // backward steps per prefetched block
 struct EdgeArgs {
     const float2* x;         // [C][pitch] complex64
     int64_t pitch, n;
+    int64_t right_shift;     // added to a RIGHT job's row pointer: rows that hold only the two end windows of a block
+                             // (uint8 ingest) keep sample i >= n - WR at column i + right_shift; 0 for whole blocks
     int32_t q, L, edge;
     ExactCoef cf;
     float2* y;               // [C][y_pitch], layout y_index(n, y_sps, y_rows)
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(EXT_THREADS) k_exact_edges(const EdgeArgs a) {
     const int j = blockIdx.x * EXT_THREADS + threadIdx.x;
     if (j >= a.n_jobs) return;
     const int car = a.jobs[j].x, mode = a.jobs[j].y;
-    const float2* __restrict__ xc = a.x + (int64_t)car * a.pitch;
+    const float2* __restrict__ xc = a.x + (int64_t)car * a.pitch + (mode == EX_RIGHT ? a.right_shift : 0);
     const int L = a.L, E = a.edge, q = a.q;
     const int64_t n = a.n;
     int m_lo = 0, m_hi = L, o_lo = 0, o_hi = L;
@@ -422,7 +424,7 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
     const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (j >= a.n_jobs) return;                           // whole warps only
     const int car = a.jobs[j].x, mode = a.jobs[j].y;
-    const float2* __restrict__ xc = a.x + (int64_t)car * a.pitch;
+    const float2* __restrict__ xc = a.x + (int64_t)car * a.pitch + (mode == EX_RIGHT ? a.right_shift : 0);
     const int L = a.L, q = a.q;
     const int64_t n = a.n;
     const EdgeRange rg = edge_range(mode, n, L, q, a.edge);
@@ -437,7 +439,9 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
 
     // ---- stage 1 forward: sample s <-> e = e_lo + s <-> input index e - PAD1 (reflected in the pads) ----
     {
-        const double2 edge_lo = xat(0), edge_hi = xat(n - 1);
+        // (a LEFT window never reaches past the block's last sample, a RIGHT one never before its first)
+        const double2 zero2 = make_double2(0.0, 0.0);
+        const double2 edge_lo = mode == EX_LEFT ? xat(0) : zero2, edge_hi = mode == EX_RIGHT ? xat(n - 1) : zero2;
         auto refl = [&](int s) {
             const int64_t i = e_lo + s - EX_PAD1;
             return i < 0 ? -i : (i >= n ? 2 * (n - 1) - i : i);

@@ -40,6 +40,7 @@ struct ExactArgs {
     const float2* x32;       // complex64 input [C][pitch] (batch path) ...
     const double2* x64;      // ... or complex128 input (helpers); exactly one is non-null
     int64_t pitch;
+    int64_t x_right_shift;   // see EdgeArgs::right_shift (edge kernels only)
     int64_t n;               // samples per carrier
     int32_t q;               // decimation factor (1: stage 1 absent)
     int32_t L;               // length after stage 1

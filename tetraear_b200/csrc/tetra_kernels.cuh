@@ -130,7 +130,17 @@ struct K1SmemFo {
     float2 ptap[2][48];     // MODE 2: this channel's modulated proto taps
 };
 
-static_assert(sizeof(K1SmemFo) <= 227 * 1024, "K1 shared memory exceeds the 227 KB a CTA may use");
+// uint8 ingest (MODE 3): in[0] / in[1] hold the converted tile being filtered / being prepared, in[2] is the ring of raw
+// byte tiles (2 bytes per sample) the bulk copies fill three tiles ahead
+constexpr int K1_RAWBUF = 4;
+constexpr int K1_RAW_BYTES = 2 * K1_TILE;
+struct K1SmemU8 {
+    K1Smem base;
+    uint64_t rawfull[K1_RAWBUF];
+};
+static_assert(K1_RAWBUF * K1_RAW_BYTES <= (int)sizeof(float2) * (K1_HDR + K1_TILE), "raw byte ring does not fit the third tile buffer");
+static_assert((sizeof(float2) * (K1_HDR + K1_TILE)) % 16 == 0 && K1_RAW_BYTES % 16 == 0, "bulk copies need 16-byte aligned slots");
+static_assert(sizeof(K1SmemFo) <= 227 * 1024 && sizeof(K1SmemU8) <= 227 * 1024, "K1 shared memory exceeds the 227 KB a CTA may use");
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
 __constant__ float c_hb[2 * TB_HB_H + 1];
@@ -140,6 +150,7 @@ __constant__ double c_req[(TB_REQ_DEG + 1) * (2 * TB_REQ_K + 1) * 2];   // Cheby
 
 struct K1Args {
     const float2* x;        // [C][pitch]
+    const uint8_t* x8;      // MODE 3: [C][pitch][2] interleaved unsigned bytes instead of x
     int64_t pitch;
     int64_t n;              // samples per carrier
     int32_t L;              // ceil(n/10)
@@ -151,7 +162,7 @@ struct K1Args {
     int64_t y_pitch;
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
-    int32_t aligned;        // 1: x base/pitch allow 16-byte bulk copies
+    int32_t aligned;        // 1: x (x8) base/pitch allow 16-byte bulk copies
     // MODE >= 1 only
     const double* fo;       // [C] Hz: freq_offset (MODE 1) / channel offset (MODE 2)
     double fs_dec;          // 240000
@@ -258,6 +269,76 @@ __device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a,
     }
 }
 
+// MODE 3: raw byte tile i of this CTA's stream -> slot i % RAWBUF of the byte ring
+__device__ __forceinline__ void k1_issue_stream_tile_u8(K1SmemU8& s8, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
+    const uint8_t* xc = a.x8 + 2 * (int64_t)sl.car * a.pitch;
+    const int64_t gx0 = (int64_t)sl.O * 10 + (int64_t)t * K1_TILE;        // a multiple of 8 (segments are multiples of 640 outputs)
+    uint8_t* dst = reinterpret_cast<uint8_t*>(&s8.base.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES;
+    uint64_t* bar = &s8.rawfull[i % K1_RAWBUF];
+    const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
+    const int hi = (int)max((int64_t)lo, min((int64_t)K1_TILE, a.n - gx0));
+    if (a.aligned) {
+        const int cnt = (hi - lo) & ~7;                    // 16-byte units; the block's last 30 samples reach no kept output
+        if (lane == 0) {
+            if (cnt > 0) {
+                mbar_expect_tx(bar, cnt * 2);
+                tma_load_1d(dst + 2 * lo, xc + 2 * (gx0 + lo), cnt * 2, bar);
+            } else {
+                mbar_arrive(bar);
+            }
+        }
+    } else {
+        for (int tt = 2 * lo + lane; tt < 2 * hi; tt += 32) dst[tt] = __ldg(xc + 2 * gx0 + tt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar);
+    }
+}
+// MODE 3: raw slot -> float tile, (byte / 127.5) - 1 per component (pyrtlsdr packed_bytes_to_iq, signal/capture.py:143-158).
+// The byte is placed in the mantissa of 2^23 (one PRMT), so no integer-to-float conversion is issued; the result is
+// within one float32 ulp of the float64 expression. Words [k0, k0 + 64 STEPS) of the tile by 64 threads: two samples
+// (one 32-bit word -> one 16-byte store) per thread and step, all loads of a group issued before the first use.
+constexpr int K1_CV_B = 32, K1_CV_D = 18;     // steps taken by stage B's / stage D's 64 threads (B has more slack)
+static_assert(64 * (K1_CV_B + K1_CV_D) == K1_TILE / 2, "the conversion must cover the tile");
+// G loads in flight per group; the group loop stays rolled (the kernel's code must keep fitting the instruction cache)
+template <int STEPS, int G>
+__device__ __forceinline__ void k1_convert_tile_u8(K1SmemU8& s8, int i, int k0, int l64) {
+    static_assert(STEPS % G == 0, "whole groups");
+    mbar_wait(&s8.rawfull[i % K1_RAWBUF], (uint32_t)((i / K1_RAWBUF) & 1));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(&s8.base.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES) + k0 + l64;
+    float4* dst = reinterpret_cast<float4*>(&s8.base.in[i & 1][K1_HDR]) + k0 + l64;
+    // packed constants (-2^23, -2^23), (1/127.5, 1/127.5), (-1, -1)
+    unsigned long long p_off, p_sc, p_m1;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(p_off) : "f"(-8388608.f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(p_sc) : "f"(1.0f / 127.5f));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(p_m1) : "f"(-1.f));
+#pragma unroll 1
+    for (int g0 = 0; g0 < STEPS; g0 += G, src += 64 * G, dst += 64 * G) {
+        uint32_t w[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) w[g] = src[64 * g];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float4 v;
+            asm("{\n\t.reg .b32 a0, a1, a2, a3;\n\t.reg .b64 q0, q1;\n\t"
+                "prmt.b32 a0, %4, 0x4B000000, 0x7440;\n\t"
+                "prmt.b32 a1, %4, 0x4B000000, 0x7441;\n\t"
+                "prmt.b32 a2, %4, 0x4B000000, 0x7442;\n\t"
+                "prmt.b32 a3, %4, 0x4B000000, 0x7443;\n\t"
+                "mov.b64 q0, {a0, a1};\n\t"
+                "mov.b64 q1, {a2, a3};\n\t"
+                "add.rn.f32x2 q0, q0, %5;\n\t"
+                "add.rn.f32x2 q1, q1, %5;\n\t"
+                "fma.rn.f32x2 q0, q0, %6, %7;\n\t"
+                "fma.rn.f32x2 q1, q1, %6, %7;\n\t"
+                "mov.b64 {%0, %1}, q0;\n\t"
+                "mov.b64 {%2, %3}, q1;\n\t}"
+                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                : "r"(w[g]), "l"(p_off), "l"(p_sc), "l"(p_m1));
+            dst[64 * g] = v;
+        }
+    }
+}
+
 // modulated proto taps of a channel at offset f: q[d] = c_proto[d] exp(-j 2 pi f (d - 20) / fs). With them and the w rotation
 // exp(-j 2 pi f 10 m / fs) stage A computes proto(x[n] exp(-j 2 pi f n / fs)) without ever forming the shifted stream.
 __device__ __forceinline__ float2 k1_modulated_tap(int d, double f, double fs) {
@@ -291,6 +372,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     K1SmemFo& sf = *reinterpret_cast<K1SmemFo*>(smem_raw);
+    K1SmemU8& s8 = *reinterpret_cast<K1SmemU8*>(smem_raw);
+    constexpr int NB = MODE == 3 ? 2 : K1_NBUF;           // float tile buffers in rotation
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slots of this CTA
@@ -306,11 +389,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     for (int i = tid; i < K1_NBUF * (K1_HDR + K1_TILE); i += K1_THREADS) (&s.in[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
+        if (MODE == 3) for (int b = 0; b < K1_RAWBUF; ++b) mbar_init(&s8.rawfull[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
-    if (MODE >= 1) {
+    if (MODE == 1 || MODE == 2) {
         const K1Slot s0 = k1_slot(a, 0);
         if (MODE == 1 && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
         if (MODE == 1) for (int i = tid; i < K1_RRING; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
@@ -323,8 +407,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     }
     __syncthreads();
     if (warp == 0) {
-        k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
-        if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
+        if (MODE == 3) {
+            for (int j = 0; j < 3 && j < n_load; ++j) k1_issue_stream_tile_u8(s8, a, j, k1_slot(a, j / a.t_item), j % a.t_item, lane);
+        } else {
+            k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
+            if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
+        }
+    }
+    if (MODE == 3) {                                      // tile 0 is converted before the roles start
+        if (warp == 8 || warp == 9) k1_convert_tile_u8<K1_CV_B, 8>(s8, 0, 0, tid - 256);
+        if (warp >= 10) k1_convert_tile_u8<K1_CV_D, 6>(s8, 0, 64 * K1_CV_B, tid - 320);
+        __syncthreads();
     }
 
     // Each role runs its own loop (own loop-carried registers); all of them meet once per iteration at
@@ -332,21 +425,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     if (warp < 4) {
         // ---------------- role A: proto, 5 outputs per lane ----------------
         // (slot, tile-in-slot) of the tile being filtered and of the tile being fetched (two ahead), kept incrementally
-        int q = 0, t = 0, q2 = 2 / a.t_item, t2 = 2 % a.t_item;
+        constexpr int AHEAD = MODE == 3 ? 3 : 2;                 // tiles the producer runs ahead of the filter
+        int q = 0, t = 0, q2 = AHEAD / a.t_item, t2 = AHEAD % a.t_item;
         K1Slot sl2 = k1_slot(a, min(q2, n_my - 1));
         int64_t slot_gx = (int64_t)k1_slot(a, 0).O * 10;      // input index of the current slot's first sample
         for (int i = 0; i < n_iter; ++i) {
             if (i < n_load) {
                 // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
-                if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
+                if (MODE == 3) {                               // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
+                    if (warp == 0 && i + 3 < n_load) k1_issue_stream_tile_u8(s8, a, i + 3, sl2, t2, lane);
+                } else if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
                 if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
                 const int L5 = tid;                            // 0..127
                 const int64_t gx0 = slot_gx + (int64_t)t * K1_TILE;
                 const int q_now = q;                           // slot of the tile being filtered
                 if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
-                mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
+                if (MODE != 3) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
                 if (gx0 < a.n && gx0 + K1_TILE > 0) {          // tiles entirely outside the block carry nothing
-                    const float2* buf = &s.in[i % K1_NBUF][0];
+                    const float2* buf = &s.in[i % NB][0];
                     const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
                     float2 acc[5];
 #pragma unroll
@@ -375,7 +471,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         }
                     }
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
-                    if (MODE >= 1) {                        // MODE 1: frequency_shift at the decimated rate (processor.py:259-261)
+                    if (MODE == 1 || MODE == 2) {           // frequency_shift at the decimated rate (processor.py:259-261)
 #pragma unroll
                         for (int g = 0; g < 5; ++g) {
                             const float2 p = sf.ph[i & 1][5 * L5 + g];
@@ -385,7 +481,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                     for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
                     // tail of this tile -> header of the next buffer
-                    if (L5 < K1_HDR) s.in[(i + 1) % K1_NBUF][L5] = buf[K1_TILE + L5];
+                    if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = buf[K1_TILE + L5];
                 }
             }
             k1_bar_sync();
@@ -433,7 +529,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         };
         // MODE 1: slot of stream coordinate 640 i + 2 R0 + PREROLL (the kept outputs of the equalised range), kept incrementally
         int qr = k1_floordiv(2 * K1_R0 + K1_PREROLL, S), rr = 2 * K1_R0 + K1_PREROLL - qr * S;
-        if (MODE >= 1 && qn < n_my)
+        if ((MODE == 1 || MODE == 2) && qn < n_my)
             open_slot(sn, tn);
         for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
@@ -483,7 +579,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                 for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
             }
-            if (MODE >= 1 && i + 1 < n_load) {
+            if (MODE == 3 && i + 1 < n_load) k1_convert_tile_u8<K1_CV_B, 8>(s8, i + 1, 0, lb);   // its share of the tile stage A filters next
+            if ((MODE == 1 || MODE == 2) && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
                 k1_phasors10(pbase, pw, &sf.ph[(i + 1) & 1][10 * lb]);
@@ -590,6 +687,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
             r_it += K1_W;
             if (r_it >= S) { r_it -= S; ++q_it; }
+            if (MODE == 3 && i + 1 < n_load) k1_convert_tile_u8<K1_CV_D, 6>(s8, i + 1, 64 * K1_CV_B, ld);   // the rest of that tile
             k1_bar_sync();
         }
         if (q_cur >= 0 && q_cur < n_my) flush(n_iter);

@@ -375,6 +375,19 @@ __global__ void __launch_bounds__(256) k_u8_to_c64(const uint8_t* __restrict__ i
         out[i] = make_float2(cv(in[2 * i]), cv(in[2 * i + 1]));
 }
 
+// uint8 ingest on the fused path: only the two block-end windows the exact edge kernels read are expanded to complex64
+// (the fused kernel converts its own tiles in shared memory). out[c] = [ x[0 .. wl) | x[n - wr .. n) ], same arithmetic.
+__global__ void __launch_bounds__(256) k_u8_edge_windows(const uint8_t* __restrict__ in, int64_t pitch, int64_t n, int32_t wl, int32_t wr,
+                                                         float2* __restrict__ out) {
+    const uint8_t* row = in + 2 * (int64_t)blockIdx.y * pitch;
+    float2* o = out + (int64_t)blockIdx.y * (wl + wr);
+    auto cv = [](uint32_t b) { return (float)((double)b / 127.5 - 1.0); };
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < wl + wr; i += gridDim.x * blockDim.x) {
+        const int64_t src = i < wl ? i : n - wr + (i - wl);
+        o[i] = make_float2(cv(row[2 * src]), cv(row[2 * src + 1]));
+    }
+}
+
 // Wideband channel selection (BASELINE config 3; the scanner's retune sweep, signal/scanner.py:383-445, done in
 // software): out[c][n] = x[n] * exp(-1j * 2 pi f_c * (n / fs)), i.e. frequency_shift (processor.py:97-100) of one
 // capture to C channel centres, with the reference's float64 phase and a complex64 result.
