@@ -115,7 +115,9 @@ int tetra_analyze_signal(tetra_ctx* ctx, const float* iq, int32_t n_captures, in
  * tetra_process_batch_sync for RTL-SDR native samples: iq_u8 [C][pitch][2] interleaved unsigned 8-bit I, Q
  * (host or device), converted on the device exactly like pyrtlsdr's packed_bytes_to_iq does before the
  * reference sees them (RTLCapture.read_samples, signal/capture.py:143-158): (byte / 127.5) - 1.
- * A quarter of the host-to-device bytes of the complex64 entry point. Synchronous.
+ * A quarter of the host-to-device bytes of the complex64 entry point. At 2.4 MS/s with no freq_offset the fused
+ * kernel reads the bytes itself (2 bytes per sample of HBM traffic; rows that start on 16-byte boundaries, i.e.
+ * pitch % 8 == 0, go through bulk copies); otherwise they are expanded to complex64 first. Synchronous.
  */
 int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t n_carriers, int64_t n_samples,
                            int64_t pitch, const double* freq_offset_hz,
