@@ -414,6 +414,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
         }
     }
+    __syncthreads();                                      // rows that are not 16-byte aligned are filled by plain stores
     if (MODE == 3) {                                      // tile 0 is converted before the roles start
         if (warp == 8 || warp == 9) k1_convert_tile_u8<K1_CV_B, 8>(s8, 0, 0, tid - 256);
         if (warp >= 10) k1_convert_tile_u8<K1_CV_D, 6>(s8, 0, 64 * K1_CV_B, tid - 320);
