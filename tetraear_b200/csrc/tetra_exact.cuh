@@ -18,8 +18,8 @@ constexpr int EX_PAD2 = 15;   // filtfilt: 3 * max(len(a), len(b)) = 3 * 5
 constexpr int EX_T1 = 256;    // stage 1 (pole radius 0.9821 per input sample)
 constexpr int EX_T2 = 160;    // same for stage 2 (pole radius 0.8837 -> 3e-9)
 constexpr int EX_U = 8;       // recursion steps per load group
-constexpr int K_EDGE = 160;   // outputs per block end owned by the exact path (= K1_EDGE)
-constexpr int K_EDGE_MAX_S2 = K_EDGE + 2 * EX_T2 + 2 * EX_PAD2;   // longest stage-2 window of an edge job
+constexpr int K_EDGE = 168;   // outputs per block end owned by the exact path (= K1_EDGE)
+constexpr int K_EDGE_MAX_S2 = K_EDGE + EX_T2 + 2 * EX_PAD2;   // bound on the stage-2 window of an edge job (E + T2 + PAD2)
 
 enum { EX_FULL = 0, EX_LEFT = 1, EX_RIGHT = 2 };
 

@@ -89,8 +89,8 @@ constexpr int K1_B0 = -326;               // u: [320 i + B0, +320) (MODE 1: the 
 constexpr int K1_R0 = K1_B0 - 326;        // MODE 1: equalised u [320 i + R0, +320), from earlier iterations' half-band output
 constexpr int K1_C0 = -942;               // v group g: [320 g + C0, +320), finished in iteration g + 3
 constexpr int K1_D0 = -2230;              // v pairs [320 i + D0, +320) -> y [640 i + 2 D0, +640)
-constexpr int K1_PREROLL = 320;           // pre-roll and post-roll of a slot in w samples (> the cascade's reach of 157)
-constexpr int K1_EDGE = 160;              // y samples at each block end owned by the exact kernel
+constexpr int K1_PREROLL = 320;           // pre-roll and post-roll of a slot in w samples (> the cascade's reach: 157, with the equaliser 167)
+constexpr int K1_EDGE = 168;              // y samples at each block end owned by the exact kernel (> the cascade's reach in every mode)
 constexpr int K1_NPH = 13;
 constexpr int K1_MIN_T_ITEM = 6;           // a slot outlasts stage C's lag behind stage A (two tap buffers suffice)
 constexpr double K1_FO_MAX_HZ = 12500.0;  // freq_offset range of the fused path (the proto's alias nulls cover +-60 kHz +- this)
@@ -109,7 +109,9 @@ static_assert((K1_A0 + K1_W) - (2 * K1_B0 - TB_HB_H) <= K1_WRING, "w ring too sm
 static_assert((3 * K1_U + K1_B0 + K1_U) - (K1_C0 - 64 + 32 * 3) <= K1_URING, "u ring too small");
 static_assert((-3 * K1_U + K1_C0 + K1_U) - (K1_D0 - TB_INT_K) <= K1_VRING, "v ring too small");
 static_assert((K1_C0 % 2) == 0 && (K1_D0 % 2) == 0 && (K1_PREROLL % 2) == 0, "16-byte aligned ring reads need even offsets");
-static_assert(TB_FIR_H + TB_REQ_K + 2 * TB_HB_H + 2 < K1_PREROLL, "pre-roll shorter than the cascade's reach");
+// reach of the cascade in 240 kS/s samples: interpolator, fir120 and equaliser count double (120 kS/s), + half-band + proto
+constexpr int K1_REACH = 2 * (TB_INT_K + TB_FIR_H + TB_REQ_K) + TB_HB_H + (TB_PROTO_H + 9) / 10;
+static_assert(K1_REACH < K1_EDGE && K1_REACH < K1_PREROLL, "kept outputs must not see samples outside their block / slot");
 static_assert((2 * K1_D0) % 2 == 0, "y pairs must start on even samples");
 
 struct K1Smem {
@@ -249,7 +251,7 @@ __device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a,
     float2* dst = &s.in[i % K1_NBUF][K1_HDR];
     uint64_t* bar = &s.full[i % K1_NBUF];
     // in-block part [lo, hi) of the tile. Samples outside the block never reach an output this kernel keeps (those are
-    // K1_EDGE away from the block ends, the cascade reaches 157), so the rest of the buffer may hold anything finite.
+    // K1_EDGE away from the block ends, the cascade reaches K1_REACH < K1_EDGE), so the rest of the buffer may hold anything finite.
     const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
     const int hi = (int)max((int64_t)lo, min((int64_t)K1_TILE, a.n - gx0));
     if (a.aligned) {
