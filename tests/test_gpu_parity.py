@@ -92,6 +92,28 @@ def test_batch_with_mixed_freq_offsets(gpu_processor):
             assert np.mean(res["dibits"][c, :nd] == r["dibits"]) > 0.999
 
 
+@pytest.mark.parametrize("fo", [0.0, 9000.0])
+def test_carriers_of_very_different_level_do_not_leak(gpu_processor, fo):
+    """The persistent kernel streams its carriers back to back through one set of buffers (CTA b takes carriers b,
+    b + 148, ...): a carrier 80-120 dB below the one before it must still come out as if it were alone (kept outputs
+    never see another carrier's tiles)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n, n_car, n_sm = 16384 + 640, 156, 148
+    base = [synth.carrier_iq(n, 400 + k, snr_db=25.0) for k in range(4)]
+    level = np.where(np.arange(n_car) < n_sm, 1.0e4, 1.0)
+    level[n_sm + 1::2] = 1.0e-2
+    xs = np.stack([(base[c % 4] * level[c]).astype(np.complex64) for c in range(n_car)])
+    res = sp.process_batch(xs, [fo] * n_car, want_symbols=True)
+    for c in list(range(4)) + list(range(n_sm, n_car)):
+        r = ref_dsp.process(xs[c].astype(np.complex128), fo, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], c
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), c
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, err)
+
+
 def test_freq_offset_outside_fused_range_uses_exact_path(gpu_processor):
     sp = gpu_processor
     sp.sample_rate = 2.4e6
