@@ -223,7 +223,7 @@ def run_ours(a):
     cap = sp.dibit_capacity(N_SAMPLES)
 
     x, base = make_inputs(torch, dev, n_local, first_carrier)
-    packed = shard.PackedStreams(total, cap, device=dev) if total % world == 0 else None
+    packed = shard.PackedStreams(total, cap, device=dev, packer=sp) if total % world == 0 else None
     if packed is not None:                                    # dibits + lengths in one buffer: ONE all-gather per step
         dib, nd, cap_row = packed.dibits, packed.n_dibits, packed.cap
     else:
@@ -249,7 +249,7 @@ def run_ours(a):
                                 sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream, freq_offsets=fos)
         if world > 1:
             if packed is not None:
-                packed.gather()                                       # one NCCL all-gather
+                packed.gather()                                       # 2-bit pack, one NCCL all-gather, unpack
             else:
                 shard.gather_dibits(dib, nd, total, all_dib, all_nd)
 

@@ -84,6 +84,17 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t n_carriers
                              uint8_t* dibits, int64_t cap, int32_t* n_dibits,
                              float* symbols, int32_t* best_phase, uint8_t* ts_match,
                              int32_t* sync_pos, int32_t max_positions, int32_t* n_sync, int32_t async);
+/*
+ * Transport packing for the exchange of dibit streams between GPUs (the north star's all-gather before the host-side
+ * TetraDecoder.decode, core/decoder.py:835): four dibits (values 0..3) per byte,
+ *   packed[k] = d[4k] | d[4k+1] << 2 | d[4k+2] << 4 | d[4k+3] << 6.
+ * Device buffers, asynchronous on the context's stream. pack: n dibits, n % 16 == 0, dibits 16-byte aligned.
+ * unpack: n_blocks blocks of packed_bytes (% 4 == 0) at a stride of in_stride bytes -> 4 * packed_bytes dibits per
+ * block at a stride of out_stride bytes (% 16 == 0): the layout an all-gather of [packed streams | lengths] leaves.
+ */
+int tetra_pack_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, uint8_t* packed);
+int tetra_unpack_dibits(tetra_ctx* ctx, const uint8_t* packed, int64_t n_blocks, int64_t packed_bytes, int64_t in_stride,
+                        uint8_t* dibits, int64_t out_stride);
 /* The same cascade for dibit streams that are already there ([C][cap] uint8 + lengths; host or device). */
 int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits,
                          int32_t n_carriers, int32_t* sync_pos, int32_t max_positions, int32_t* n_sync);

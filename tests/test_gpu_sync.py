@@ -129,3 +129,22 @@ def test_sync_positions_random_streams_property(gpu_processor):
     got = sp.sync_positions(d, nd)
     for c in range(n_car):
         assert got[c] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(d[c, :nd[c]])), c
+
+
+def test_transport_packing_kernels_match_host_form(gpu_processor):
+    """tetra_pack_dibits / tetra_unpack_dibits against the host-tensor form the gloo tests use (tetraear_b200/shard.py)."""
+    import torch
+    from tetraear_b200 import shard
+    sp = gpu_processor
+    rng = np.random.default_rng(11)
+    world, n_local, cap = 3, 5, 48
+    d = torch.from_numpy(rng.integers(0, 4, size=(world, n_local, cap), dtype=np.uint8)).cuda()
+    block = n_local * cap // 4 + 4 * n_local
+    wire = torch.zeros(world * block, dtype=torch.uint8, device="cuda")
+    for r in range(world):                                    # what every rank contributes to the all-gather
+        sp.pack_dibits_device(d[r].data_ptr(), n_local * cap, wire[r * block:].data_ptr())
+    out = torch.zeros_like(d)
+    sp.unpack_dibits_device(wire.data_ptr(), world, n_local * cap // 4, block, out.data_ptr(), n_local * cap)
+    sp.synchronize()
+    assert torch.equal(out, d)
+    assert torch.equal(wire.view(world, block)[0, : n_local * cap // 4].cpu(), shard._pack_cpu(d[0].cpu()))

@@ -78,6 +78,14 @@ def test_gather_dibits_world2_gloo(n_carriers):
     assert list(ok) == [1] * world
 
 
+def test_transport_packing_round_trip():
+    rng = np.random.default_rng(3)
+    d = torch.from_numpy(rng.integers(0, 4, size=64, dtype=np.uint8))
+    p = shard._pack_cpu(d)
+    assert p.shape == (16,) and int(p[0]) == int(d[0]) | int(d[1]) << 2 | int(d[2]) << 4 | int(d[3]) << 6
+    assert torch.equal(shard._unpack_cpu(p), d)
+
+
 def test_gather_is_identity_without_process_group():
     d = torch.zeros((3, 5), dtype=torch.uint8)
     n = torch.zeros(3, dtype=torch.int32)

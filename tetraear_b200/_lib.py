@@ -34,6 +34,8 @@ _SIGS = {
                                      C.c_void_p, C.c_void_p]),
     "tetra_process_wideband": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tetra_pack_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "tetra_unpack_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),
     "tetra_enable_kernel_timing": (C.c_int, [c_ctx_p, C.c_int]),
     "tetra_kernel_time_ms": (C.c_double, [c_ctx_p, C.POINTER(C.c_int32)]),

@@ -819,6 +819,39 @@ int tetra_process_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const dou
     return tetra_process_batch(ctx, (const float*)ctx->wide.p, C, N, N, nullptr, dibits, cap, n_dibits, symbols, best_phase, ts_match, 0);
 }
 
+int tetra_pack_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, uint8_t* packed) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n < 0 || (n & 15) || (n > 0 && (!dibits || !packed)) || ((reinterpret_cast<uintptr_t>(dibits) & 15) != 0) ||
+        ((reinterpret_cast<uintptr_t>(packed) & 3) != 0))
+        return fail(ctx, TETRA_E_INVALID, "tetra_pack_dibits: n must be a multiple of 16, dibits 16-byte and packed 4-byte aligned");
+    if (n == 0) return TETRA_OK;
+    if (!is_device_ptr(dibits) || !is_device_ptr(packed)) return fail(ctx, TETRA_E_INVALID, "tetra_pack_dibits: device buffers only");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t n16 = n / 16;
+    k_pack_dibits<<<(unsigned)std::min<int64_t>((n16 + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>((const uint4*)dibits, n16, (uint32_t*)packed);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TETRA_OK;
+}
+
+int tetra_unpack_dibits(tetra_ctx* ctx, const uint8_t* packed, int64_t n_blocks, int64_t packed_bytes, int64_t in_stride,
+                        uint8_t* dibits, int64_t out_stride) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (n_blocks < 0 || n_blocks > 65535 || packed_bytes < 0 || (packed_bytes & 3) || (in_stride & 3) || (out_stride & 15) ||
+        in_stride < packed_bytes || out_stride < 4 * packed_bytes || (n_blocks > 0 && packed_bytes > 0 && (!packed || !dibits)) ||
+        ((reinterpret_cast<uintptr_t>(packed) & 3) != 0) || ((reinterpret_cast<uintptr_t>(dibits) & 15) != 0))
+        return fail(ctx, TETRA_E_INVALID, "tetra_unpack_dibits: bad sizes or alignment");
+    if (n_blocks == 0 || packed_bytes == 0) return TETRA_OK;
+    if (!is_device_ptr(dibits) || !is_device_ptr(packed)) return fail(ctx, TETRA_E_INVALID, "tetra_unpack_dibits: device buffers only");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t words = packed_bytes / 4;
+    const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((words + 255) / 256, (148 * 8 + n_blocks - 1) / n_blocks));
+    k_unpack_dibits<<<dim3(gx, (unsigned)n_blocks), 256, 0, ctx->stream>>>(packed, words, in_stride, dibits, out_stride);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TETRA_OK;
+}
+
 int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits, int32_t C,
                          int32_t* sync_pos, int32_t max_pos, int32_t* n_sync) {
     if (!ctx) return TETRA_E_INVALID;

@@ -437,4 +437,29 @@ __global__ void __launch_bounds__(256) k_sync_match(const SyncArgs a) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Transport packing of dibit streams (values 0..3) for the one collective of the path: four dibits per byte,
+//   packed[k] = d[4k] | d[4k+1] << 2 | d[4k+2] << 4 | d[4k+3] << 6.
+// A thread turns 16 dibits (one 16-byte load) into one 32-bit word and back.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack4(uint32_t w) { return (w | (w >> 6) | (w >> 12) | (w >> 18)) & 0xFFu; }
+__device__ __forceinline__ uint32_t unpack4(uint32_t b) { return (b & 3u) | ((b & 0xCu) << 6) | ((b & 0x30u) << 12) | ((b & 0xC0u) << 18); }
+
+__global__ void __launch_bounds__(256) k_pack_dibits(const uint4* __restrict__ in, int64_t n16, uint32_t* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(in + i);
+        out[i] = pack4(v.x) | (pack4(v.y) << 8) | (pack4(v.z) << 16) | (pack4(v.w) << 24);
+    }
+}
+// blocks of `words` packed 32-bit words at a stride of in_stride bytes -> 16 * words dibits per block at out_stride bytes
+__global__ void __launch_bounds__(256) k_unpack_dibits(const uint8_t* __restrict__ in, int64_t words, int64_t in_stride,
+                                                       uint8_t* __restrict__ out, int64_t out_stride) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(in + (int64_t)blockIdx.y * in_stride);
+    uint4* dst = reinterpret_cast<uint4*>(out + (int64_t)blockIdx.y * out_stride);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < words; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(src + i);
+        dst[i] = make_uint4(unpack4(w & 0xFFu), unpack4((w >> 8) & 0xFFu), unpack4((w >> 16) & 0xFFu), unpack4(w >> 24));
+    }
+}
+
 }  // namespace tetra

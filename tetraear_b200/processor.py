@@ -358,6 +358,15 @@ class SignalProcessor:
         self._check(self._lib.tetra_last_phase_ms(self._ctx, out.ctypes.data), "last_phase_ms")
         return out.tolist()
 
+    def pack_dibits_device(self, dibits_ptr: int, n: int, packed_ptr: int):
+        """Four dibits per byte for transport (device pointers, asynchronous on the context's stream)."""
+        self._check(self._lib.tetra_pack_dibits(self._ctx, dibits_ptr, n, packed_ptr), "pack_dibits")
+
+    def unpack_dibits_device(self, packed_ptr: int, n_blocks: int, packed_bytes: int, in_stride: int, dibits_ptr: int, out_stride: int):
+        """Inverse of ``pack_dibits_device`` over the blocks an all-gather leaves (device pointers, asynchronous)."""
+        self._check(self._lib.tetra_unpack_dibits(self._ctx, packed_ptr, n_blocks, packed_bytes, in_stride, dibits_ptr, out_stride),
+                    "unpack_dibits")
+
     def launch_count(self) -> int:
         return int(self._lib.tetra_launch_count(self._ctx))
 

@@ -6,8 +6,8 @@ tetraear/ui/modern.py:1879), so carriers are block-partitioned over the ranks, e
 only its own IQ, and the decoded dibit streams are exchanged once with an all-gather so that every rank
 can run the host-side ``TetraDecoder`` on all carriers (BASELINE.json north_star).
 
-torch.distributed is plumbing here (NCCL over NVLink on the GPU box, gloo in the CPU tests); nothing in
-this module computes.
+torch.distributed is plumbing here (NCCL over NVLink on the GPU box, gloo in the CPU tests); the only
+arithmetic in this module is the host-tensor form of the 2-bit transport packing used by those tests.
 """
 from __future__ import annotations
 
@@ -76,35 +76,62 @@ def gather_dibits(dibits: torch.Tensor, n_dibits: torch.Tensor, n_carriers: int,
     return out_dibits, out_n
 
 
-class PackedStreams:
-    """The dibit streams and their lengths of one rank in ONE buffer, so that the exchange is a single collective:
-    ``[n_local * cap]`` uint8 dibits followed by ``[n_local]`` int32 lengths (cap is rounded up to a multiple of 4 so
-    the lengths stay aligned). ``dibits`` / ``n_dibits`` are views the demodulator writes into; ``gather()`` all-gathers
-    the buffer and returns views over the received blocks."""
+def _pack_cpu(d: torch.Tensor) -> torch.Tensor:
+    """Reference packing for host tensors (the gloo tests): four dibits per byte, first dibit in the low bits."""
+    q = d.reshape(-1, 4).to(torch.int32)
+    return (q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)).to(torch.uint8)
 
-    def __init__(self, n_carriers: int, cap: int, device=None, group=None):
+
+def _unpack_cpu(p: torch.Tensor) -> torch.Tensor:
+    q = p.reshape(-1, 1).to(torch.int32)
+    return torch.cat([(q >> s) & 3 for s in (0, 2, 4, 6)], dim=1).to(torch.uint8).reshape(-1)
+
+
+class PackedStreams:
+    """The dibit streams and their lengths of one rank in ONE buffer, so that the exchange is a single collective, with
+    the dibits packed four to a byte for the wire: ``[n_local * cap / 4]`` bytes followed by ``[n_local]`` int32 lengths
+    (cap is rounded up to a multiple of 16). ``dibits`` / ``n_dibits`` are what the demodulator writes into;
+    ``gather()`` packs, all-gathers the buffer and unpacks every rank's block. On the GPU the packing runs in the
+    library's kernels (``packer`` = the ``SignalProcessor`` whose stream the demodulation runs on)."""
+
+    def __init__(self, n_carriers: int, cap: int, device=None, group=None, packer=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if n_carriers % self.world:
             raise ValueError("PackedStreams needs an even partition; use gather_dibits for ragged ones")
         self.n_carriers, self.n_local = n_carriers, n_carriers // self.world
-        self.cap = (cap + 3) & ~3
-        self.block = self.n_local * self.cap + 4 * self.n_local
+        self.cap = (cap + 15) & ~15
+        self.packer = packer
+        self.packed_bytes = self.n_local * self.cap // 4
+        self.block = self.packed_bytes + 4 * self.n_local
+        self.dibits = torch.zeros((self.n_local, self.cap), dtype=torch.uint8, device=device)
         self.local = torch.zeros(self.block, dtype=torch.uint8, device=device)
-        self.all = torch.zeros(self.block * self.world, dtype=torch.uint8, device=device) if self.world > 1 else self.local
-        self.dibits = self.local[: self.n_local * self.cap].view(self.n_local, self.cap)
-        self.n_dibits = self.local[self.n_local * self.cap:].view(torch.int32)
+        self.n_dibits = self.local[self.packed_bytes:].view(torch.int32)
+        if self.world > 1:
+            self.all = torch.zeros(self.block * self.world, dtype=torch.uint8, device=device)
+            self.out = torch.zeros((self.world, self.n_local, self.cap), dtype=torch.uint8, device=device)
+        if self.dibits.is_cuda and packer is None and self.world > 1:
+            raise ValueError("PackedStreams on a GPU needs the SignalProcessor as packer")
 
     def gather(self):
-        """One all-gather. Returns views over the received blocks: dibits ``[world, n_local, cap]`` (carrier c is
-        ``[c // n_local, c % n_local]``) and lengths ``[world, n_local]`` -- no copy is made."""
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.all, self.local, group=self.group)
+        """Pack, one all-gather, unpack. Returns dibits ``[world, n_local, cap]`` (carrier c is
+        ``[c // n_local, c % n_local]``) and lengths ``[world, n_local]``."""
+        if self.world == 1:
+            return self.dibits.unsqueeze(0), self.n_dibits.unsqueeze(0)
+        if self.dibits.is_cuda:
+            self.packer.pack_dibits_device(self.dibits.data_ptr(), self.n_local * self.cap, self.local.data_ptr())
+        else:
+            self.local[: self.packed_bytes] = _pack_cpu(self.dibits)
+        dist.all_gather_into_tensor(self.all, self.local, group=self.group)
         blocks = self.all.view(self.world, self.block)
-        d = blocks[:, : self.n_local * self.cap].unflatten(1, (self.n_local, self.cap))
-        n = blocks[:, self.n_local * self.cap:].view(torch.int32)
-        return d, n
+        if self.dibits.is_cuda:
+            self.packer.unpack_dibits_device(self.all.data_ptr(), self.world, self.packed_bytes, self.block,
+                                             self.out.data_ptr(), self.n_local * self.cap)
+        else:
+            for r in range(self.world):
+                self.out[r] = _unpack_cpu(blocks[r, : self.packed_bytes]).view(self.n_local, self.cap)
+        return self.out, blocks[:, self.packed_bytes:].view(torch.int32)
 
 
 def max_over_ranks(value: float, device=None, group=None) -> float:
