@@ -287,8 +287,8 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
         const int nf = (int)(rg.e_hi - rg.e_lo), nb = (int)(rg.e_hi - rg.e_stop);
         const int n2 = (int)(rg.f_hi - rg.f_lo), nb2 = (int)(rg.f_hi - rg.f_stop);
         if (n2 > 32 * EXW_S2MAX || nb2 > 32 * EXW_S2MAX) return fail(ctx, TETRA_E_UNSUPPORTED, "edge window too long for the warp kernel");
-        sos_transition_powers(ea.cf, (nf + 31) / 32, ctx->edge_mats.data() + (var + 0) * 5 * 64);
-        sos_transition_powers(ea.cf, (nb + 31) / 32, ctx->edge_mats.data() + (var + 1) * 5 * 64);
+        sos_transition_powers(ea.cf, exw_chunk_len(nf), ctx->edge_mats.data() + (var + 0) * 5 * 64);
+        sos_transition_powers(ea.cf, exw_chunk_len(nb), ctx->edge_mats.data() + (var + 1) * 5 * 64);
         ba_transition_powers(ea.cf, (n2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 0) * 5 * 16);
         ba_transition_powers(ea.cf, (nb2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 1) * 5 * 16);
     }

@@ -269,6 +269,13 @@ __host__ __device__ inline EdgeRange edge_range(int mode, int64_t n, int L, int 
 // The serial depth drops from n to 2 n / 32 steps plus the scan.
 // ----------------------------------------------------------------------------------------------
 constexpr int EXW_BLK = 8;                // steps per prefetched block inside a chunk
+// chunk length of a pass of n steps over 32 lanes: at least n / 32, stretched so that what follows the three pipeline-fill
+// steps is a whole number of blocks (steps outside the blocks take the slow, branching path; the last lanes may run short or empty)
+__host__ __device__ inline int exw_chunk_len(int n) {
+    int lc = (n + 31) / 32;
+    const int r = lc > 3 ? (lc - 3) % EXW_BLK : 0;
+    return r ? lc + EXW_BLK - r : lc;
+}
 constexpr int EXW_S2MAX = 16;             // stage-2 chunk length bound (inputs of a chunk stay in registers)
 static_assert(K_EDGE_MAX_S2 <= 32 * EXW_S2MAX, "stage-2 window does not fit 32 chunks of EXW_S2MAX");
 
@@ -364,7 +371,7 @@ __device__ __forceinline__ void vec_to_skew(const double (&v)[8][2], SkewState& 
 template <class Raw, class Load, class Cook, class Emit>
 __device__ __forceinline__ void sos_pass_warp(const ExactCoef& cf, int n_steps, double2 x0, const double* __restrict__ mp,
                                               int lane, Load&& load, Cook&& cook, Emit&& emit) {
-    const int lc = (n_steps + 31) / 32;
+    const int lc = exw_chunk_len(n_steps);
     const int start = lane * lc;
     const int len = max(0, min(lc, n_steps - start));
     SkewState st;
