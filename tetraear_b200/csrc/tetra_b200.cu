@@ -304,7 +304,9 @@ int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, cons
     g.e.w1 = w1; g.e.wz = wz; g.e.fo = ea.fo; g.e.fs_dec = ea.fs_dec;
     g.m1 = (const double*)ctx->mats.p;
     g.m2 = (const double*)ctx->mats.p + 4 * 5 * 64;
-    k_exact_edges_warp<<<(int)nj, 32, 0, st>>>(g);          // one warp = one job = one block: fits beside the fused kernel's CTA
+    // one warp = one job = one block. (Its 248 registers do not fit the 6400 a fused-kernel CTA leaves free in an SM
+    // sub-partition: the blocks start as those CTAs retire. Capped to fit, it slowed the fused kernel by more than it hid.)
+    k_exact_edges_warp<<<(int)nj, 32, 0, st>>>(g);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -513,7 +515,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         if (f != 0.0) any_fo = true;
         if (!(std::fabs(f) <= K1_FO_MAX_HZ)) fo_in_range = false;     // also catches NaN
     }
-    // The fused path covers freq_offset = 0 (MODE 0) and, with per-carrier complex taps, |freq_offset| <= 12.5 kHz
+    // The fused path covers freq_offset = 0 (MODE 0) and, with the NCO + equaliser of MODE 1, |freq_offset| <= 12.5 kHz
     // (MODE 1: the GUI's AFC range, ui/modern.py:1949-1967); anything else runs the exact recursion over the block.
     const bool use_fast = fast_ok && (!any_fo || fo_in_range);
     const bool u8_fused = u8 && use_fast && !any_fo && edge_mode != 2;
@@ -647,7 +649,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ka.aligned = ((reinterpret_cast<uintptr_t>(u8) & 15) == 0) && ((u8_pitch & 7) == 0);
         }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
-        // edge windows run beside the bulk kernel on the side stream
+        // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {
                 for (int k = 0; k < 4; ++k) CK(cudaEventCreate(&ctx->ph_ev[k]));
