@@ -469,15 +469,21 @@ __global__ void __launch_bounds__(32) k_exact_edges_warp(const EdgeWarpArgs w) {
     {
         const int nb = (int)(e_hi - rg.e_stop);
         const double w_nco = a.fo ? (2.0 * M_PI) * a.fo[car] : 0.0;
+        // decimation bookkeeping of this lane's chunk: the emitted samples come in order, input index i = q m + r counts down
+        int m = 0, r = -1;
         sos_pass_warp<double2>(a.cf, nb, s1[nf - 1], w.m1 + (var + 1) * 5 * 64, lane,
             [&](int s) { return s1[nf - 1 - min(s, nb - 1)]; },
-            [&](double2 r, int) { return r; },
+            [&](double2 v, int) { return v; },
             [&](int s, double yr, double yi) {
-                const int64_t i = e_hi - 1 - s - EX_PAD1;  // >= 0
-                if (i % q == 0) {
-                    const int m = (int)(i / q);
-                    if (i < n && m >= m_lo && m < m_hi) sz[m - m_lo] = edge_nco(make_double2(yr, yi), m, w_nco, a.fs_dec);
+                if (r < 0) {                               // first sample of the chunk
+                    const int64_t i = e_hi - 1 - s - EX_PAD1;  // >= 0
+                    m = (int)(i / q); r = (int)(i - (int64_t)m * q);
                 }
+                if (r == 0) {
+                    if ((int64_t)q * m < n && m >= m_lo && m < m_hi) sz[m - m_lo] = edge_nco(make_double2(yr, yi), m, w_nco, a.fs_dec);
+                    r = q; --m;
+                }
+                --r;
             });
     }
     __syncwarp();
