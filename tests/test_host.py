@@ -96,6 +96,46 @@ def test_fir_tables_reproduce_reference_interior():
     assert err[160:-160].max() < 2e-6
 
 
+def test_freq_offset_equaliser_table_and_model():
+    """The Chebyshev-series equaliser of the fused freq_offset path (tools/design_filters.py -> TB_REQ_CHEB): the committed
+    header matches the generator, and a numpy model of the chain (NCO on the proto output, half-band, 11-tap equaliser,
+    fir120, interpolation) equals decimate -> frequency_shift -> filtfilt away from the block ends."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import design_filters as df
+    taps = df.design()
+    assert taps["req_err"] < 5e-7
+    hdr = open(os.path.join(ROOT, "tetraear_b200", "csrc", "taps_generated.h")).read()
+    body = re.search(r"TB_REQ_CHEB\[(\d+)\] = \{(.*?)\};", hdr, re.S)
+    vals = np.array([float(v) for v in body.group(2).replace("\n", " ").split(",")])
+    coef = taps["req_cheb"]
+    want = np.stack([coef.real, coef.imag], axis=-1).reshape(-1)
+    assert int(body.group(1)) == want.size == (df.REQ_DEG + 1) * (2 * df.REQ_K + 1) * 2
+    assert np.abs(vals - want).max() < 1e-12, "taps_generated.h is stale"
+    rng = np.random.default_rng(5)
+    n = 1 << 16
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)) / np.sqrt(2.0)      # white: every frequency is exercised
+    for fo in (12500.0, -7777.0, 1234.5):
+        r = np.polynomial.chebyshev.chebvander(np.array([fo / df.REQ_FOMAX]), df.REQ_DEG)[0] @ coef
+        L = (n + 9) // 10
+        m0 = 2 * (df.FIR_H + df.INT_K + df.HB_H + df.REQ_K) + 16
+        xe = np.concatenate([np.zeros(10 * m0 + df.PROTO_H, complex), x, np.zeros(10 * m0 + df.PROTO_H + 20, complex)])
+        w = signal.fftconvolve(xe, taps["proto"].astype(complex), mode="same")[df.PROTO_H::10][: L + 2 * m0]
+        w = w * np.exp(-2j * np.pi * fo * (np.arange(len(w)) - m0) / df.FS1)
+        u = np.convolve(np.convolve(w, taps["hb"], mode="same")[0::2], r, mode="same")
+        v = np.convolve(u, taps["fir120"], mode="same")
+        odd = np.zeros(len(v), complex)
+        for k in range(df.INT_K):
+            odd += taps["interp_half"][k] * (np.roll(v, k) + np.roll(v, -(k + 1)))
+        y = np.empty(2 * len(v), complex)
+        y[0::2], y[1::2] = v, odd
+        y = y[m0: m0 + L]
+        dec = signal.decimate(x, 10)
+        ref = ref_dsp.channel_filter(dec * np.exp(-2j * np.pi * fo * np.arange(len(dec)) / df.FS1), 25000, 240000.0)
+        err = np.abs(y - ref) / np.abs(ref).max()
+        assert err[200:-200].max() < 2.5e-6, (fo, err[200:-200].max())
+
+
 def test_find_sync_replay_on_crafted_streams():
     """Host replay (tetra_find_sync / tetra_sync_cascade) over oracle match counts on streams that reach every level of
     decode()'s cascade: planted TS1/TS2 with 0..5 bit errors, hits closer than the 250-bit jump, noise only."""
