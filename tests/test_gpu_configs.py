@@ -120,6 +120,32 @@ def test_u8_ingest_fused_path(gpu_processor, n):
         assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
 
 
+def test_u8_ingest_fused_path_many_carriers_per_cta(gpu_processor):
+    """More carriers than SMs: every persistent CTA streams several byte rows back to back (slot changes in the byte ring)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n, n_car = 16384 + 1280, 310
+    base = []
+    for k in range(5):
+        x = synth.carrier_iq(n, 520 + k, snr_db=22.0, alphabet="centred" if k & 1 else "pi4")
+        z = x / np.abs(x).max() * 0.9
+        base.append(np.stack([np.clip(np.round((z.real + 1.0) * 127.5), 0, 255), np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)], axis=-1).astype(np.uint8))
+    raw = np.stack([base[(3 * c + c // 148) % 5] for c in range(n_car)])
+    res = sp.process_batch_u8(raw, None, want_symbols=True)
+    refs = {}
+    for c in (0, 1, 147, 148, 149, 200, 296, 297, 309):
+        k = (3 * c + c // 148) % 5
+        if k not in refs:
+            x128 = (base[k][:, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (base[k][:, 1].astype(np.float64) / 127.5 - 1.0)
+            refs[k] = ref_dsp.process(x128, 0.0, 2.4e6)
+        r = refs[k]
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], c
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), c
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, err)
+
+
 def test_scanner_analysis_matches_reference_golden(gpu_processor):
     """TetraSignalDetector's per-sample analysis on the device vs the reference's own numbers."""
     import os, sys
