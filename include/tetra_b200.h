@@ -49,6 +49,10 @@ int tetra_synchronize(tetra_ctx* ctx);
  * (n_symbols - 1, signal/processor.py:213-215 and :135). */
 int64_t tetra_dibit_capacity(const tetra_ctx* ctx, int64_t n_samples);
 
+/* Number of soft symbols extract_symbols keeps for an N-sample block whose timing pick chose `best_phase`
+ * ((len - best_phase) // sps, signal/processor.py:213-215; the whole block below 2 samples per symbol, :184-186). */
+int64_t tetra_symbol_count(const tetra_ctx* ctx, int64_t n_samples, int32_t best_phase);
+
 /*
  * Replaces SignalProcessor.process (signal/processor.py:221-273) for a batch of C independent
  * carriers, plus -- optionally -- the bit expansion and the training-sequence correlation of
@@ -199,6 +203,16 @@ int tetra_resample(tetra_ctx* ctx, const double* in, int64_t n, int64_t n_out, d
  */
 int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n_samples, int32_t nfft, int32_t hop,
                   float* out, int64_t* rows);
+
+/*
+ * Block-end corrections of the fused 2.4 MS/s path, exposed for testing: what SciPy's sosfiltfilt / filtfilt edge
+ * handling (odd extension, zi * x0, inside scipy.signal.decimate and filter_signal, processor.py:254 and :79) adds to
+ * the shift-invariant response of the zero-extended block, for the 168 outputs next to each end of every carrier.
+ *   iq host [C][pitch] complex64, freq_offset_hz host [C] or NULL, out host [C][2][168] complex64 (left end m = 0..,
+ *   right end output L-1-t, t = 0..). n_samples >= 16384.
+ */
+int tetra_edge_corrections(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int64_t n_samples, int64_t pitch,
+                           const double* freq_offset_hz, float* out);
 
 /* Filter design used by the generic path (what scipy.signal.butter / cheby1 return to the
  * reference at processor.py:78 and inside scipy.signal.decimate). Exposed for testing. */

@@ -37,6 +37,11 @@ CASES = [
     ("tiny_100", dict(seed=10, alphabet="centred", snr_db=30.0), 100, 2.4e6, 0.0),
     ("tiny_20", dict(seed=11, alphabet="centred", snr_db=30.0), 20, 2.4e6, 0.0),
     ("tiny_300", dict(seed=12, alphabet="centred", snr_db=30.0), 300, 2.4e6, 0.0),
+    ("one_symbol_200", dict(seed=13, alphabet="centred", snr_db=30.0), 200, 2.4e6, 0.0),      # 20 samples at 240 kS/s: one symbol, no dibit
+    # the true TETRA symbol rate (133.33 samples per symbol at 2.4 MS/s): the reference still samples every 13th of 240 kS/s,
+    # so its timing drifts through the block and decisions sit near the region borders
+    ("truerate_2p18", dict(seed=14, alphabet="pi4", snr_db=30.0, sps=400, decim=3), 1 << 18, 2.4e6, 0.0),
+    ("truerate_2p18_fo", dict(seed=15, alphabet="centred", snr_db=30.0, sps=400, decim=3), 1 << 18, 2.4e6, 2000.0),
 ]
 SYNC_THRESHOLDS = (0.90, 0.85, 0.80, 0.78)
 
@@ -69,7 +74,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     dec = TetraDecoder()
     versions = np.array([np.__version__, scipy.__version__])
+    only_missing = "--missing" in sys.argv
     for name, gen, n, fs, fo in CASES:
+        if only_missing and os.path.exists(os.path.join(OUT, name + ".npz")):
+            continue
         x = synth.carrier_iq(n, **gen)
         sp = SignalProcessor(fs)
         dib = sp.process(x.astype(np.complex128), fo)
@@ -107,6 +115,8 @@ def main():
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
         print(name, len(dib), len(syms), best)
 
+    if only_missing and os.path.exists(os.path.join(OUT, "helpers.npz")):
+        return
     # ---- helper methods, exercised the way the reference's unit tests do (tests/unit/test_signal_processor.py) ----
     xs = helper_signal()
     sp = SignalProcessor(2.4e6)

@@ -108,7 +108,7 @@ def test_u8_ingest_fused_path(gpu_processor, n):
         raw[c, :, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
     before = sp.launch_count()
     res = sp.process_batch_u8(raw, None, want_symbols=True, want_sync=True)
-    assert sp.launch_count() - before == 4                     # windows, fused kernel, edges, finalize: no expansion pass
+    assert sp.launch_count() - before == 3                     # fused kernel, block-end corrections, finalize: no expansion pass
     for c in range(n_car):
         x128 = (raw[c, :, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (raw[c, :, 1].astype(np.float64) / 127.5 - 1.0)
         r = ref_dsp.process(x128, 0.0, 2.4e6)

@@ -18,6 +18,7 @@ _SIGS = {
     "tetra_set_stream": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tetra_synchronize": (C.c_int, [c_ctx_p]),
     "tetra_dibit_capacity": (C.c_int64, [c_ctx_p, C.c_int64]),
+    "tetra_symbol_count": (C.c_int64, [c_ctx_p, C.c_int64, C.c_int32]),
     "tetra_process_batch": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                       C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int32]),
@@ -50,6 +51,7 @@ _SIGS = {
     "tetra_resample": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "tetra_stft_db": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_int64)]),
+    "tetra_edge_corrections": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "tetra_design_butter4": (C.c_int, [C.c_double, C.c_void_p, C.c_void_p]),
     "tetra_design_cheby1_sos8": (C.c_int, [C.c_double, C.c_double, C.c_void_p]),
 }
@@ -70,9 +72,12 @@ def load():
     if _build.is_stale():
         try:
             path = _build.build()
-        except Exception:
+        except Exception as e:
             if not os.path.exists(path):
                 raise
+            import logging
+            logging.getLogger("tetraear.signal.processor").warning(
+                "libtetra_b200.so is older than its sources and could not be rebuilt (%s); loading the stale library", e)
     lib = C.CDLL(path)
     for name, (res, args) in _SIGS.items():
         fn = getattr(lib, name)      # AttributeError if the library does not export a declared symbol

@@ -24,6 +24,7 @@
 #include "tetra_kernels.cuh"
 #include "tetra_exact.cuh"
 #include "tetra_edges.cuh"
+#include "tetra_edgecorr.cuh"
 #include "tetra_finalize.cuh"
 #include "tetra_stft.cuh"
 
@@ -67,6 +68,8 @@ struct tetra_ctx {
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
+    DevBuf etab, ecorr;                // block-end correction tables (edge_tables_generated.h) and corrections [C][2][K_EDGE]
+    EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
     size_t max_scratch_bytes = (size_t)6 << 30;
@@ -128,7 +131,43 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
+    // block-end correction tables -> one device buffer
+    {
+        const double* src[7] = {ET_G1, ET_WC, ET_WAC, ET_RINGC, ET_RING, ET_U, ET_U2};
+        const size_t cnt[7] = {sizeof ET_G1 / sizeof(double), sizeof ET_WC / sizeof(double), sizeof ET_WAC / sizeof(double),
+                               sizeof ET_RINGC / sizeof(double), sizeof ET_RING / sizeof(double), sizeof ET_U / sizeof(double),
+                               sizeof ET_U2 / sizeof(double)};
+        static_assert(sizeof ET_G1 == sizeof(double) * (2 * ET_G + 1) && sizeof ET_WC == sizeof(double) * 8 * ET_NC &&
+                      sizeof ET_WAC == sizeof(double) * 8 * ET_NAC && sizeof ET_RINGC == sizeof(double) * 8 * ET_NRING &&
+                      sizeof ET_RING == sizeof(double) * 8 * ET_NRING && sizeof ET_U == sizeof(double) * 64, "edge tables changed shape");
+        size_t total = 0;
+        for (size_t c : cnt) total += (c + 3) & ~(size_t)3;             // every table starts on a 32-byte boundary
+        CK(ctx->etab.ensure(total * sizeof(double)));
+        const double* dev[7];
+        size_t off = 0;
+        for (int k = 0; k < 7; ++k) {
+            dev[k] = (const double*)ctx->etab.p + off;
+            CK(cudaMemcpy((double*)ctx->etab.p + off, src[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice));
+            off += (cnt[k] + 3) & ~(size_t)3;
+        }
+        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6]};
+    }
     ctx->tables_uploaded = true;
+    return 0;
+}
+
+// block-end corrections of the fused path (k_edge_correct) for C carriers -> ctx->ecorr
+int launch_edge_correct(tetra_ctx* ctx, cudaStream_t st, const float2* x, const uint8_t* x8, int64_t pitch, int64_t n, int32_t L,
+                        const double* d_fo, const double* d_chan, double fs, double fs_dec, const ExactCoef& cf, int32_t C) {
+    CK(ctx->ecorr.ensure((size_t)C * 2 * K_EDGE * sizeof(float2)));
+    EdgeCorrArgs ea;
+    ea.x = x; ea.x8 = x8; ea.pitch = pitch; ea.n = n; ea.L = L; ea.fo = d_fo; ea.chan = d_chan; ea.fs = fs; ea.fs_dec = fs_dec;
+    ea.cf = cf; ea.t = ctx->etab_ptrs; ea.d = (float2*)ctx->ecorr.p;
+    if (x8) k_edge_correct<1><<<C, KC_THREADS, 0, st>>>(ea);
+    else if (d_chan) k_edge_correct<2><<<C, KC_THREADS, 0, st>>>(ea);
+    else k_edge_correct<0><<<C, KC_THREADS, 0, st>>>(ea);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 
@@ -351,7 +390,8 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
-                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab};
+                      &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
+                      &ctx->etab, &ctx->ecorr};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -385,6 +425,12 @@ int64_t tetra_dibit_capacity(const tetra_ctx* ctx, int64_t n) {
     Plan p = make_plan(ctx->sample_rate, n);
     int64_t ns = p.sps > 1 ? p.L / p.sps : p.L;
     return ns > 1 ? ns - 1 : 0;
+}
+int64_t tetra_symbol_count(const tetra_ctx* ctx, int64_t n, int32_t best_phase) {
+    if (!ctx || n <= 0) return 0;
+    Plan p = make_plan(ctx->sample_rate, n);
+    if (p.sps <= 1) return p.L;                        // processor.py:184-186: no timing pick below 2 samples per symbol
+    return std::max<int64_t>(0, (p.L - best_phase) / p.sps);
 }
 int64_t tetra_launch_count(const tetra_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int tetra_enable_kernel_timing(tetra_ctx* ctx, int on) {
@@ -479,6 +525,10 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         if (n_sync) { if (d_nsync) CK(cudaMemsetAsync(n_sync, 0, sizeof(int32_t) * C, st)); else memset(n_sync, 0, sizeof(int32_t) * C); }
         return TETRA_OK;
     }
+    if (sync_pos && cap > FIN_DIB_SMEM)                // checked before anything is enqueued
+        return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
+    if (sync_pos && (int64_t)max_pos < (2 * cap) / 250 + 2)
+        return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
     if (pl.sps > 1 && (pl.sps + pl.step - 1) / pl.step > FIN_MAXPH)
         return fail(ctx, TETRA_E_UNSUPPORTED, "timing search with more than %d phases", FIN_MAXPH);
     int rc = upload_tables(ctx);
@@ -584,7 +634,10 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     ea.has_s1 = pl.has_s1; ea.has_s2 = pl.has_s2;
     fill_coef(ea.cf, pl.has_s1 ? pl.q : 1, pl.wn);
     ea.fo = chan_hz ? nullptr : d_fo; ea.fs_dec = pl.rate;
-    if (chan_hz) {
+    // block ends of the fused path: corrections from the input alone (default), or -- TETRA_EDGE_MODE = 1 / 3 / 2 -- the
+    // literal recursions of round 1 over windows at each end (kept for A/B measurements)
+    const bool edge_corr = edge_mode == 0;
+    if (chan_hz && !edge_corr) {
         // the exact edge kernels take each channel's shifted stream; only the block-end windows they read are formed
         CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
         int64_t w1 = 0, wz = 0, w1r = 0;
@@ -597,7 +650,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(cudaGetLastError());
         ea.x32 = (const float2*)ctx->wide.p; ea.pitch = N;
     }
-    if (u8_fused) {
+    if (u8_fused && !edge_corr) {
         // the exact edge kernels read complex64: expand the two end windows of every block, compactly
         const EdgeRange rl = edge_range(EX_LEFT, N, (int)pl.L, pl.q, K1_EDGE), rr = edge_range(EX_RIGHT, N, (int)pl.L, pl.q, K1_EDGE);
         const int64_t wl = std::min<int64_t>(N, ((rl.e_hi - EX_PAD1) + 7) & ~(int64_t)7);
@@ -649,6 +702,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ka.aligned = ((reinterpret_cast<uintptr_t>(u8) & 15) == 0) && ((u8_pitch & 7) == 0);
         }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
+        ka.zero_ext = edge_corr ? 1 : 0;
         // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {
@@ -681,7 +735,10 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
         if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
         // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
-        if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+        if (edge_corr)
+            rc = launch_edge_correct(ctx, ctx->side, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
+                                     (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
+        else if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
         else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
         else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
         if (rc) return rc;
@@ -691,6 +748,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
+        fa.edge_corr = edge_corr ? (const float2*)ctx->ecorr.p : nullptr;
     } else {
         rc = launch_exact(ctx, st, ea, full_jobs, 0);
         if (rc) return rc;
@@ -1149,6 +1207,32 @@ int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n, int32_t nfft, int3
     if (rc) return fail(ctx, TETRA_E_CUDA, "tetra_stft_db: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CK(cudaGetLastError());
     if (!d_out) CK(cudaMemcpyAsync(out, dout, (size_t)rows * nfft * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_edge_corrections(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz, float* out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C <= 0 || !iq || !out || pitch < N) return fail(ctx, TETRA_E_INVALID, "tetra_edge_corrections: bad arguments");
+    const Plan pl = make_plan(2.4e6, N);
+    if (N < 16384 || N > ((int64_t)1 << 30)) return fail(ctx, TETRA_E_UNSUPPORTED, "tetra_edge_corrections: the fused path needs 16384 <= n <= 2^30");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_tables(ctx);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(ctx->in.ensure((size_t)C * N * sizeof(float2)));
+    CK(cudaMemcpy2DAsync(ctx->in.p, N * sizeof(float2), iq, pitch * sizeof(float2), N * sizeof(float2), C, cudaMemcpyHostToDevice, st));
+    const double* d_fo = nullptr;
+    if (fo_hz) {
+        CK(ctx->fo.ensure(sizeof(double) * C));
+        CK(cudaMemcpyAsync(ctx->fo.p, fo_hz, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+        d_fo = (const double*)ctx->fo.p;
+    }
+    ExactCoef cf;
+    fill_coef(cf, 10, pl.wn);
+    rc = launch_edge_correct(ctx, st, (const float2*)ctx->in.p, nullptr, N, N, (int32_t)pl.L, d_fo, nullptr, 2.4e6, 240000.0, cf, C);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, ctx->ecorr.p, (size_t)C * 2 * K_EDGE * sizeof(float2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return TETRA_OK;
 }

@@ -24,6 +24,8 @@ struct FinArgs {
     const double* partial;   // [C][n_seg][16] power sums of the bulk kernel (or null)
     int32_t n_seg;
     int32_t bulk_lo, bulk_hi;  // y range already covered by `partial` (empty if bulk_lo >= bulk_hi)
+    const float2* edge_corr; // [C][2][K_EDGE] or null: block-end corrections (tetra_edgecorr.cuh) to add to y[m], m < K_EDGE,
+                             // and y[L-1-t], t < K_EDGE, wherever they are read
     uint8_t* dibits;         // [C][cap]
     int64_t cap;
     int32_t* n_dibits;       // [C]
@@ -209,6 +211,15 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     const float2* __restrict__ y = a.y + (int64_t)car * a.y_pitch;
     const int L = a.L, sps = a.sps, step = a.step;
     const int nph = (sps + step - 1) / step;            // phases tried: 0, step, 2 step, ... (<= FIN_MAXPH)
+    const float2* __restrict__ ec = a.edge_corr ? a.edge_corr + (int64_t)car * 2 * K_EDGE : nullptr;
+    // sample n of the filtered stream: the fused kernel's output plus, next to the block ends, the correction
+    auto y_at = [&](int n, float2 v) {
+        if (ec) {
+            if (n < K_EDGE) { const float2 d = ec[n]; v.x += d.x; v.y += d.y; }
+            if (n >= L - K_EDGE) { const float2 d = ec[K_EDGE + (L - 1 - n)]; v.x += d.x; v.y += d.y; }
+        }
+        return v;
+    };
     int best = 0;
     if (sps > 1) {
         // Power sum of phase ph over n = ph + sps*k, k < cnt = (L - ph) / sps. Thread (g, p) = (tid / nph, tid % nph)
@@ -225,11 +236,11 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
             const int k_lo_end = has_bulk ? min(cnt, max(0, (a.bulk_lo - ph + sps - 1) / sps)) : cnt;
             const int k_hi_beg = has_bulk ? max(k_lo_end, (a.bulk_hi - ph + sps - 1) / sps) : cnt;
             for (int k = g; k < k_lo_end; k += G) {
-                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
+                const float2 v = y_at(ph + sps * k, y[y_index(ph + sps * k, sps, a.y_rows)]);
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
             for (int k = k_hi_beg + g; k < cnt; k += G) {
-                const float2 v = y[y_index(ph + sps * k, sps, a.y_rows)];
+                const float2 v = y_at(ph + sps * k, y[y_index(ph + sps * k, sps, a.y_rows)]);
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
         }
@@ -272,9 +283,9 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
         float2 s1[FIN_B], s0[FIN_B];
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
-            const int k = min(k0 + j * FIN_THREADS, n_sym - 1);
-            s1[j] = ys[ks * k];
-            s0[j] = ys[ks * max(k - 1, 0)];
+            const int k = min(k0 + j * FIN_THREADS, n_sym - 1), kp = max(k - 1, 0);
+            s1[j] = y_at(best + stride * k, ys[ks * k]);
+            s0[j] = y_at(best + stride * kp, ys[ks * kp]);
         }
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {

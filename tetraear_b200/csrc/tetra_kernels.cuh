@@ -165,6 +165,9 @@ struct K1Args {
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x (x8) base/pitch allow 16-byte bulk copies
+    int32_t zero_ext;       // 1: the block is extended by zeros and y is written over the whole block (the block-end corrections
+                            //    of tetra_edgecorr.cuh are added by the finalize kernel); 0: K1_EDGE outputs at each end are left
+                            //    to the exact edge kernels and what lies beyond the block is arbitrary
     // MODE >= 1 only
     const double* fo;       // [C] Hz: freq_offset (MODE 1) / channel offset (MODE 2)
     double fs_dec;          // 240000
@@ -444,7 +447,30 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 const int q_now = q;                           // slot of the tile being filtered
                 if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
                 if (MODE != 3) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
-                if (gx0 < a.n && gx0 + K1_TILE > 0) {          // tiles entirely outside the block carry nothing
+                const bool inside = gx0 < a.n && gx0 + K1_TILE > 0;
+                if (a.zero_ext && inside && (gx0 < 0 || gx0 + K1_TILE > a.n)) {
+                    // a tile that straddles a block end: what lies outside the block becomes zero (the cascade then computes
+                    // the shift-invariant response of the zero-extended block, which the block-end corrections refer to)
+                    float2* wb = &s.in[i % NB][0];
+                    const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
+                    const int hi = (int)min((int64_t)K1_TILE, a.n - gx0);
+                    const float2 zero = make_float2(0.f, 0.f);
+                    if (gx0 < 0 && L5 < K1_HDR) wb[L5] = zero;                  // the header precedes the block as well
+                    for (int k = L5; k < lo; k += 128) wb[K1_HDR + k] = zero;
+                    for (int k = hi + L5; k < K1_TILE; k += 128) wb[K1_HDR + k] = zero;
+                    // a bulk copy moves whole 16-byte units: the block's last samples it left out come by plain loads
+                    if (MODE == 3) {
+                        const int done = a.aligned ? ((hi - lo) & ~7) : (hi - lo);
+                        if (L5 < hi - lo - done) {
+                            const uint8_t* pb = a.x8 + 2 * ((int64_t)k1_slot(a, q_now).car * a.pitch + gx0 + lo + done + L5);
+                            wb[K1_HDR + lo + done + L5] = make_float2(fmaf((float)pb[0], 1.0f / 127.5f, -1.f), fmaf((float)pb[1], 1.0f / 127.5f, -1.f));
+                        }
+                    } else if (a.aligned && ((hi - lo) & 1) && L5 == 0) {
+                        wb[K1_HDR + hi - 1] = __ldg(a.x + (int64_t)k1_slot(a, q_now).car * a.pitch + gx0 + hi - 1);
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                if (inside) {
                     const float2* buf = &s.in[i % NB][0];
                     const float4* p4 = reinterpret_cast<const float4*>(buf + 50 * L5);
                     float2 acc[5];
@@ -485,6 +511,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
                     // tail of this tile -> header of the next buffer
                     if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = buf[K1_TILE + L5];
+                } else if (a.zero_ext) {                       // a tile entirely outside the block: zeros
+                    const int wbase = K1_W * i + K1_A0 + 5 * L5;
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = make_float2(0.f, 0.f);
+                    if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = make_float2(0.f, 0.f);
                 }
             }
             k1_bar_sync();
@@ -609,7 +640,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
         int q_cur = -1;                                     // slot the sums belong to (-1: none yet)
         K1Slot sl = {0, 0, 0, 0};
-        int y_lo = 0, y_hi = 0;
+        int y_lo = 0, y_hi = 0;                             // outputs whose power this kernel sums
+        int st_lo = 0, st_hi = 0;                           // outputs this kernel stores
         float2* yc = a.y;
         // hand the sums of slot q_cur to `partial`; i = iteration about to run (the rotations so far make slot j of
         // pacc mean phase (n0 + j) % 13 with n0 this thread's first output of iteration i under the OLD slot)
@@ -638,14 +670,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 if (q_cur >= 0 && q_cur < n_my) {
                     sl = k1_slot(a, q_cur);
                     y_lo = max(sl.n_lo, K1_EDGE); y_hi = min(sl.n_hi, a.L - K1_EDGE);
+                    // with the zero extension the whole block is stored (the K1_EDGE outputs at each end still lack their
+                    // correction, so their power is left to the finalize kernel)
+                    st_lo = a.zero_ext ? sl.n_lo : y_lo; st_hi = a.zero_ext ? sl.n_hi : y_hi;
                     yc = a.y + (int64_t)sl.car * a.y_pitch;
                 } else {
-                    y_lo = y_hi = 0;
+                    y_lo = y_hi = st_lo = st_hi = 0;
                 }
             }
             const int nu0 = K1_U * i + K1_D0 + 5 * ld;      // stream v index of the first output pair
             const int n0 = 2 * nu0 - q_cur * S + sl.O;      // y index of the first output within the carrier (even)
-            if (n0 + 10 > y_lo && n0 < y_hi) {
+            if (n0 + 10 > st_lo && n0 < st_hi) {
                 float2 v[5 + 2 * TB_INT_K - 1];             // v[nu0-7 .. nu0+4+8]
 #pragma unroll
                 for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) v[t] = s.v[(nu0 - (TB_INT_K - 1) + t) & (K1_VRING - 1)];
@@ -673,10 +708,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                     for (int r = 0; r < 10; ++r) {
                         const int n = n0 + r;
-                        if (n >= y_lo && n < y_hi) {
-                            yc[(int64_t)row * a.y_rows + col] = yv[r];
-                            pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
-                        }
+                        if (n >= st_lo && n < st_hi) yc[(int64_t)row * a.y_rows + col] = yv[r];
+                        if (n >= y_lo && n < y_hi) pacc[r] += (double)fmaf(yv[r].x, yv[r].x, yv[r].y * yv[r].y);
                         if (++row == K1_NPH) { row = 0; ++col; }
                     }
                 }

@@ -358,7 +358,8 @@ __global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restric
 __global__ void __launch_bounds__(256) k_u8_to_c64(const uint8_t* __restrict__ in, int64_t n_samples, float2* __restrict__ out) {
     const int64_t n16 = n_samples / 8;
     const uint4* in16 = reinterpret_cast<const uint4*>(in);
-    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0;
+    // 16-byte loads AND 16-byte stores: rows of an odd length leave every other output row only 8-byte aligned
+    const bool aligned = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     auto cv = [](uint32_t b) { return (float)((double)b / 127.5 - 1.0); };
     if (aligned) {
         for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x) {

@@ -143,10 +143,18 @@ class SignalProcessor:
             self.symbols = np.array([], dtype=complex)
             return np.array([], dtype=np.uint8)
         n = int(res["n_dibits"][0])
-        n_sym = n + 1 if n > 0 else int(res["n_symbols"][0])
+        n_sym = int(res["n_symbols"][0])
         self.symbols = res["symbols"][0, :n_sym].astype(np.complex128)
         self.best_phase = int(res["best_phase"][0])
         return res["dibits"][0, :n].copy()
+
+    def _n_symbols(self, n, nd, ph):
+        """soft symbols per carrier: n_dibits + 1, and for blocks too short for a dibit what extract_symbols keeps
+        (one symbol -> no dibit, but ``.symbols`` still holds it: processor.py:213-215, 268)"""
+        out = np.where(nd > 0, nd + 1, 0).astype(np.int32)
+        for c in np.nonzero(nd <= 0)[0]:
+            out[c] = int(self._lib.tetra_symbol_count(self._ctx, int(n), int(ph[c])))
+        return out
 
     def process_batch(self, iq, freq_offsets=None, want_symbols=True, want_match=False, want_sync=False):
         """Batched ``process``: iq complex64 [C, N] (numpy), freq_offsets [C] or None.
@@ -181,8 +189,7 @@ class SignalProcessor:
             mt.ctypes.data if mt is not None else None,
             spos.ctypes.data if want_sync else None, max_pos if want_sync else 0, nsync.ctypes.data if want_sync else None,
             0), "process_batch")
-        n_sym = np.where(nd > 0, nd + 1, 0).astype(np.int32)
-        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=n_sym, best_phase=ph)
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=self._n_symbols(n, nd, ph), best_phase=ph)
         if want_sync:
             out["sync_pos"] = spos
             out["n_sync"] = nsync
@@ -219,7 +226,7 @@ class SignalProcessor:
             mt.ctypes.data if mt is not None else None,
             spos.ctypes.data if want_sync else None, max_pos if want_sync else 0, nsync.ctypes.data if want_sync else None),
             "process_batch_u8")
-        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=np.where(nd > 0, nd + 1, 0).astype(np.int32), best_phase=ph)
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=self._n_symbols(n, nd, ph), best_phase=ph)
         if sym is not None:
             out["symbols"] = sym
         if mt is not None:
@@ -248,7 +255,7 @@ class SignalProcessor:
             self._ctx, x.ctypes.data, n, fr.ctypes.data, n_ch, dib.ctypes.data, cap, nd.ctypes.data,
             sym.ctypes.data if sym is not None else None, ph.ctypes.data,
             mt.ctypes.data if mt is not None else None), "process_wideband")
-        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=np.where(nd > 0, nd + 1, 0).astype(np.int32), best_phase=ph)
+        out = dict(dibits=dib[:, :cap], n_dibits=nd, n_symbols=self._n_symbols(n, nd, ph), best_phase=ph)
         if sym is not None:
             out["symbols"] = sym
         if mt is not None:
@@ -256,15 +263,20 @@ class SignalProcessor:
         return out
 
     # -- device-resident batch (bench / multi-GPU): pointers are raw CUDA addresses ----------
+    def set_stream(self, stream=None):
+        """Work of this context is enqueued on `stream` (a cudaStream_t as int; 0 = the legacy default stream,
+        None = the context's own non-blocking stream)."""
+        if stream is not None and int(stream) == 0:
+            stream = 1                                    # cudaStreamLegacy
+        self._check(self._lib.tetra_set_stream(self._ctx, stream), "set_stream")
+
     def process_batch_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int,
                              cap: int, n_dibits_ptr: int, symbols_ptr: int = 0, best_phase_ptr: int = 0,
                              ts_match_ptr: int = 0, stream=None, freq_offsets=None):
         """Enqueue on `stream` (a cudaStream_t as int; 0 = the legacy default stream, None = the
         context's own stream) with all buffers already in HBM; asynchronous."""
         self._sync_rate()
-        if stream is not None and int(stream) == 0:
-            stream = 1                                    # cudaStreamLegacy
-        self._check(self._lib.tetra_set_stream(self._ctx, stream), "set_stream")
+        self.set_stream(stream)
         fo = None
         if freq_offsets is not None:
             fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)

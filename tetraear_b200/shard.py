@@ -120,6 +120,8 @@ class PackedStreams:
         if self.world == 1:
             return self.dibits.unsqueeze(0), self.n_dibits.unsqueeze(0)
         if self.dibits.is_cuda:
+            # the library's pack / unpack kernels and the collective must be ordered on ONE stream: torch's current one
+            self.packer.set_stream(torch.cuda.current_stream(self.dibits.device).cuda_stream)
             self.packer.pack_dibits_device(self.dibits.data_ptr(), self.n_local * self.cap, self.local.data_ptr())
         else:
             self.local[: self.packed_bytes] = _pack_cpu(self.dibits)

@@ -71,9 +71,14 @@ def dqpsk_baseband(n_samples: int, seed: int, alphabet: str = "pi4", sps: int = 
 
 
 def carrier_iq(n_samples: int, seed: int, snr_db: float = 30.0, alphabet: str = "pi4",
-               sps: int = SPS_FULL) -> np.ndarray:
-    """One 25 kHz carrier at baseband + white noise over the full band -> complex64[n_samples]."""
-    y = dqpsk_baseband(n_samples, seed, alphabet, sps)
+               sps: int = SPS_FULL, decim: int = 1) -> np.ndarray:
+    """One 25 kHz carrier at baseband + white noise over the full band -> complex64[n_samples].
+
+    ``decim`` > 1 shapes at ``sps`` samples per symbol and keeps every ``decim``-th sample: sps=400, decim=3 is the true
+    TETRA rate, 18 000 symbols/s at 2.4 MS/s = 133.33 samples per symbol."""
+    y = dqpsk_baseband(n_samples * decim, seed, alphabet, sps)[::decim]
+    if decim > 1:
+        y = y / np.sqrt(np.mean(np.abs(y) ** 2))
     rng = np.random.default_rng([seed, 0xA17C])
     sigma = np.sqrt(10.0 ** (-snr_db / 10.0) / 2.0)
     noise = sigma * (rng.standard_normal(n_samples) + 1j * rng.standard_normal(n_samples))
