@@ -68,7 +68,7 @@ struct tetra_ctx {
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
-    DevBuf etab, ecorr;                // block-end correction tables (edge_tables_generated.h) and corrections [C][2][K_EDGE]
+    DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
     EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
@@ -133,39 +133,45 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
     // block-end correction tables -> one device buffer
     {
-        const double* src[7] = {ET_G1, ET_WC, ET_WAC, ET_RINGC, ET_RING, ET_U, ET_U2};
-        const size_t cnt[7] = {sizeof ET_G1 / sizeof(double), sizeof ET_WC / sizeof(double), sizeof ET_WAC / sizeof(double),
-                               sizeof ET_RINGC / sizeof(double), sizeof ET_RING / sizeof(double), sizeof ET_U / sizeof(double),
-                               sizeof ET_U2 / sizeof(double)};
+        constexpr int NT = 10;
+        const double* src[NT] = {ET_G1, ET_WC, ET_WAC, ET_RINGC, ET_RING, ET_U, ET_U2, ET_BP, ET_BC, ET_BV};
+        const size_t cnt[NT] = {sizeof ET_G1 / sizeof(double), sizeof ET_WC / sizeof(double), sizeof ET_WAC / sizeof(double),
+                                sizeof ET_RINGC / sizeof(double), sizeof ET_RING / sizeof(double), sizeof ET_U / sizeof(double),
+                                sizeof ET_U2 / sizeof(double), sizeof ET_BP / sizeof(double), sizeof ET_BC / sizeof(double),
+                                sizeof ET_BV / sizeof(double)};
         static_assert(sizeof ET_G1 == sizeof(double) * (2 * ET_G + 1) && sizeof ET_WC == sizeof(double) * 8 * ET_NC &&
                       sizeof ET_WAC == sizeof(double) * 8 * ET_NAC && sizeof ET_RINGC == sizeof(double) * 8 * ET_NRING &&
                       sizeof ET_RING == sizeof(double) * 8 * ET_NRING && sizeof ET_U == sizeof(double) * 64, "edge tables changed shape");
         size_t total = 0;
         for (size_t c : cnt) total += (c + 3) & ~(size_t)3;             // every table starts on a 32-byte boundary
         CK(ctx->etab.ensure(total * sizeof(double)));
-        const double* dev[7];
+        const double* dev[NT];
         size_t off = 0;
-        for (int k = 0; k < 7; ++k) {
+        for (int k = 0; k < NT; ++k) {
             dev[k] = (const double*)ctx->etab.p + off;
             CK(cudaMemcpy((double*)ctx->etab.p + off, src[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice));
             off += (cnt[k] + 3) & ~(size_t)3;
         }
-        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6]};
+        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9]};
     }
     ctx->tables_uploaded = true;
     return 0;
 }
 
-// block-end corrections of the fused path (k_edge_correct) for C carriers -> ctx->ecorr
+// block-end corrections of the fused path (k_edge_states + k_edge_recursions) for C carriers -> ctx->ecorr
 int launch_edge_correct(tetra_ctx* ctx, cudaStream_t st, const float2* x, const uint8_t* x8, int64_t pitch, int64_t n, int32_t L,
                         const double* d_fo, const double* d_chan, double fs, double fs_dec, const ExactCoef& cf, int32_t C) {
     CK(ctx->ecorr.ensure((size_t)C * 2 * K_EDGE * sizeof(float2)));
+    CK(ctx->estate.ensure((size_t)C * KC_NSTATE * sizeof(double2)));
     EdgeCorrArgs ea;
     ea.x = x; ea.x8 = x8; ea.pitch = pitch; ea.n = n; ea.L = L; ea.fo = d_fo; ea.chan = d_chan; ea.fs = fs; ea.fs_dec = fs_dec;
-    ea.cf = cf; ea.t = ctx->etab_ptrs; ea.d = (float2*)ctx->ecorr.p;
-    if (x8) k_edge_correct<1><<<C, KC_THREADS, 0, st>>>(ea);
-    else if (d_chan) k_edge_correct<2><<<C, KC_THREADS, 0, st>>>(ea);
-    else k_edge_correct<0><<<C, KC_THREADS, 0, st>>>(ea);
+    ea.cf = cf; ea.t = ctx->etab_ptrs; ea.n_carriers = C; ea.states = (double2*)ctx->estate.p; ea.d = (float2*)ctx->ecorr.p;
+    const int g1 = (C + KC_THREADS / 32 - 1) / (KC_THREADS / 32);
+    const dim3 g2((C + KC2_THREADS - 1) / KC2_THREADS, 2);
+    if (x8) { k_edge_states<1><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<1><<<g2, KC2_THREADS, 0, st>>>(ea); }
+    else if (d_chan) { k_edge_states<2><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<2><<<g2, KC2_THREADS, 0, st>>>(ea); }
+    else { k_edge_states<0><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<0><<<g2, KC2_THREADS, 0, st>>>(ea); }
+    ctx->launches++;
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -391,7 +397,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
-                      &ctx->etab, &ctx->ecorr};
+                      &ctx->etab, &ctx->ecorr, &ctx->estate};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -711,6 +717,16 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             }
             CK(cudaEventRecord(ctx->ph_ev[0], st));
         }
+        // TETRA_EDGE_SERIAL=1 (measurement only): the block-end corrections run ahead of the fused kernel on the same stream,
+        // so that the timeline's second entry is their stand-alone duration
+        static const int edge_serial = getenv("TETRA_EDGE_SERIAL") ? atoi(getenv("TETRA_EDGE_SERIAL")) : 0;
+        if (edge_corr && edge_serial) {
+            if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], st));
+            rc = launch_edge_correct(ctx, st, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
+                                     (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
+            if (rc) return rc;
+            if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], st));
+        }
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
         // the fused kernel goes first: its persistent CTAs (one per SM) must not queue behind the edge blocks
@@ -733,16 +749,18 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         CK(cudaGetLastError());
         if (t1) CK(cudaEventRecord(t1, st));
         // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
-        if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
+        const bool side_edges = !(edge_corr && edge_serial);
+        if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
         // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
-        if (edge_corr)
+        if (!side_edges) rc = 0;
+        else if (edge_corr)
             rc = launch_edge_correct(ctx, ctx->side, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
                                      (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
         else if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
         else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
         else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
         if (rc) return rc;
-        if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
+        if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));

@@ -1,4 +1,4 @@
-// KC: block-end corrections of the fused path.
+// KC: block-end corrections of the fused path (k_edge_states + k_edge_recursions).
 //
 // The reference chain  decimate(x, 10) -> [NCO] -> filtfilt(butter4)  (tetraear/signal/processor.py:245-264) is
 // shift-invariant except next to the two ends of a block, where SciPy's sosfiltfilt / filtfilt use an odd extension
@@ -8,8 +8,9 @@
 //        D[m] = reference(x)[m] - cascade(x zero-extended)[m]        for the K_EDGE outputs next to each end,
 // which is linear in x and is driven by a handful of IIR filter states at the block end. Those states are dot products
 // of the block's first / last ~1200 samples with fixed weight tables (edge_tables_generated.h, from tools/edge_model.py,
-// where the derivation and a float64 model of exactly these steps live); a few hundred literal order-4 recursion
-// steps at 240 kS/s then give D. The kernel depends on the input only, so it runs beside the fused kernel; the
+// where the derivation and a float64 model of exactly these steps live): k_edge_states, one warp per carrier. A few hundred
+// literal order-4 recursion steps at 240 kS/s then give D: k_edge_recursions, one thread per (carrier, end), the lanes
+// of a warp walking 32 carriers in lockstep. Both depend on the input only, so they run beside the fused kernel; the
 // finalize kernel adds D to the fused kernel's output where it reads the block ends.
 #pragma once
 #include <cuda_runtime.h>
@@ -19,7 +20,9 @@
 
 namespace tetra {
 
-constexpr int KC_THREADS = 128;
+constexpr int KC_THREADS = 128;           // k_edge_states: one warp per carrier, four carriers per CTA
+constexpr int KC2_THREADS = 64;           // k_edge_recursions: one thread per (carrier, block end)
+constexpr int KC_NSTATE = 8 + 8 + 2 * ET_NPTS + 4;   // per carrier: s_c, s_ac0, pts_r, pts_l, s2_k1 (complex128)
 static_assert(ET_NPTS == EX_PAD2 + 1, "stage 2's odd extension needs PAD2 + 1 decimator outputs");
 static_assert(ET_TD <= K_EDGE && ET_NRING >= 10 * ET_TD + 10, "ringing tables too short");
 static_assert(ET_G >= 10 * ET_NPTS, "pointwise windows start inside the block");
@@ -32,6 +35,9 @@ struct EdgeTables {          // device copies of edge_tables_generated.h
     const double* ring;      // [NRING][8]  backward-pass output at offset p into the ringing of unit state k
     const double* u;         // [8][8]      backward-pass state after the whole ringing of unit state k
     const double* u2;        // [4][4]      the same for the Butterworth stage (lfilter zi layout)
+    const double* bp;        // [4][2]      poles of the Butterworth stage
+    const double* bc;        // [4][2]      its input vector in modal coordinates
+    const double* bv;        // [4][4][2]   modal coordinates -> lfilter state
 };
 
 struct EdgeCorrArgs {
@@ -44,6 +50,8 @@ struct EdgeCorrArgs {
     double fs, fs_dec;
     ExactCoef cf;
     EdgeTables t;
+    int32_t n_carriers;
+    double2* states;         // [C][KC_NSTATE] scratch between the two kernels
     float2* d;               // [C][2][K_EDGE]: D_left[m] (m = 0..), D_right[t] (output L-1-t)
 };
 
@@ -54,15 +62,6 @@ __device__ __forceinline__ dcx cexp_turns(double turns) {          // exp(-j 2 p
     sincospi(-2.0 * (turns - rint(turns)), &r.y, &r.x);
     return r;
 }
-
-struct KcSmem {
-    double red[KC_THREADS / 32][8][2];
-    dcx s_c[8], s_ac0[8], pts_r[ET_NPTS], pts_l[ET_NPTS], s2_k1[4], ds[8], dsc[8], ds2[4], s2_l[4], y2e[EX_PAD2];
-    dcx buf_r1[ET_TD];       // right end: stage-1 correction d1[t] (output L-1-t), then its causal response in place
-    dcx buf_r2[ET_T2];       // right end: zero-extended stream beyond the block z'[L+t], then its causal response in place
-    dcx buf_l1[K_EDGE];      // left end: stage-1 correction d1[m], then the causal response of the difference in place
-    dcx buf_l2[ET_TD];       // left end: zero-extended stream before the block z'[-t], t = 1..TD at index t-1
-};
 
 // sample i (0 <= i < n) of this carrier as the reference sees it (complex128)
 template <int IN>
@@ -75,27 +74,6 @@ __device__ __forceinline__ dcx kc_load(const EdgeCorrArgs& a, int car, double ch
     dcx r{(double)v.x, (double)v.y};
     if (IN == 2) r = cmul(r, cexp_turns(chan_hz * ((double)i / a.fs)));     // processor.py:97-100 at the full rate
     return r;
-}
-
-// block-wide sums of 8 complex accumulators -> dst[0..8) (valid after the trailing barrier)
-__device__ __forceinline__ void kc_reduce8(KcSmem& s, dcx (&acc)[8], dcx* dst) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-            acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
-            acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
-        }
-        if (lane == 0) { s.red[warp][k][0] = acc[k].x; s.red[warp][k][1] = acc[k].y; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-        dcx t{0.0, 0.0};
-        for (int w = 0; w < KC_THREADS / 32; ++w) { t.x += s.red[w][threadIdx.x][0]; t.y += s.red[w][threadIdx.x][1]; }
-        dst[threadIdx.x] = t;
-    }
-    __syncthreads();
 }
 
 struct KcBa { dcx z[4]; };
@@ -124,26 +102,28 @@ __device__ __forceinline__ void kc_sos_from(SosState& ss, const dcx* v) {
         ss.z[k][1][0] = v[2 * k + 1].x; ss.z[k][1][1] = v[2 * k + 1].y;
     }
 }
-
-// one weighted sum pass: acc[k] += w_k(j) * x(j) over j = tid, tid + 128, ...; two samples in flight per thread
-#define KC_PASS(COUNT, LOADX, WEIGHT)                                                                   \
-    for (int j0 = tid; j0 < (COUNT); j0 += 2 * KC_THREADS) {                                            \
-        const int j1 = j0 + KC_THREADS;                                                                 \
-        const bool two = j1 < (COUNT);                                                                  \
-        const dcx v0 = LOADX(j0);                                                                       \
-        const dcx v1 = two ? LOADX(j1) : dcx{0.0, 0.0};                                                 \
-        double w0[8], w1[8];                                                                            \
-        _Pragma("unroll") for (int k = 0; k < 8; ++k) { w0[k] = WEIGHT(k, j0); w1[k] = two ? WEIGHT(k, j1) : 0.0; } \
-        _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                                 \
-            acc[k].x += w0[k] * v0.x; acc[k].y += w0[k] * v0.y;                                         \
-            acc[k].x += w1[k] * v1.x; acc[k].y += w1[k] * v1.y;                                         \
-        }                                                                                               \
+// sums of NA complex accumulators over the lanes of a warp -> dst[0..NA) (global), written by lane 0
+template <int NA>
+__device__ __forceinline__ void kc_warp_sum(dcx (&acc)[NA], double2* dst, int lane) {
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, o);
+            acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, o);
+        }
+        if (lane == 0) dst[k] = make_double2(acc[k].x, acc[k].y);
     }
+}
 
+// ----------------------------------------------------------------------------------------------
+// k_edge_states: the functionals. One warp per carrier; lane l takes samples l, l + 32, ... of each end.
+// ----------------------------------------------------------------------------------------------
 template <int IN>   // 0: complex64 rows, 1: uint8 rows, 2: channels of one shared complex64 capture
-__global__ void __launch_bounds__(KC_THREADS) k_edge_correct(const EdgeCorrArgs a) {
-    __shared__ KcSmem s;
-    const int car = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+__global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a) {
+    const int lane = threadIdx.x & 31;
+    const int car = blockIdx.x * (KC_THREADS / 32) + (threadIdx.x >> 5);
+    if (car >= a.n_carriers) return;                          // whole warps
     const int64_t n = a.n;
     const int L = a.L;
     const int k0 = (int)((n - 1) % 10);
@@ -151,276 +131,357 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_correct(const EdgeCorrArgs 
     const double fo = a.fo ? a.fo[car] : 0.0;
     auto xr = [&](int d) { return kc_load<IN>(a, car, chan_hz, n - 1 - d); };      // d samples before the last one
     auto xl = [&](int i) { return kc_load<IN>(a, car, chan_hz, i); };
-    const ExactCoef& cf = a.cf;
-    const dcx rstep = cexp_turns(fo / a.fs_dec);              // NCO rotation per 240 kS/s sample, exp(-j W)
-    const dcx rstep_c{rstep.x, -rstep.y};                     // exp(+j W)
-    auto rot_at = [&](int64_t j) { return fo == 0.0 ? dcx{1.0, 0.0} : cexp_turns(fo * (double)j / a.fs_dec); };
+    double2* out = a.states + (int64_t)car * KC_NSTATE;
+    const double* __restrict__ g1 = a.t.g1;
+    constexpr int UN = 4;                                      // samples in flight per lane
 
-    // ---------------- phase A: states and pointwise decimator outputs as dot products with the weight tables ----------------
     dcx acc[8];
     auto clear = [&]() {
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = dcx{0.0, 0.0};
     };
-    {   // causal cascade state after x[n-1]
+    // ---- causal cascade state after x[n-1] ----
+    {
         clear();
         const double* __restrict__ wc = a.t.wc;
-#define KC_W(k, j) wc[(k) * ET_NC + (j)]
-        KC_PASS(ET_NC, xr, KC_W)
-#undef KC_W
-        kc_reduce8(s, acc, s.s_c);
+        for (int d0 = lane; d0 < ET_NC; d0 += 32 * UN) {
+            dcx v[UN];
+#pragma unroll
+            for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < ET_NC ? xr(d0 + 32 * q) : dcx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+                const int d = min(d0 + 32 * q, ET_NC - 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const double w = wc[k * ET_NC + d]; acc[k].x += w * v[q].x; acc[k].y += w * v[q].y; }
+            }
+        }
+        kc_warp_sum(acc, out, lane);
     }
-    {   // backward-pass state at position 0 of the zero-extended stream
+    // ---- backward-pass state at position 0 of the zero-extended stream ----
+    {
         clear();
         const double* __restrict__ wac = a.t.wac;
-#define KC_W(k, j) wac[(k) * ET_NAC + (j)]
-        KC_PASS(ET_NAC, xl, KC_W)
-#undef KC_W
-        kc_reduce8(s, acc, s.s_ac0);
-    }
-    const double* __restrict__ g1 = a.t.g1;
-    for (int h = 0; h < ET_NPTS / 8; ++h) {
-        // z of the zero-extended stream at output L-1-t: sum_d g1[d - k0 - 10 t] x[n-1-d]   (t = 8 h + k)
-        clear();
-        const int off_r = ET_G - k0 - 80 * h;
-#define KC_W(k, j) (((j) + off_r - 10 * (k)) >= 0 && ((j) + off_r - 10 * (k)) <= 2 * ET_G ? g1[(j) + off_r - 10 * (k)] : 0.0)
-        KC_PASS(k0 + 10 * (8 * h + 7) + ET_G + 1, xr, KC_W)
-#undef KC_W
-        kc_reduce8(s, acc, s.pts_r + 8 * h);
-        // ... and at output t: sum_i g1[10 t - i] x[i]
-        clear();
-        const int off_l = ET_G + 80 * h;
-#define KC_W(k, j) ((off_l + 10 * (k) - (j)) >= 0 && (off_l + 10 * (k) - (j)) <= 2 * ET_G ? g1[off_l + 10 * (k) - (j)] : 0.0)
-        KC_PASS(10 * (8 * h + 7) + ET_G + 1, xl, KC_W)
-#undef KC_W
-        kc_reduce8(s, acc, s.pts_l + 8 * h);
-    }
-
-    // ---------------- phase B: one job per warp ----------------
-    if (warp == 0) {
-        // right end, stage 1. Forward pass over the 27-sample odd extension from the state after x[n-1] (sosfiltfilt's
-        // forward pass), then the backward pass back over it from zi * (last forward output); the zero-extended stream
-        // has there the backward pass's state after the forward ringing instead (U s_c)
-        if (lane == 0) {
-            dcx scv[8];
+        for (int d0 = lane; d0 < ET_NAC; d0 += 32 * UN) {
+            dcx v[UN];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) scv[k] = s.s_c[k];
+            for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < ET_NAC ? xl(d0 + 32 * q) : dcx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+                const int d = min(d0 + 32 * q, ET_NAC - 1);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { const double w = wac[k * ET_NAC + d]; acc[k].x += w * v[q].x; acc[k].y += w * v[q].y; }
+            }
+        }
+        kc_warp_sum(acc, out + 8, lane);
+    }
+    // ---- pointwise decimator outputs of the zero-extended stream: at output L-1-t, sum_d g1[d - k0 - 10 t] x[n-1-d],
+    //      and at output t, sum_i g1[10 t - i] x[i]   (t = 8 h + k) ----
+    for (int h = 0; h < ET_NPTS / 8; ++h) {
+        clear();
+        const int off_r = ET_G - k0 - 80 * h, cnt_r = k0 + 10 * (8 * h + 7) + ET_G + 1;
+        for (int d0 = lane; d0 < cnt_r; d0 += 32 * UN) {
+            dcx v[UN];
+#pragma unroll
+            for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < cnt_r ? xr(d0 + 32 * q) : dcx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int idx = d0 + 32 * q + off_r - 10 * k;
+                    const double w = (idx >= 0 && idx <= 2 * ET_G) ? g1[idx] : 0.0;
+                    acc[k].x += w * v[q].x; acc[k].y += w * v[q].y;
+                }
+            }
+        }
+        kc_warp_sum(acc, out + 16 + 8 * h, lane);
+        clear();
+        const int off_l = ET_G + 80 * h, cnt_l = 10 * (8 * h + 7) + ET_G + 1;
+        for (int d0 = lane; d0 < cnt_l; d0 += 32 * UN) {
+            dcx v[UN];
+#pragma unroll
+            for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < cnt_l ? xl(d0 + 32 * q) : dcx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int idx = off_l + 10 * k - (d0 + 32 * q);
+                    const double w = (idx >= 0 && idx <= 2 * ET_G) ? g1[idx] : 0.0;
+                    acc[k].x += w * v[q].x; acc[k].y += w * v[q].y;
+                }
+            }
+        }
+        kc_warp_sum(acc, out + 16 + ET_NPTS + 8 * h, lane);
+    }
+    // ---- causal Butterworth state of the zero-extended stream at the right end ----
+    // In modal coordinates (A = V diag(p) V^-1, lambda_r = p_r e^{jW}):
+    //   s(L) = V sigma,  sigma_r = c_r e^{-jW(L-1)} sum_d x[n-1-d] Om_r(d - k0),  Om_r(u) = g1[u] + lambda_r Om_r(u - 10).
+    // Ten chains (u mod 10) of NSTEP steps, each cut into three segments: a lane runs its segment from zero, then the
+    // segments' carries are chained with shuffles.
+    {
+        constexpr int LO = -(ET_G + 10) - ((-(ET_G + 10)) % 10 + 10) % 10;     // multiple of 10 at or below -(G + 10)
+        constexpr int NU = ET_G + 10 * ET_T2 + 10;
+        constexpr int NSTEP = (NU - LO) / 10;
+        constexpr int NSEG = 3, SL = (NSTEP + NSEG - 1) / NSEG;
+        static_assert((NU - LO) % 10 == 0, "whole steps");
+        const dcx rstep_c = cexp_turns(-fo / a.fs_dec);       // exp(+j W)
+        const int sg = lane / 10, chain = lane % 10;          // lanes 30, 31 idle
+        const bool active = lane < 10 * NSEG;
+        dcx lam[4], om[4], sl[4], ps[4], pw[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            lam[r] = cmul(dcx{a.t.bp[2 * r], a.t.bp[2 * r + 1]}, rstep_c);
+            om[r] = sl[r] = ps[r] = dcx{0.0, 0.0};
+            pw[r] = lam[r];
+        }
+        const int j0 = sg * SL, j1 = min(j0 + SL, NSTEP);
+        if (active) {
+            constexpr int BLK = 8;
+            for (int jb = j0; jb < j1; jb += BLK) {
+                double g[BLK];
+                dcx v[BLK];
+#pragma unroll
+                for (int q = 0; q < BLK; ++q) {
+                    const int u = LO + chain + 10 * (jb + q);
+                    const bool in = jb + q < j1;
+                    g[q] = (in && u >= -ET_G && u <= ET_G) ? g1[u + ET_G] : 0.0;
+                    const int d = u + k0;
+                    v[q] = (in && d >= 0 && (int64_t)d < n) ? xr(d) : dcx{0.0, 0.0};
+                }
+#pragma unroll
+                for (int q = 0; q < BLK; ++q) {
+                    if (jb + q < j1) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            om[r] = cmul(lam[r], om[r]);
+                            om[r].x += g[q];
+                            const dcx t0 = cmul(v[q], om[r]), t1 = cmul(v[q], pw[r]);
+                            sl[r].x += t0.x; sl[r].y += t0.y;
+                            ps[r].x += t1.x; ps[r].y += t1.y;
+                            pw[r] = cmul(pw[r], lam[r]);
+                        }
+                    }
+                }
+            }
+        }
+        // carries: C(segment) = lambda^SL C(previous segment) + Om_end(previous segment); pw / lambda = lambda^(steps taken)
+        dcx C[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) C[r] = dcx{0.0, 0.0};
+        for (int round = 1; round < NSEG; ++round) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double cx = __shfl_up_sync(0xffffffffu, C[r].x, 10), cy = __shfl_up_sync(0xffffffffu, C[r].y, 10);
+                const double ex = __shfl_up_sync(0xffffffffu, om[r].x, 10), ey = __shfl_up_sync(0xffffffffu, om[r].y, 10);
+                const double px = __shfl_up_sync(0xffffffffu, pw[r].x, 10), py = __shfl_up_sync(0xffffffffu, pw[r].y, 10);
+                if (sg == round) {
+                    // the previous segment took SL steps: its pw is lambda^(SL + 1)
+                    const double den = lam[r].x * lam[r].x + lam[r].y * lam[r].y;
+                    const dcx lsl = cmul(dcx{px, py}, dcx{lam[r].x / den, -lam[r].y / den});
+                    const dcx t = cmul(lsl, dcx{cx, cy});
+                    C[r] = dcx{t.x + ex, t.y + ey};
+                }
+            }
+        }
+        dcx tot[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const dcx t = cmul(C[r], ps[r]);
+            tot[r] = active ? dcx{sl[r].x + t.x, sl[r].y + t.y} : dcx{0.0, 0.0};
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                tot[r].x += __shfl_xor_sync(0xffffffffu, tot[r].x, o);
+                tot[r].y += __shfl_xor_sync(0xffffffffu, tot[r].y, o);
+            }
+        }
+        if (lane < 4) {
+            // sigma_r = c_r e^{-jW(L-1)} S_r ; s = V sigma
+            const dcx rl = cexp_turns(fo * (double)(L - 1) / a.fs_dec);
+            dcx st{0.0, 0.0};
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const dcx sig = cmul(cmul(dcx{a.t.bc[2 * r], a.t.bc[2 * r + 1]}, rl), tot[r]);
+                const dcx t = cmul(dcx{a.t.bv[2 * (4 * lane + r)], a.t.bv[2 * (4 * lane + r) + 1]}, sig);
+                st.x += t.x; st.y += t.y;
+            }
+            out[16 + 2 * ET_NPTS + lane] = make_double2(st.x, st.y);
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_edge_recursions: from the states to the corrections. Thread = one carrier, blockIdx.y = the end (0 left, 1 right):
+// a few hundred serial order-4 steps per thread, the same instruction stream in every lane.
+// ----------------------------------------------------------------------------------------------
+template <int IN>
+__global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrArgs a) {
+    const int car = blockIdx.x * KC2_THREADS + threadIdx.x;
+    if (car >= a.n_carriers) return;
+    const int64_t n = a.n;
+    const int L = a.L;
+    const int k0 = (int)((n - 1) % 10);
+    const double chan_hz = (IN == 2) ? a.chan[car] : 0.0;
+    const double fo = a.fo ? a.fo[car] : 0.0;
+    auto xr = [&](int d) { return kc_load<IN>(a, car, chan_hz, n - 1 - d); };
+    auto xl = [&](int i) { return kc_load<IN>(a, car, chan_hz, i); };
+    const ExactCoef& cf = a.cf;
+    const dcx rstep = cexp_turns(fo / a.fs_dec);              // NCO rotation per 240 kS/s sample, exp(-j W)
+    const dcx rstep_c{rstep.x, -rstep.y};                     // exp(+j W)
+    auto rot_at = [&](int64_t j) { return cexp_turns(fo * (double)j / a.fs_dec); };
+    const double2* stt = a.states + (int64_t)car * KC_NSTATE;
+    auto ld = [&](int k) { const double2 v = stt[k]; return dcx{v.x, v.y}; };
+    float2* dl = a.d + (int64_t)car * 2 * K_EDGE;
+    float2* dr = dl + K_EDGE;
+    KcBa st;
+
+    if (blockIdx.y == 1) {
+        // ================= right end =================
+        dcx scv[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) scv[k] = ld(k);
+        // stage 1: forward pass over the 27-sample odd extension from the state after x[n-1] (sosfiltfilt's forward pass), then
+        // the backward pass back over it from zi * (last forward output); the zero-extended stream has there the backward
+        // pass's state after the forward ringing instead (U s_c)
+        dcx ds[8];
+        {
             SosState ss;
             kc_sos_from(ss, scv);
             const dcx x_last = xr(0);
             double2 yf[EX_PAD1];
-#pragma unroll
             for (int j = 0; j < EX_PAD1; ++j) {
                 const dcx v = xr(1 + j);
-                yf[j] = make_double2(2.0 * x_last.x - v.x, 2.0 * x_last.y - v.y);
+                yf[j] = sos_step(ss, cf, make_double2(2.0 * x_last.x - v.x, 2.0 * x_last.y - v.y));
             }
-            for (int j = 0; j < EX_PAD1; ++j) yf[j] = sos_step(ss, cf, yf[j]);
             sos_init(ss, cf, yf[EX_PAD1 - 1]);
             for (int j = EX_PAD1 - 1; j >= 0; --j) sos_step(ss, cf, yf[j]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const dcx ku = kc_dot8(a.t.u + 8 * k, scv);
-                s.ds[k] = dcx{ss.z[k >> 1][k & 1][0] - ku.x, ss.z[k >> 1][k & 1][1] - ku.y};
+                ds[k] = dcx{ss.z[k >> 1][k & 1][0] - ku.x, ss.z[k >> 1][k & 1][1] - ku.y};
             }
         }
-        __syncwarp();
-        // stage-1 correction d1[t] at output L-1-t: zero-input ringing of the backward pass from ds, after the NCO
-        dcx dsv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dsv[k] = s.ds[k];
-        for (int t = lane; t < ET_TD; t += 32)
-            s.buf_r1[t] = cmul(kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, dsv), rot_at(L - 1 - t));
-    } else if (warp == 1) {
-        // left end, stage 1: the exact forward state at position 0 -- zi * ext[0], then the 27 odd-extension samples
-        // (positions -27 .. -1); the zero-extended stream starts from a zero state
-        if (lane == 0) {
-            const dcx x0 = xl(0);
-            double2 e[EX_PAD1];
-#pragma unroll
-            for (int j = 0; j < EX_PAD1; ++j) {
-                const dcx v = xl(EX_PAD1 - j);
-                e[j] = make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y);
-            }
-            SosState ss;
-            sos_init(ss, cf, e[0]);
-            for (int j = 0; j < EX_PAD1; ++j) sos_step(ss, cf, e[j]);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s.dsc[k] = dcx{ss.z[k >> 1][k & 1][0], ss.z[k >> 1][k & 1][1]};
-        }
-        __syncwarp();
-        dcx dsv[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) dsv[k] = s.dsc[k];
-        for (int m = lane; m < K_EDGE; m += 32)
-            s.buf_l1[m] = m < ET_TD ? cmul(kc_dot8(a.t.ring + (int64_t)(10 * m) * 8, dsv), rot_at(m)) : dcx{0.0, 0.0};
-    } else if (warp == 2) {
-        // the zero-extended stream outside the block: beyond the end the backward pass over the forward ringing,
-        // z[L+t] = RING[9-k0+10t] . s_c; before the start the backward pass's own ringing, z[-t] = RINGC[10t-1] . s_ac0
-        dcx v[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = s.s_c[k];
-        for (int t = lane; t < ET_T2; t += 32)
-            s.buf_r2[t] = t < ET_TD ? cmul(kc_dot8(a.t.ring + (int64_t)(9 - k0 + 10 * t) * 8, v), rot_at(L + t)) : dcx{0.0, 0.0};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = s.s_ac0[k];
-        for (int t = 1 + lane; t <= ET_TD; t += 32)
-            s.buf_l2[t - 1] = cmul(kc_dot8(a.t.ringc + (int64_t)(10 * t - 1) * 8, v), rot_at(-t));
-    } else {
-        // causal Butterworth state of the zero-extended stream at the right end:
-        // s(L) = e^{-jW(L-1)} sum_d x[n-1-d] Wv(d - k0),  Wv(u) = Bv g1[u] + e^{jW} A Wv(u - 10): ten independent chains,
-        // inputs fetched a block of steps ahead of the recursion
-        dcx S[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-        if (lane < 10) {
-            double bv[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) bv[k] = cf.b[k + 1] - cf.a[k + 1] * cf.b[0];
-            constexpr int LO = -(ET_G + 10) - ((-(ET_G + 10)) % 10 + 10) % 10;     // multiple of 10 at or below -(G + 10)
-            constexpr int NU = ET_G + 10 * ET_T2 + 10;
-            constexpr int NSTEP = (NU - LO) / 10;
-            constexpr int BLK = 8;
-            static_assert((NU - LO) % 10 == 0, "whole steps");
-            dcx W[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-            auto fetch = [&](int step, double& g, dcx& v) {
-                const int u = LO + lane + 10 * step;
-                g = (step < NSTEP && u >= -ET_G && u <= ET_G) ? g1[u + ET_G] : 0.0;
-                const int d = u + k0;
-                v = (step < NSTEP && d >= 0 && (int64_t)d < n) ? xr(d) : dcx{0.0, 0.0};
-            };
-            double gc[BLK], gn[BLK];
-            dcx vc[BLK], vn[BLK];
-#pragma unroll
-            for (int q = 0; q < BLK; ++q) fetch(q, gc[q], vc[q]);
-            for (int s0 = 0; s0 < NSTEP; s0 += BLK) {
-#pragma unroll
-                for (int q = 0; q < BLK; ++q) fetch(s0 + BLK + q, gn[q], vn[q]);
-#pragma unroll
-                for (int q = 0; q < BLK; ++q) {
-                    if (s0 + q < NSTEP) {
-                        dcx t[4];
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            t[k].x = -cf.a[k + 1] * W[0].x + (k < 3 ? W[k + 1].x : 0.0);
-                            t[k].y = -cf.a[k + 1] * W[0].y + (k < 3 ? W[k + 1].y : 0.0);
-                        }
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            W[k] = fo == 0.0 ? t[k] : cmul(rstep_c, t[k]);
-                            W[k].x += bv[k] * gc[q];
-                            const dcx p = cmul(vc[q], W[k]);
-                            S[k].x += p.x; S[k].y += p.y;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < BLK; ++q) { gc[q] = gn[q]; vc[q] = vn[q]; }
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-            for (int o = 8; o; o >>= 1) {
-                S[k].x += __shfl_xor_sync(0xffffffffu, S[k].x, o);
-                S[k].y += __shfl_xor_sync(0xffffffffu, S[k].y, o);
-            }
-        }
-        if (lane < 4) s.s2_k1[lane] = cmul(S[lane], rot_at(L - 1));
-    }
-    __syncthreads();
-
-    // ---------------- phase C: the forward recursions of stage 2, one thread each ----------------
-    float2* dl = a.d + (int64_t)car * 2 * K_EDGE;
-    float2* dr = dl + K_EDGE;
-    KcBa st;
-    if (tid == 0) {
-        // right end: causal response of the stage-1 correction over the block's last TD outputs (ascending time = descending t)
+        // stage-1 correction d1[t] at output L-1-t (zero-input ringing of the backward pass from ds) after the NCO, and its
+        // causal Butterworth response over the block's last TD outputs (ascending time = descending t)
+        dcx ydl[ET_TD], d1s[ET_NPTS];
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.z[k] = dcx{0.0, 0.0};
-        for (int t = ET_TD - 1; t >= 0; --t) s.buf_r1[t] = kc_ba_step(st, cf, s.buf_r1[t]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s.ds2[k] = st.z[k];
-    } else if (tid == 32) {
-        // left end: exact decimator outputs 0..15 after the NCO, stage 2's odd extension (positions -15 .. -1) from zi * ext[0]
-        dcx zpe[ET_NPTS];
         {
-            dcx rot{1.0, 0.0};
-#pragma unroll
-            for (int t = 0; t < ET_NPTS; ++t) {
-                const dcx p = cmul(s.pts_l[t], rot);
-                zpe[t] = dcx{p.x + s.buf_l1[t].x, p.y + s.buf_l1[t].y};
+            dcx rot = rot_at(L - ET_TD);
+            for (int t = ET_TD - 1; t >= 0; --t) {
+                const dcx d1 = cmul(kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, ds), rot);
+                if (t < ET_NPTS) d1s[t] = d1;
+                ydl[t] = kc_ba_step(st, cf, d1);
                 rot = cmul(rot, rstep);
             }
         }
-        const dcx e0{2.0 * zpe[0].x - zpe[EX_PAD2].x, 2.0 * zpe[0].y - zpe[EX_PAD2].y};
+        // exact stream: the last 16 decimator outputs after the NCO, the 15-sample odd extension, forward pass held at F
+        dcx s2k[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) st.z[k] = dcx{cf.zi2[k] * e0.x, cf.zi2[k] * e0.y};
-#pragma unroll
-        for (int j = 0; j < EX_PAD2; ++j)
-            kc_ba_step(st, cf, dcx{2.0 * zpe[0].x - zpe[EX_PAD2 - j].x, 2.0 * zpe[0].y - zpe[EX_PAD2 - j].y});
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s.s2_l[k] = st.z[k];
-    } else if (tid == 64) {
-        // right end: the zero-extended stream's forward pass beyond the block, from its state at the end
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st.z[k] = s.s2_k1[k];
-        for (int t = 0; t < ET_T2; ++t) s.buf_r2[t] = kc_ba_step(st, cf, s.buf_r2[t]);
-    } else if (tid == 96) {
-        // left end: the zero-extended stream's forward state at position 0 (its ringing before the block, from a zero state)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st.z[k] = dcx{0.0, 0.0};
-        for (int t = ET_TD; t >= 1; --t) kc_ba_step(st, cf, s.buf_l2[t - 1]);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s.buf_l2[k] = st.z[k];
-    }
-    __syncthreads();
-
-    // ---------------- phase D: the rest of the forward passes and the backward passes ----------------
-    if (tid == 0) {
-        // right end, exact stream: the last 16 decimator outputs after the NCO, the 15-sample odd extension, forward pass held at F
-        dcx zpe[ET_NPTS];
-        {
-            dcx rot = rot_at(L - 1);
-#pragma unroll
-            for (int t = 0; t < ET_NPTS; ++t) {
-                const dcx p = cmul(s.pts_r[t], rot);
-                zpe[t] = p;
-                rot = cmul(rot, rstep_c);
-            }
+        for (int k = 0; k < 4; ++k) {
+            s2k[k] = ld(16 + 2 * ET_NPTS + k);
+            st.z[k].x += s2k[k].x; st.z[k].y += s2k[k].y;
         }
-        // (the stage-1 correction of those outputs: it was overwritten by its causal response; recompute the 16 values)
-        {
-            dcx dsv[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) dsv[k] = s.ds[k];
-            dcx rot = rot_at(L - 1);
-            for (int t = 0; t < ET_NPTS; ++t) {
-                const dcx d1 = cmul(kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, dsv), rot);
-                zpe[t].x += d1.x; zpe[t].y += d1.y;
-                rot = cmul(rot, rstep_c);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) st.z[k] = dcx{s.s2_k1[k].x + s.ds2[k].x, s.s2_k1[k].y + s.ds2[k].y};
         dcx y2e[EX_PAD2];
-#pragma unroll
-        for (int j = 0; j < EX_PAD2; ++j)
-            y2e[j] = kc_ba_step(st, cf, dcx{2.0 * zpe[0].x - zpe[1 + j].x, 2.0 * zpe[0].y - zpe[1 + j].y});
+        {
+            dcx zpe[ET_NPTS];
+            dcx rot = rot_at(L - 1);
+            for (int t = 0; t < ET_NPTS; ++t) {
+                const dcx p = cmul(ld(16 + t), rot);
+                zpe[t] = dcx{p.x + d1s[t].x, p.y + d1s[t].y};
+                rot = cmul(rot, rstep_c);
+            }
+            for (int j = 0; j < EX_PAD2; ++j)
+                y2e[j] = kc_ba_step(st, cf, dcx{2.0 * zpe[0].x - zpe[1 + j].x, 2.0 * zpe[0].y - zpe[1 + j].y});
+        }
         const dcx F = y2e[EX_PAD2 - 1];
+        // zero-extended stream beyond the block: the backward pass over the forward ringing, z[L+t] = RING[9-k0+10t] . s_c,
+        // through the forward pass from that stream's state at the end
+        dcx y2k[ET_T2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st.z[k] = s2k[k];
+        {
+            dcx rot = rot_at(L);
+            for (int t = 0; t < ET_T2; ++t) {
+                dcx in{0.0, 0.0};
+                if (t < ET_TD) in = cmul(kc_dot8(a.t.ring + (int64_t)(9 - k0 + 10 * t) * 8, scv), rot);
+                y2k[t] = kc_ba_step(st, cf, in);
+                rot = cmul(rot, rstep);
+            }
+        }
         // backward pass over the difference of the two forward outputs, from zi * F (filtfilt's backward start)
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.z[k] = dcx{cf.zi2[k] * F.x, cf.zi2[k] * F.y};
-        for (int t = ET_T2 - 1; t >= EX_PAD2; --t) kc_ba_step(st, cf, dcx{F.x - s.buf_r2[t].x, F.y - s.buf_r2[t].y});
-#pragma unroll
-        for (int t = EX_PAD2 - 1; t >= 0; --t) kc_ba_step(st, cf, dcx{y2e[t].x - s.buf_r2[t].x, y2e[t].y - s.buf_r2[t].y});
+        for (int t = ET_T2 - 1; t >= 0; --t) {
+            const dcx e = t < EX_PAD2 ? y2e[t] : F;
+            kc_ba_step(st, cf, dcx{e.x - y2k[t].x, e.y - y2k[t].y});
+        }
         for (int t = 0; t < K_EDGE; ++t) {
-            const dcx v = kc_ba_step(st, cf, t < ET_TD ? s.buf_r1[t] : dcx{0.0, 0.0});
+            const dcx v = kc_ba_step(st, cf, t < ET_TD ? ydl[t] : dcx{0.0, 0.0});
             dr[t] = make_float2((float)v.x, (float)v.y);
         }
-    } else if (tid == 32) {
-        // left end: causal response to the state difference and the stage-1 correction over the K_EDGE outputs; behind them
-        // the forward state rings out, which the backward pass sees as the start state U2 . state; then the backward pass
+    } else {
+        // ================= left end =================
+        dcx sac[8];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) st.z[k] = dcx{s.s2_l[k].x - s.buf_l2[k].x, s.s2_l[k].y - s.buf_l2[k].y};
-        for (int m = 0; m < K_EDGE; ++m) s.buf_l1[m] = kc_ba_step(st, cf, s.buf_l1[m]);
+        for (int k = 0; k < 8; ++k) sac[k] = ld(8 + k);
+        // stage 1: the exact forward state at position 0 -- zi * ext[0], then the 27 odd-extension samples (positions -27 .. -1);
+        // the zero-extended stream starts from a zero state
+        dcx dsc[8];
+        {
+            const dcx x0 = xl(0);
+            SosState ss;
+            {
+                const dcx v = xl(EX_PAD1);
+                sos_init(ss, cf, make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y));
+            }
+            for (int j = 0; j < EX_PAD1; ++j) {
+                const dcx v = xl(EX_PAD1 - j);
+                sos_step(ss, cf, make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y));
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) dsc[k] = dcx{ss.z[k >> 1][k & 1][0], ss.z[k >> 1][k & 1][1]};
+        }
+        // stage-1 correction d1[m] at output m (backward pass over the forward ringing of dsc) after the NCO
+        dcx dy[K_EDGE];
+        {
+            dcx rot{1.0, 0.0};
+            for (int m = 0; m < ET_TD; ++m) {
+                dy[m] = cmul(kc_dot8(a.t.ring + (int64_t)(10 * m) * 8, dsc), rot);
+                rot = cmul(rot, rstep);
+            }
+            for (int m = ET_TD; m < K_EDGE; ++m) dy[m] = dcx{0.0, 0.0};
+        }
+        // exact decimator outputs 0..15 after the NCO, stage 2's odd extension (positions -15 .. -1) from zi * ext[0]
+        {
+            dcx zpe[ET_NPTS];
+            dcx rot{1.0, 0.0};
+            for (int t = 0; t < ET_NPTS; ++t) {
+                const dcx p = cmul(ld(16 + ET_NPTS + t), rot);
+                zpe[t] = dcx{p.x + dy[t].x, p.y + dy[t].y};
+                rot = cmul(rot, rstep);
+            }
+            const dcx e0{2.0 * zpe[0].x - zpe[EX_PAD2].x, 2.0 * zpe[0].y - zpe[EX_PAD2].y};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) st.z[k] = dcx{cf.zi2[k] * e0.x, cf.zi2[k] * e0.y};
+            for (int j = 0; j < EX_PAD2; ++j)
+                kc_ba_step(st, cf, dcx{2.0 * zpe[0].x - zpe[EX_PAD2 - j].x, 2.0 * zpe[0].y - zpe[EX_PAD2 - j].y});
+        }
+        // the zero-extended stream before the block is the backward pass's own ringing, z[-t] = RINGC[10t-1] . s_ac0: its forward
+        // state at position 0 (from a zero state)
+        {
+            KcBa sk;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) sk.z[k] = dcx{0.0, 0.0};
+            dcx rot = rot_at(-ET_TD);
+            for (int t = ET_TD; t >= 1; --t) {
+                kc_ba_step(sk, cf, cmul(kc_dot8(a.t.ringc + (int64_t)(10 * t - 1) * 8, sac), rot));
+                rot = cmul(rot, rstep);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { st.z[k].x -= sk.z[k].x; st.z[k].y -= sk.z[k].y; }
+        }
+        // causal response to the state difference and the stage-1 correction over the K_EDGE outputs; behind them the forward
+        // state rings out, which the backward pass sees as the start state U2 . state; then the backward pass
+        for (int m = 0; m < K_EDGE; ++m) dy[m] = kc_ba_step(st, cf, dy[m]);
         KcBa sb;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -429,11 +490,10 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_correct(const EdgeCorrArgs 
             for (int j = 0; j < 4; ++j) { sb.z[k].x += a.t.u2[4 * k + j] * st.z[j].x; sb.z[k].y += a.t.u2[4 * k + j] * st.z[j].y; }
         }
         for (int m = K_EDGE - 1; m >= 0; --m) {
-            const dcx v = kc_ba_step(sb, cf, s.buf_l1[m]);
+            const dcx v = kc_ba_step(sb, cf, dy[m]);
             dl[m] = make_float2((float)v.x, (float)v.y);
         }
     }
 }
-#undef KC_PASS
 
 }  // namespace tetra

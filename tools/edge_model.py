@@ -97,6 +97,11 @@ def build_tables():
         _, zf = signal.lfilter(B_BUT, A_BUT, r2[::-1], zi=np.zeros(4))
         U2[:, k] = zf
     t["u2"] = U2
+    # modal form of lfilter's state recursion s' = A s + Bv x (transposed direct form II): A = V diag(p) V^-1, so that
+    # s(L) = V sigma(L), sigma_r(L) = c_r sum_k p_r^k x[L-1-k], c = V^-1 Bv -- scalar recurrences that split into segments
+    A, Bv = s2_weights(0.0, 0)
+    p, V = np.linalg.eig(A)
+    t["bp"] = p; t["bv"] = V; t["bc"] = np.linalg.solve(V, Bv.astype(complex))
     return t
 
 
@@ -224,6 +229,36 @@ def s2_functional_right(xr, n, fo, tab):
     return s_t * np.exp(-1j * 2 * np.pi * fo * ((L - 1) / 240000.0))
 
 
+def s2_functional_right_modal(xr, n, fo, tab, seg_len=34):
+    """the same state through the modal form, evaluated the way the kernel does: per chain (u mod 10) and segment of
+    `seg_len` steps a local pass from zero, then the carries"""
+    k0 = (n - 1) % Q
+    L = (n + Q - 1) // Q
+    lam = tab["bp"] * np.exp(1j * 2 * np.pi * fo / 240000.0)
+    g1 = tab["g1"]
+    n_u = G_HALF + Q * T2 + Q
+    lo = -(G_HALF + Q); lo -= lo % Q
+    n_step = (n_u - lo) // Q
+    S = np.zeros(4, complex)
+    for b in range(Q):
+        C = np.zeros(4, complex)
+        for s0 in range(0, n_step, seg_len):
+            om = np.zeros(4, complex); sl = np.zeros(4, complex); ps = np.zeros(4, complex); pw = lam.copy()
+            for j in range(s0, min(s0 + seg_len, n_step)):
+                u = lo + b + Q * j
+                g = g1[u + G_HALF] if abs(u) <= G_HALF else 0.0
+                d = u + k0
+                xv = xr[d] if 0 <= d < n else 0.0
+                om = lam * om + g
+                sl += xv * om
+                ps += xv * pw
+                pw = pw * lam
+            S += sl + C * ps
+            C = lam ** min(seg_len, n_step - s0) * C + om
+    sigma = tab["bc"] * S * np.exp(-1j * 2 * np.pi * fo * ((L - 1) / 240000.0))
+    return tab["bv"] @ sigma
+
+
 def left_edge(x, n, fo, tab):
     """D[m], m = 0..EDGE-1"""
     s_ac0 = tab["wac"] @ x[:NAC]
@@ -298,6 +333,10 @@ def write_header(tab, path):
         arr(fh, "ET_RING", tab["ring"])             # [NRING][8]     backward-pass output at offset p into the ringing of unit state k
         arr(fh, "ET_U", tab["u"])                   # [8][8]         backward-pass state after the whole ringing of unit state k
         arr(fh, "ET_U2", tab["u2"])                 # [4][4]         the same for the Butterworth stage (lfilter zi layout)
+        cx = lambda a: np.stack([np.asarray(a).real, np.asarray(a).imag], axis=-1)
+        arr(fh, "ET_BP", cx(tab["bp"]))             # [4][2]         poles of the Butterworth stage (re, im)
+        arr(fh, "ET_BC", cx(tab["bc"]))             # [4][2]         its input vector in modal coordinates
+        arr(fh, "ET_BV", cx(tab["bv"]))             # [4][4][2]      modal coordinates -> lfilter state
 
 
 if __name__ == "__main__":
