@@ -69,6 +69,7 @@ struct tetra_ctx {
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
     DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
+    DevBuf flags;                      // [2][C] int32: work items done per carrier, carriers finalized beside the fused kernel
     EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
@@ -133,12 +134,12 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
     // block-end correction tables -> one device buffer
     {
-        constexpr int NT = 10;
-        const double* src[NT] = {ET_G1, ET_WC, ET_WAC, ET_RINGC, ET_RING, ET_U, ET_U2, ET_BP, ET_BC, ET_BV};
+        constexpr int NT = 11;
+        const double* src[NT] = {ET_G1, ET_WC, ET_WAC, ET_RINGC, ET_RING, ET_U, ET_U2, ET_W0, ET_BP, ET_BC, ET_BV};
         const size_t cnt[NT] = {sizeof ET_G1 / sizeof(double), sizeof ET_WC / sizeof(double), sizeof ET_WAC / sizeof(double),
                                 sizeof ET_RINGC / sizeof(double), sizeof ET_RING / sizeof(double), sizeof ET_U / sizeof(double),
-                                sizeof ET_U2 / sizeof(double), sizeof ET_BP / sizeof(double), sizeof ET_BC / sizeof(double),
-                                sizeof ET_BV / sizeof(double)};
+                                sizeof ET_U2 / sizeof(double), sizeof ET_W0 / sizeof(double), sizeof ET_BP / sizeof(double),
+                                sizeof ET_BC / sizeof(double), sizeof ET_BV / sizeof(double)};
         static_assert(sizeof ET_G1 == sizeof(double) * (2 * ET_G + 1) && sizeof ET_WC == sizeof(double) * 8 * ET_NC &&
                       sizeof ET_WAC == sizeof(double) * 8 * ET_NAC && sizeof ET_RINGC == sizeof(double) * 8 * ET_NRING &&
                       sizeof ET_RING == sizeof(double) * 8 * ET_NRING && sizeof ET_U == sizeof(double) * 64, "edge tables changed shape");
@@ -152,10 +153,15 @@ int upload_tables(tetra_ctx* ctx) {
             CK(cudaMemcpy((double*)ctx->etab.p + off, src[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice));
             off += (cnt[k] + 3) & ~(size_t)3;
         }
-        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9]};
+        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9], dev[10]};
     }
     ctx->tables_uploaded = true;
     return 0;
+}
+
+int edge_serial_mode() {
+    static const int v = getenv("TETRA_EDGE_SERIAL") ? atoi(getenv("TETRA_EDGE_SERIAL")) : 0;
+    return v;
 }
 
 // block-end corrections of the fused path (k_edge_states + k_edge_recursions) for C carriers -> ctx->ecorr
@@ -397,7 +403,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
-                      &ctx->etab, &ctx->ecorr, &ctx->estate};
+                      &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->flags};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -675,6 +681,12 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     fa.dibits = k_dib; fa.cap = cap; fa.n_dibits = k_nd; fa.symbols = k_sym; fa.best_phase = k_ph;
     fa.phase_scratch = (int32_t*)ctx->phase.p;
 
+    const bool fused_match = ts_match && cap > 0 && cap <= FIN_DIB_SMEM;
+    fa.match = fused_match ? k_match : nullptr;
+    const bool fused_sync = sync_pos && cap <= FIN_DIB_SMEM;
+    fa.sync_pos = fused_sync ? k_spos : nullptr; fa.max_pos = max_pos; fa.n_sync = k_nsync;
+    fa.n_carriers = C;
+
     if (use_fast) {
         // segments: enough CTAs to fill the machine when there are few carriers
         // Work items = (carrier, segment), streamed back to back by min(SMs, items) persistent CTAs: the launch takes
@@ -709,6 +721,15 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
         ka.zero_ext = edge_corr ? 1 : 0;
+        // finalize beside the fused kernel (TETRA_FIN_OVERLAP=0 switches it off): per-carrier completion counters
+        static const int fin_overlap_env = getenv("TETRA_FIN_OVERLAP") ? atoi(getenv("TETRA_FIN_OVERLAP")) : 1;
+        const bool fin_overlap = edge_corr && fin_overlap_env != 0 && !edge_serial_mode();
+        ka.done = nullptr;
+        if (fin_overlap) {
+            CK(ctx->flags.ensure(sizeof(int32_t) * 2 * C));
+            CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int32_t) * 2 * C, st));
+            ka.done = (int32_t*)ctx->flags.p;
+        }
         // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {
@@ -719,7 +740,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         }
         // TETRA_EDGE_SERIAL=1 (measurement only): the block-end corrections run ahead of the fused kernel on the same stream,
         // so that the timeline's second entry is their stand-alone duration
-        static const int edge_serial = getenv("TETRA_EDGE_SERIAL") ? atoi(getenv("TETRA_EDGE_SERIAL")) : 0;
+        const int edge_serial = edge_serial_mode();
         if (edge_corr && edge_serial) {
             if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], st));
             rc = launch_edge_correct(ctx, st, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
@@ -761,23 +782,25 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
         if (rc) return rc;
         if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
-        CK(cudaEventRecord(ctx->ev_join, ctx->side));
-        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
-        if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
         fa.edge_corr = edge_corr ? (const float2*)ctx->ecorr.p : nullptr;
+        if (fin_overlap) {
+            // behind the corrections on the side stream: finalize every carrier as soon as the fused kernel has published it
+            fa.done = ka.done; fa.done_target = n_seg; fa.fin_state = ka.done + C;
+            k_finalize_overlap<<<std::min(C, sms), FIN_THREADS, 0, ctx->side>>>(fa);
+            ctx->launches++;
+            CK(cudaGetLastError());
+        }
+        CK(cudaEventRecord(ctx->ev_join, ctx->side));
+        CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
     } else {
         rc = launch_exact(ctx, st, ea, full_jobs, 0);
         if (rc) return rc;
         fa.partial = nullptr; fa.n_seg = 0; fa.bulk_lo = 0; fa.bulk_hi = 0;
     }
     if (ctx->timing && use_fast && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[2], st));
-    const bool fused_match = ts_match && cap > 0 && cap <= FIN_DIB_SMEM;
-    fa.match = fused_match ? k_match : nullptr;
-    const bool fused_sync = sync_pos && cap <= FIN_DIB_SMEM;
-    fa.sync_pos = fused_sync ? k_spos : nullptr; fa.max_pos = max_pos; fa.n_sync = k_nsync;
-    if (sync_pos && !fused_sync) return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
     k_finalize<<<C, FIN_THREADS, 0, st>>>(fa);
     ctx->launches++;
     CK(cudaGetLastError());

@@ -35,6 +35,7 @@ struct EdgeTables {          // device copies of edge_tables_generated.h
     const double* ring;      // [NRING][8]  backward-pass output at offset p into the ringing of unit state k
     const double* u;         // [8][8]      backward-pass state after the whole ringing of unit state k
     const double* u2;        // [4][4]      the same for the Butterworth stage (lfilter zi layout)
+    const double* w0;        // [4][NW0]    freq_offset = 0: weights of the Butterworth state at the right end, W0[k][u + 9]
     const double* bp;        // [4][2]      poles of the Butterworth stage
     const double* bc;        // [4][2]      its input vector in modal coordinates
     const double* bv;        // [4][4][2]   modal coordinates -> lfilter state
@@ -213,7 +214,27 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
         kc_warp_sum(acc, out + 16 + ET_NPTS + 8 * h, lane);
     }
     // ---- causal Butterworth state of the zero-extended stream at the right end ----
-    // In modal coordinates (A = V diag(p) V^-1, lambda_r = p_r e^{jW}):
+    // s(L) = e^{-jW(L-1)} sum_d x[n-1-d] Wv(d - k0),  Wv(u) = Bv g1[u] + e^{jW} A Wv(u - 10)  (tools/edge_model.py).
+    // Without a freq_offset the weights are real and fixed: one more table pass.
+    if (fo == 0.0) {
+        dcx a4[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        const double* __restrict__ w0 = a.t.w0 + 9 - k0;      // w0[k * NW0 + d] = W0[k][d - k0 + 9]
+        const int cnt = ET_NW0 - 9 + k0;
+        for (int d0 = lane; d0 < cnt; d0 += 32 * UN) {
+            dcx v[UN];
+#pragma unroll
+            for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < cnt ? xr(d0 + 32 * q) : dcx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < UN; ++q) {
+                const int d = min(d0 + 32 * q, cnt - 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const double w = w0[k * ET_NW0 + d]; a4[k].x += w * v[q].x; a4[k].y += w * v[q].y; }
+            }
+        }
+        kc_warp_sum(a4, out + 16 + 2 * ET_NPTS, lane);
+        return;
+    }
+    // With one: in modal coordinates (A = V diag(p) V^-1, lambda_r = p_r e^{jW}):
     //   s(L) = V sigma,  sigma_r = c_r e^{-jW(L-1)} sum_d x[n-1-d] Om_r(d - k0),  Om_r(u) = g1[u] + lambda_r Om_r(u - 10).
     // Ten chains (u mod 10) of NSTEP steps, each cut into three segments: a lane runs its segment from zero, then the
     // segments' carries are chained with shuffles.
@@ -365,9 +386,11 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.z[k] = dcx{0.0, 0.0};
         {
+#pragma unroll 8
+            for (int t = 0; t < ET_TD; ++t) ydl[t] = kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, ds);    // independent: loads in flight
             dcx rot = rot_at(L - ET_TD);
             for (int t = ET_TD - 1; t >= 0; --t) {
-                const dcx d1 = cmul(kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, ds), rot);
+                const dcx d1 = cmul(ydl[t], rot);
                 if (t < ET_NPTS) d1s[t] = d1;
                 ydl[t] = kc_ba_step(st, cf, d1);
                 rot = cmul(rot, rstep);
@@ -399,10 +422,12 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.z[k] = s2k[k];
         {
+#pragma unroll 8
+            for (int t = 0; t < ET_TD; ++t) y2k[t] = kc_dot8(a.t.ring + (int64_t)(9 - k0 + 10 * t) * 8, scv);
             dcx rot = rot_at(L);
             for (int t = 0; t < ET_T2; ++t) {
                 dcx in{0.0, 0.0};
-                if (t < ET_TD) in = cmul(kc_dot8(a.t.ring + (int64_t)(9 - k0 + 10 * t) * 8, scv), rot);
+                if (t < ET_TD) in = cmul(y2k[t], rot);
                 y2k[t] = kc_ba_step(st, cf, in);
                 rot = cmul(rot, rstep);
             }
@@ -443,9 +468,11 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
         // stage-1 correction d1[m] at output m (backward pass over the forward ringing of dsc) after the NCO
         dcx dy[K_EDGE];
         {
+#pragma unroll 8
+            for (int m = 0; m < ET_TD; ++m) dy[m] = kc_dot8(a.t.ring + (int64_t)(10 * m) * 8, dsc);
             dcx rot{1.0, 0.0};
             for (int m = 0; m < ET_TD; ++m) {
-                dy[m] = cmul(kc_dot8(a.t.ring + (int64_t)(10 * m) * 8, dsc), rot);
+                dy[m] = cmul(dy[m], rot);
                 rot = cmul(rot, rstep);
             }
             for (int m = ET_TD; m < K_EDGE; ++m) dy[m] = dcx{0.0, 0.0};
@@ -471,9 +498,12 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
             KcBa sk;
 #pragma unroll
             for (int k = 0; k < 4; ++k) sk.z[k] = dcx{0.0, 0.0};
+            dcx zk[ET_TD];
+#pragma unroll 8
+            for (int t = 1; t <= ET_TD; ++t) zk[t - 1] = kc_dot8(a.t.ringc + (int64_t)(10 * t - 1) * 8, sac);
             dcx rot = rot_at(-ET_TD);
             for (int t = ET_TD; t >= 1; --t) {
-                kc_ba_step(sk, cf, cmul(kc_dot8(a.t.ringc + (int64_t)(10 * t - 1) * 8, sac), rot));
+                kc_ba_step(sk, cf, cmul(zk[t - 1], rot));
                 rot = cmul(rot, rstep);
             }
 #pragma unroll

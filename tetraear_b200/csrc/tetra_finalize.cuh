@@ -24,6 +24,11 @@ struct FinArgs {
     const double* partial;   // [C][n_seg][16] power sums of the bulk kernel (or null)
     int32_t n_seg;
     int32_t bulk_lo, bulk_hi;  // y range already covered by `partial` (empty if bulk_lo >= bulk_hi)
+    // overlap with the fused kernel (k_finalize_overlap): a carrier is ready when done[car] == done_target
+    const int32_t* done;     // [C] counters the fused kernel increments, or null
+    int32_t done_target;     // work items per carrier (n_seg)
+    int32_t* fin_state;      // [C] or null: 1 once a carrier has been finalized (the in-order launch skips those)
+    int32_t n_carriers;
     const float2* edge_corr; // [C][2][K_EDGE] or null: block-end corrections (tetra_edgecorr.cuh) to add to y[m], m < K_EDGE,
                              // and y[L-1-t], t < K_EDGE, wherever they are read
     uint8_t* dibits;         // [C][cap]
@@ -201,22 +206,32 @@ __device__ __forceinline__ void pack_dibits(const uint8_t* s_dib, int nd, uint32
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
-    __shared__ double red[FIN_THREADS];
-    __shared__ int s_best;
-    __shared__ __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
-    __shared__ uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
-    __shared__ SyncScratch s_sync;
-    const int car = blockIdx.x, tid = threadIdx.x;
-    const float2* __restrict__ y = a.y + (int64_t)car * a.y_pitch;
+struct FinSmem {
+    double red[FIN_THREADS];
+    int s_best, s_ready;
+    __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
+    uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
+    SyncScratch s_sync;
+};
+
+// everything k_finalize does for one carrier, by the FIN_THREADS threads of a CTA. y, partial and the corrections are read
+// with L2 loads (ld.global.cg): under k_finalize_overlap they were written by a kernel that is still running
+__device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car, FinSmem& sm) {
+    double* red = sm.red;
+    int& s_best = sm.s_best;
+    uint8_t* s_dib = sm.s_dib;
+    uint32_t* s_bits = sm.s_bits;
+    SyncScratch& s_sync = sm.s_sync;
+    const int tid = threadIdx.x;
+    const float2* y = a.y + (int64_t)car * a.y_pitch;
     const int L = a.L, sps = a.sps, step = a.step;
     const int nph = (sps + step - 1) / step;            // phases tried: 0, step, 2 step, ... (<= FIN_MAXPH)
-    const float2* __restrict__ ec = a.edge_corr ? a.edge_corr + (int64_t)car * 2 * K_EDGE : nullptr;
+    const float2* ec = a.edge_corr ? a.edge_corr + (int64_t)car * 2 * K_EDGE : nullptr;
     // sample n of the filtered stream: the fused kernel's output plus, next to the block ends, the correction
     auto y_at = [&](int n, float2 v) {
         if (ec) {
-            if (n < K_EDGE) { const float2 d = ec[n]; v.x += d.x; v.y += d.y; }
-            if (n >= L - K_EDGE) { const float2 d = ec[K_EDGE + (L - 1 - n)]; v.x += d.x; v.y += d.y; }
+            if (n < K_EDGE) { const float2 d = __ldcg(ec + n); v.x += d.x; v.y += d.y; }
+            if (n >= L - K_EDGE) { const float2 d = __ldcg(ec + K_EDGE + (L - 1 - n)); v.x += d.x; v.y += d.y; }
         }
         return v;
     };
@@ -236,11 +251,11 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
             const int k_lo_end = has_bulk ? min(cnt, max(0, (a.bulk_lo - ph + sps - 1) / sps)) : cnt;
             const int k_hi_beg = has_bulk ? max(k_lo_end, (a.bulk_hi - ph + sps - 1) / sps) : cnt;
             for (int k = g; k < k_lo_end; k += G) {
-                const float2 v = y_at(ph + sps * k, y[y_index(ph + sps * k, sps, a.y_rows)]);
+                const float2 v = y_at(ph + sps * k, __ldcg(y + y_index(ph + sps * k, sps, a.y_rows)));
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
             for (int k = k_hi_beg + g; k < cnt; k += G) {
-                const float2 v = y_at(ph + sps * k, y[y_index(ph + sps * k, sps, a.y_rows)]);
+                const float2 v = y_at(ph + sps * k, __ldcg(y + y_index(ph + sps * k, sps, a.y_rows)));
                 acc += (double)v.x * (double)v.x + (double)v.y * (double)v.y;
             }
         }
@@ -255,7 +270,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
                 double sum = 0.0;
                 for (int gg = 0; gg < G; ++gg) sum += red[gg * nph + pp];
                 if (a.partial && has_bulk)
-                    for (int sg = 0; sg < a.n_seg; ++sg) sum += a.partial[((int64_t)car * a.n_seg + sg) * 16 + ph];
+                    for (int sg = 0; sg < a.n_seg; ++sg) sum += __ldcg(a.partial + ((int64_t)car * a.n_seg + sg) * 16 + ph);
                 const double mean = sum / (double)cnt;
                 if (mean > best_pow) { best_pow = mean; best = ph; }
             }
@@ -284,8 +299,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
             const int k = min(k0 + j * FIN_THREADS, n_sym - 1), kp = max(k - 1, 0);
-            s1[j] = y_at(best + stride * k, ys[ks * k]);
-            s0[j] = y_at(best + stride * kp, ys[ks * kp]);
+            s1[j] = y_at(best + stride * k, __ldcg(ys + ks * k));
+            s0[j] = y_at(best + stride * kp, __ldcg(ys + ks * kp));
         }
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
@@ -329,6 +344,45 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     if (a.sync_pos) {
         const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
         if (tid == 0) a.n_sync[car] = n;
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
+    __shared__ FinSmem sm;
+    const int car = blockIdx.x;
+    if (a.fin_state && a.fin_state[car]) return;        // already done beside the fused kernel
+    finalize_carrier(a, car, sm);
+}
+
+// The same, beside the fused kernel: a persistent grid walks the carriers in the order the fused kernel finishes them
+// (CTA j takes carriers j, j + grid, ...) and starts on a carrier as soon as all its work items are published. The wait is
+// bounded: a carrier that does not become ready in time is left to the in-order k_finalize launch that always follows
+// (so nothing here can stall the fused kernel for good, whatever the block scheduler does).
+constexpr long long FIN_WAIT_CYCLES = 100000000LL;       // ~50 ms
+__global__ void __launch_bounds__(FIN_THREADS) k_finalize_overlap(const FinArgs a) {
+    __shared__ FinSmem sm;
+    for (int car = blockIdx.x; car < a.n_carriers; car += gridDim.x) {
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            int ready = 0;
+            for (;;) {
+                int v;
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.done + car) : "memory");
+                if (v >= a.done_target) { ready = 1; break; }
+                if (clock64() - t0 > FIN_WAIT_CYCLES) break;
+                __nanosleep(1000);
+            }
+            sm.s_ready = ready;
+        }
+        __syncthreads();
+        const int ready = sm.s_ready;
+        if (ready) {
+            finalize_carrier(a, car, sm);
+            __syncthreads();                             // the shared buffers are reused by the next carrier
+            if (threadIdx.x == 0) a.fin_state[car] = 1;
+        } else {
+            __syncthreads();
+        }
     }
 }
 

@@ -165,6 +165,8 @@ struct K1Args {
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x (x8) base/pitch allow 16-byte bulk copies
+    int32_t* done;          // [C] or null: incremented (release) once per finished work item of a carrier, after its y and partial
+                            //               stores: lets the finalize kernel start on a carrier while this kernel is still running
     int32_t zero_ext;       // 1: the block is extended by zeros and y is written over the whole block (the block-end corrections
                             //    of tetra_edgecorr.cuh are added by the finalize kernel); 0: K1_EDGE outputs at each end are left
                             //    to the exact edge kernels and what lies beyond the block is arbitrary
@@ -657,6 +659,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 a.partial[((int64_t)blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
             }
             asm volatile("bar.sync 2, 64;" ::: "memory");
+            // every y store of this item (all 64 threads, ordered by the barrier) and its partial sums are published
+            if (a.done && ld == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(a.done + sl.car) : "memory");
 #pragma unroll
             for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
         };

@@ -99,7 +99,16 @@ def build_tables():
     t["u2"] = U2
     # modal form of lfilter's state recursion s' = A s + Bv x (transposed direct form II): A = V diag(p) V^-1, so that
     # s(L) = V sigma(L), sigma_r(L) = c_r sum_k p_r^k x[L-1-k], c = V^-1 Bv -- scalar recurrences that split into segments
+    # W0[k][u + 9], u = -9 .. NU-1: for freq_offset = 0 the weights of s2_functional_right are real and fixed
     A, Bv = s2_weights(0.0, 0)
+    n_u = G_HALF + Q * T2 + Q
+    lo = -(G_HALF + Q); lo -= lo % Q
+    Wf = np.zeros((n_u - lo, 4))
+    for u in range(lo, n_u):
+        prev = Wf[u - lo - Q] if u - Q >= lo else np.zeros(4)
+        gv = t["g1"][u + G_HALF] if abs(u) <= G_HALF else 0.0
+        Wf[u - lo] = A @ prev + Bv * gv
+    t["w0"] = Wf[-9 - lo:].T.copy()
     p, V = np.linalg.eig(A)
     t["bp"] = p; t["bv"] = V; t["bc"] = np.linalg.solve(V, Bv.astype(complex))
     return t
@@ -333,6 +342,8 @@ def write_header(tab, path):
         arr(fh, "ET_RING", tab["ring"])             # [NRING][8]     backward-pass output at offset p into the ringing of unit state k
         arr(fh, "ET_U", tab["u"])                   # [8][8]         backward-pass state after the whole ringing of unit state k
         arr(fh, "ET_U2", tab["u2"])                 # [4][4]         the same for the Butterworth stage (lfilter zi layout)
+        fh.write("#define ET_NW0 %d\n" % tab["w0"].shape[1])
+        arr(fh, "ET_W0", tab["w0"])                 # [4][NW0]       freq_offset = 0: weights of the Butterworth state at the right end, W0[k][u + 9]
         cx = lambda a: np.stack([np.asarray(a).real, np.asarray(a).imag], axis=-1)
         arr(fh, "ET_BP", cx(tab["bp"]))             # [4][2]         poles of the Butterworth stage (re, im)
         arr(fh, "ET_BC", cx(tab["bc"]))             # [4][2]         its input vector in modal coordinates
