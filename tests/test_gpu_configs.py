@@ -107,7 +107,11 @@ def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
         z = xs[c] / np.abs(xs[c]).max() * 0.9                  # fill most of the ADC range
         raw[c, :, 0] = np.clip(np.round((z.real + 1.0) * 127.5), 0, 255)
         raw[c, :, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
+    before = sp.launch_count()
     res = sp.process_batch_u8(raw, [0.0, 777.0], want_symbols=True, want_sync=True)
+    # bytes + AFC offset is the live path's combination (ui/modern.py:2021-2022 on signal/capture.py:143-158 samples): it stays
+    # on the fused kernel (bytes read as they are, NCO + equaliser inside), no expansion to complex64
+    assert sp.launch_count() - before == 4
     for c, fo in enumerate((0.0, 777.0)):
         x128 = (raw[c, :, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (raw[c, :, 1].astype(np.float64) / 127.5 - 1.0)
         r = ref_dsp.process(x128, fo, 2.4e6)
@@ -122,7 +126,7 @@ def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
 @pytest.mark.parametrize("n", [1 << 17, (1 << 17) + 1235, 16384 + 8])
 def test_u8_ingest_fused_path(gpu_processor, n):
     """freq_offset 0 at 2.4 MS/s: the fused kernel reads the bytes itself (bulk copies when the rows are 16-byte
-    aligned, plain loads otherwise) and only the block-end windows are expanded for the exact edge kernels."""
+    aligned, plain loads otherwise); the block-end correction kernels read the bytes too."""
     sp = gpu_processor
     sp.sample_rate = 2.4e6
     n_car = 3
@@ -134,7 +138,7 @@ def test_u8_ingest_fused_path(gpu_processor, n):
         raw[c, :, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
     before = sp.launch_count()
     res = sp.process_batch_u8(raw, None, want_symbols=True, want_sync=True)
-    assert sp.launch_count() - before == 4                     # fused kernel, block-end states + recursions, finalize: no expansion pass
+    assert sp.launch_count() - before == 4                     # fused kernel, block-end states + recursions, finalize: no expansion, no window pass
     for c in range(n_car):
         x128 = (raw[c, :, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (raw[c, :, 1].astype(np.float64) / 127.5 - 1.0)
         r = ref_dsp.process(x128, 0.0, 2.4e6)
@@ -144,6 +148,64 @@ def test_u8_ingest_fused_path(gpu_processor, n):
         err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
         assert err <= SOFT_TOL, err
         assert [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]] == ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(r["dibits"]))
+
+
+def test_u8_with_offsets_many_carriers_per_cta(gpu_processor):
+    """Bytes + per-carrier freq_offsets with more carriers than SMs (slot changes of byte ring, phasors and equaliser taps)."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n, n_car = 16384 + 640, 300
+    base = []
+    for k in range(4):
+        x = synth.carrier_iq(n, 540 + k, snr_db=24.0, alphabet="centred" if k & 1 else "pi4")
+        z = x / np.abs(x).max() * 0.9
+        base.append(np.stack([np.clip(np.round((z.real + 1.0) * 127.5), 0, 255), np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)], axis=-1).astype(np.uint8))
+    raw = np.stack([base[c % 4] for c in range(n_car)])
+    fos = np.random.default_rng(8).uniform(-12000.0, 12000.0, size=n_car)
+    fos[::7] = 0.0
+    res = sp.process_batch_u8(raw, fos, want_symbols=True)
+    for c in (0, 1, 2, 7, 147, 148, 149, 150, 296, 299):
+        b = base[c % 4]
+        x128 = (b[:, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (b[:, 1].astype(np.float64) / 127.5 - 1.0)
+        r = ref_dsp.process(x128, float(fos[c]), 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], c
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), c
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, err)
+
+
+def test_u8_device_rows_with_padding_on_the_expanding_path(gpu_processor):
+    """Device-resident byte rows of an odd length padded to a multiple of 8 samples, at a rate the fused kernel does not
+    take: the expansion to complex64 writes rows that are only 8-byte aligned (plain stores, not 16-byte ones)."""
+    import ctypes as C
+    import torch
+    sp = gpu_processor
+    n, pitch, n_car, fs = 20003, 20008, 3, 2.048e6
+    sp.sample_rate = fs
+    sp._sync_rate()
+    host = np.zeros((n_car, pitch, 2), dtype=np.uint8)
+    for c in range(n_car):
+        x = synth.carrier_iq(n, 560 + c, snr_db=25.0, alphabet="centred", sps=112)
+        z = x / np.abs(x).max() * 0.9
+        host[c, :n, 0] = np.clip(np.round((z.real + 1.0) * 127.5), 0, 255)
+        host[c, :n, 1] = np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)
+    dev = torch.from_numpy(host).cuda()
+    cap = sp.dibit_capacity(n)
+    dib = np.zeros((n_car, cap), dtype=np.uint8)
+    nd = np.zeros(n_car, dtype=np.int32)
+    ph = np.zeros(n_car, dtype=np.int32)
+    sym = np.zeros((n_car, cap + 1), dtype=np.complex64)
+    fos = np.array([0.0, 250.0, -1000.0])
+    sp._check(sp._lib.tetra_process_batch_u8(sp._ctx, dev.data_ptr(), n_car, n, pitch, fos.ctypes.data, dib.ctypes.data, cap,
+                                             nd.ctypes.data, sym.ctypes.data, ph.ctypes.data, None, None, 0, None), "process_batch_u8")
+    for c in range(n_car):
+        x128 = (host[c, :n, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (host[c, :n, 1].astype(np.float64) / 127.5 - 1.0)
+        r = ref_dsp.process(x128, float(fos[c]), fs)
+        assert int(nd[c]) == len(r["dibits"]) and int(ph[c]) == r["best_phase"], c
+        assert np.array_equal(dib[c, : nd[c]], r["dibits"]), c
+        assert np.abs(sym[c, : nd[c] + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max() <= SOFT_TOL
+    sp.sample_rate = 2.4e6
 
 
 def test_u8_ingest_fused_path_many_carriers_per_cta(gpu_processor):

@@ -69,7 +69,6 @@ struct tetra_ctx {
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
     DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
-    DevBuf flags;                      // [2][C] int32: work items done per carrier, carriers finalized beside the fused kernel
     EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
@@ -132,6 +131,7 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFoU8)));
     // block-end correction tables -> one device buffer
     {
         constexpr int NT = 11;
@@ -403,7 +403,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
-                      &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->flags};
+                      &ctx->etab, &ctx->ecorr, &ctx->estate};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -580,7 +580,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     // The fused path covers freq_offset = 0 (MODE 0) and, with the NCO + equaliser of MODE 1, |freq_offset| <= 12.5 kHz
     // (MODE 1: the GUI's AFC range, ui/modern.py:1949-1967); anything else runs the exact recursion over the block.
     const bool use_fast = fast_ok && (!any_fo || fo_in_range);
-    const bool u8_fused = u8 && use_fast && !any_fo && edge_mode != 2;
+    const bool u8_fused = u8 && use_fast && edge_mode != 2;       // with a freq_offset too (MODE 4): the GUI's live combination
     if (u8 && !u8_fused) {
         CK(ctx->wide.ensure((size_t)C * N * sizeof(float2)));
         if (u8_pitch == N) {
@@ -685,7 +685,6 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     fa.match = fused_match ? k_match : nullptr;
     const bool fused_sync = sync_pos && cap <= FIN_DIB_SMEM;
     fa.sync_pos = fused_sync ? k_spos : nullptr; fa.max_pos = max_pos; fa.n_sync = k_nsync;
-    fa.n_carriers = C;
 
     if (use_fast) {
         // segments: enough CTAs to fill the machine when there are few carriers
@@ -721,15 +720,6 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
         ka.zero_ext = edge_corr ? 1 : 0;
-        // finalize beside the fused kernel (TETRA_FIN_OVERLAP=0 switches it off): per-carrier completion counters
-        static const int fin_overlap_env = getenv("TETRA_FIN_OVERLAP") ? atoi(getenv("TETRA_FIN_OVERLAP")) : 1;
-        const bool fin_overlap = edge_corr && fin_overlap_env != 0 && !edge_serial_mode();
-        ka.done = nullptr;
-        if (fin_overlap) {
-            CK(ctx->flags.ensure(sizeof(int32_t) * 2 * C));
-            CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(int32_t) * 2 * C, st));
-            ka.done = (int32_t*)ctx->flags.p;
-        }
         // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {
@@ -762,7 +752,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ctx->ev_used++;
             CK(cudaEventRecord(t0, st));
         }
-        if (u8_fused) k1_channelize_demod<3><<<k1_grid, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
+        if (u8_fused && any_fo) k1_channelize_demod<4><<<k1_grid, K1_THREADS, sizeof(K1SmemFoU8), st>>>(ka);
+        else if (u8_fused) k1_channelize_demod<3><<<k1_grid, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
         else if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
@@ -785,13 +776,6 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
         fa.edge_corr = edge_corr ? (const float2*)ctx->ecorr.p : nullptr;
-        if (fin_overlap) {
-            // behind the corrections on the side stream: finalize every carrier as soon as the fused kernel has published it
-            fa.done = ka.done; fa.done_target = n_seg; fa.fin_state = ka.done + C;
-            k_finalize_overlap<<<std::min(C, sms), FIN_THREADS, 0, ctx->side>>>(fa);
-            ctx->launches++;
-            CK(cudaGetLastError());
-        }
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));

@@ -368,10 +368,12 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
             kc_sos_from(ss, scv);
             const dcx x_last = xr(0);
             double2 yf[EX_PAD1];
-            for (int j = 0; j < EX_PAD1; ++j) {
+#pragma unroll
+            for (int j = 0; j < EX_PAD1; ++j) {                   // all loads first
                 const dcx v = xr(1 + j);
-                yf[j] = sos_step(ss, cf, make_double2(2.0 * x_last.x - v.x, 2.0 * x_last.y - v.y));
+                yf[j] = make_double2(2.0 * x_last.x - v.x, 2.0 * x_last.y - v.y);
             }
+            for (int j = 0; j < EX_PAD1; ++j) yf[j] = sos_step(ss, cf, yf[j]);
             sos_init(ss, cf, yf[EX_PAD1 - 1]);
             for (int j = EX_PAD1 - 1; j >= 0; --j) sos_step(ss, cf, yf[j]);
 #pragma unroll
@@ -389,6 +391,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll 8
             for (int t = 0; t < ET_TD; ++t) ydl[t] = kc_dot8(a.t.ringc + (int64_t)(k0 + 10 * t) * 8, ds);    // independent: loads in flight
             dcx rot = rot_at(L - ET_TD);
+#pragma unroll 4
             for (int t = ET_TD - 1; t >= 0; --t) {
                 const dcx d1 = cmul(ydl[t], rot);
                 if (t < ET_NPTS) d1s[t] = d1;
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll 8
             for (int t = 0; t < ET_TD; ++t) y2k[t] = kc_dot8(a.t.ring + (int64_t)(9 - k0 + 10 * t) * 8, scv);
             dcx rot = rot_at(L);
+#pragma unroll 4
             for (int t = 0; t < ET_T2; ++t) {
                 dcx in{0.0, 0.0};
                 if (t < ET_TD) in = cmul(y2k[t], rot);
@@ -435,10 +439,12 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
         // backward pass over the difference of the two forward outputs, from zi * F (filtfilt's backward start)
 #pragma unroll
         for (int k = 0; k < 4; ++k) st.z[k] = dcx{cf.zi2[k] * F.x, cf.zi2[k] * F.y};
+#pragma unroll 4
         for (int t = ET_T2 - 1; t >= 0; --t) {
             const dcx e = t < EX_PAD2 ? y2e[t] : F;
             kc_ba_step(st, cf, dcx{e.x - y2k[t].x, e.y - y2k[t].y});
         }
+#pragma unroll 4
         for (int t = 0; t < K_EDGE; ++t) {
             const dcx v = kc_ba_step(st, cf, t < ET_TD ? ydl[t] : dcx{0.0, 0.0});
             dr[t] = make_float2((float)v.x, (float)v.y);
@@ -453,15 +459,15 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
         dcx dsc[8];
         {
             const dcx x0 = xl(0);
-            SosState ss;
-            {
-                const dcx v = xl(EX_PAD1);
-                sos_init(ss, cf, make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y));
-            }
-            for (int j = 0; j < EX_PAD1; ++j) {
+            double2 e[EX_PAD1];
+#pragma unroll
+            for (int j = 0; j < EX_PAD1; ++j) {                   // all loads first
                 const dcx v = xl(EX_PAD1 - j);
-                sos_step(ss, cf, make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y));
+                e[j] = make_double2(2.0 * x0.x - v.x, 2.0 * x0.y - v.y);
             }
+            SosState ss;
+            sos_init(ss, cf, e[0]);
+            for (int j = 0; j < EX_PAD1; ++j) sos_step(ss, cf, e[j]);
 #pragma unroll
             for (int k = 0; k < 8; ++k) dsc[k] = dcx{ss.z[k >> 1][k & 1][0], ss.z[k >> 1][k & 1][1]};
         }
@@ -502,6 +508,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll 8
             for (int t = 1; t <= ET_TD; ++t) zk[t - 1] = kc_dot8(a.t.ringc + (int64_t)(10 * t - 1) * 8, sac);
             dcx rot = rot_at(-ET_TD);
+#pragma unroll 4
             for (int t = ET_TD; t >= 1; --t) {
                 kc_ba_step(sk, cf, cmul(zk[t - 1], rot));
                 rot = cmul(rot, rstep);
@@ -511,6 +518,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
         }
         // causal response to the state difference and the stage-1 correction over the K_EDGE outputs; behind them the forward
         // state rings out, which the backward pass sees as the start state U2 . state; then the backward pass
+#pragma unroll 4
         for (int m = 0; m < K_EDGE; ++m) dy[m] = kc_ba_step(st, cf, dy[m]);
         KcBa sb;
 #pragma unroll
@@ -519,6 +527,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll
             for (int j = 0; j < 4; ++j) { sb.z[k].x += a.t.u2[4 * k + j] * st.z[j].x; sb.z[k].y += a.t.u2[4 * k + j] * st.z[j].y; }
         }
+#pragma unroll 4
         for (int m = K_EDGE - 1; m >= 0; --m) {
             const dcx v = kc_ba_step(sb, cf, dy[m]);
             dl[m] = make_float2((float)v.x, (float)v.y);

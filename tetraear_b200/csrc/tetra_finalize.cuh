@@ -24,11 +24,6 @@ struct FinArgs {
     const double* partial;   // [C][n_seg][16] power sums of the bulk kernel (or null)
     int32_t n_seg;
     int32_t bulk_lo, bulk_hi;  // y range already covered by `partial` (empty if bulk_lo >= bulk_hi)
-    // overlap with the fused kernel (k_finalize_overlap): a carrier is ready when done[car] == done_target
-    const int32_t* done;     // [C] counters the fused kernel increments, or null
-    int32_t done_target;     // work items per carrier (n_seg)
-    int32_t* fin_state;      // [C] or null: 1 once a carrier has been finalized (the in-order launch skips those)
-    int32_t n_carriers;
     const float2* edge_corr; // [C][2][K_EDGE] or null: block-end corrections (tetra_edgecorr.cuh) to add to y[m], m < K_EDGE,
                              // and y[L-1-t], t < K_EDGE, wherever they are read
     uint8_t* dibits;         // [C][cap]
@@ -208,14 +203,14 @@ __device__ __forceinline__ void pack_dibits(const uint8_t* s_dib, int nd, uint32
 
 struct FinSmem {
     double red[FIN_THREADS];
-    int s_best, s_ready;
+    int s_best;
     __align__(16) uint8_t s_dib[FIN_DIB_SMEM];
     uint32_t s_bits[FIN_DIB_SMEM / 16 + 2];
     SyncScratch s_sync;
 };
 
 // everything k_finalize does for one carrier, by the FIN_THREADS threads of a CTA. y, partial and the corrections are read
-// with L2 loads (ld.global.cg): under k_finalize_overlap they were written by a kernel that is still running
+// once: L2 loads (ld.global.cg)
 __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car, FinSmem& sm) {
     double* red = sm.red;
     int& s_best = sm.s_best;
@@ -261,19 +256,26 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
         }
         red[tid] = acc;
         __syncthreads();
-        if (tid == 0) {
-            double best_pow = -1.0;
-            for (int pp = 0; pp < nph; ++pp) {
-                const int ph = pp * step;
-                const int cnt = (L - ph) / sps;
-                if (cnt <= 0) continue;
+        // one thread per phase adds up its partial sums (same order as before), then thread 0 takes the first maximum
+        double mean = -2.0;
+        if (tid < nph) {
+            const int ph = tid * step;
+            const int cnt = (L - ph) / sps;
+            if (cnt > 0) {
                 double sum = 0.0;
-                for (int gg = 0; gg < G; ++gg) sum += red[gg * nph + pp];
+                for (int gg = 0; gg < G; ++gg) sum += red[gg * nph + tid];
                 if (a.partial && has_bulk)
                     for (int sg = 0; sg < a.n_seg; ++sg) sum += __ldcg(a.partial + ((int64_t)car * a.n_seg + sg) * 16 + ph);
-                const double mean = sum / (double)cnt;
-                if (mean > best_pow) { best_pow = mean; best = ph; }
+                mean = sum / (double)cnt;
             }
+        }
+        __syncthreads();
+        if (tid < nph) red[tid] = mean;
+        __syncthreads();
+        if (tid == 0) {
+            double best_pow = -1.0;
+            for (int pp = 0; pp < nph; ++pp)
+                if (red[pp] > best_pow) { best_pow = red[pp]; best = pp * step; }      // phases without a symbol hold -2
             s_best = best;
         }
         __syncthreads();
@@ -349,41 +351,7 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     __shared__ FinSmem sm;
-    const int car = blockIdx.x;
-    if (a.fin_state && a.fin_state[car]) return;        // already done beside the fused kernel
-    finalize_carrier(a, car, sm);
-}
-
-// The same, beside the fused kernel: a persistent grid walks the carriers in the order the fused kernel finishes them
-// (CTA j takes carriers j, j + grid, ...) and starts on a carrier as soon as all its work items are published. The wait is
-// bounded: a carrier that does not become ready in time is left to the in-order k_finalize launch that always follows
-// (so nothing here can stall the fused kernel for good, whatever the block scheduler does).
-constexpr long long FIN_WAIT_CYCLES = 100000000LL;       // ~50 ms
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize_overlap(const FinArgs a) {
-    __shared__ FinSmem sm;
-    for (int car = blockIdx.x; car < a.n_carriers; car += gridDim.x) {
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            int ready = 0;
-            for (;;) {
-                int v;
-                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.done + car) : "memory");
-                if (v >= a.done_target) { ready = 1; break; }
-                if (clock64() - t0 > FIN_WAIT_CYCLES) break;
-                __nanosleep(1000);
-            }
-            sm.s_ready = ready;
-        }
-        __syncthreads();
-        const int ready = sm.s_ready;
-        if (ready) {
-            finalize_carrier(a, car, sm);
-            __syncthreads();                             // the shared buffers are reused by the next carrier
-            if (threadIdx.x == 0) a.fin_state[car] = 1;
-        } else {
-            __syncthreads();
-        }
-    }
+    finalize_carrier(a, blockIdx.x, sm);
 }
 
 // standalone: sync positions from dibit streams (the same device code; used when the streams come from elsewhere)

@@ -140,9 +140,15 @@ struct K1SmemU8 {
     K1Smem base;
     uint64_t rawfull[K1_RAWBUF];
 };
+// uint8 ingest with a freq_offset (MODE 4): both of the above
+struct K1SmemFoU8 {
+    K1SmemFo fo;
+    uint64_t rawfull[K1_RAWBUF];
+};
 static_assert(K1_RAWBUF * K1_RAW_BYTES <= (int)sizeof(float2) * (K1_HDR + K1_TILE), "raw byte ring does not fit the third tile buffer");
 static_assert((sizeof(float2) * (K1_HDR + K1_TILE)) % 16 == 0 && K1_RAW_BYTES % 16 == 0, "bulk copies need 16-byte aligned slots");
-static_assert(sizeof(K1SmemFo) <= 227 * 1024 && sizeof(K1SmemU8) <= 227 * 1024, "K1 shared memory exceeds the 227 KB a CTA may use");
+static_assert(sizeof(K1SmemFo) <= 227 * 1024 && sizeof(K1SmemU8) <= 227 * 1024 && sizeof(K1SmemFoU8) <= 227 * 1024,
+              "K1 shared memory exceeds the 227 KB a CTA may use");
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
 __constant__ float c_hb[2 * TB_HB_H + 1];
@@ -165,8 +171,6 @@ struct K1Args {
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x (x8) base/pitch allow 16-byte bulk copies
-    int32_t* done;          // [C] or null: incremented (release) once per finished work item of a carrier, after its y and partial
-                            //               stores: lets the finalize kernel start on a carrier while this kernel is still running
     int32_t zero_ext;       // 1: the block is extended by zeros and y is written over the whole block (the block-end corrections
                             //    of tetra_edgecorr.cuh are added by the finalize kernel); 0: K1_EDGE outputs at each end are left
                             //    to the exact edge kernels and what lies beyond the block is arbitrary
@@ -277,11 +281,11 @@ __device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a,
 }
 
 // MODE 3: raw byte tile i of this CTA's stream -> slot i % RAWBUF of the byte ring
-__device__ __forceinline__ void k1_issue_stream_tile_u8(K1SmemU8& s8, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
+__device__ __forceinline__ void k1_issue_stream_tile_u8(K1Smem& sb, uint64_t* rawfull, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
     const uint8_t* xc = a.x8 + 2 * (int64_t)sl.car * a.pitch;
     const int64_t gx0 = (int64_t)sl.O * 10 + (int64_t)t * K1_TILE;        // a multiple of 8 (segments are multiples of 640 outputs)
-    uint8_t* dst = reinterpret_cast<uint8_t*>(&s8.base.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES;
-    uint64_t* bar = &s8.rawfull[i % K1_RAWBUF];
+    uint8_t* dst = reinterpret_cast<uint8_t*>(&sb.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES;
+    uint64_t* bar = &rawfull[i % K1_RAWBUF];
     const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
     const int hi = (int)max((int64_t)lo, min((int64_t)K1_TILE, a.n - gx0));
     if (a.aligned) {
@@ -305,14 +309,15 @@ __device__ __forceinline__ void k1_issue_stream_tile_u8(K1SmemU8& s8, const K1Ar
 // within one float32 ulp of the float64 expression. Words [k0, k0 + 64 STEPS) of the tile by 64 threads: two samples
 // (one 32-bit word -> one 16-byte store) per thread and step, all loads of a group issued before the first use.
 constexpr int K1_CV_B = 32, K1_CV_D = 18;     // steps taken by stage B's / stage D's 64 threads (B has more slack)
-static_assert(64 * (K1_CV_B + K1_CV_D) == K1_TILE / 2, "the conversion must cover the tile");
+constexpr int K1_CV_B_FO = 8, K1_CV_D_FO = 42;   // with a freq_offset stage B also runs the equaliser: stage D takes most of the tile
+static_assert(64 * (K1_CV_B + K1_CV_D) == K1_TILE / 2 && 64 * (K1_CV_B_FO + K1_CV_D_FO) == K1_TILE / 2, "the conversion must cover the tile");
 // G loads in flight per group; the group loop stays rolled (the kernel's code must keep fitting the instruction cache)
 template <int STEPS, int G>
-__device__ __forceinline__ void k1_convert_tile_u8(K1SmemU8& s8, int i, int k0, int l64) {
+__device__ __forceinline__ void k1_convert_tile_u8(K1Smem& sb, uint64_t* rawfull, int i, int k0, int l64) {
     static_assert(STEPS % G == 0, "whole groups");
-    mbar_wait(&s8.rawfull[i % K1_RAWBUF], (uint32_t)((i / K1_RAWBUF) & 1));
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(&s8.base.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES) + k0 + l64;
-    float4* dst = reinterpret_cast<float4*>(&s8.base.in[i & 1][K1_HDR]) + k0 + l64;
+    mbar_wait(&rawfull[i % K1_RAWBUF], (uint32_t)((i / K1_RAWBUF) & 1));
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(&sb.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES) + k0 + l64;
+    float4* dst = reinterpret_cast<float4*>(&sb.in[i & 1][K1_HDR]) + k0 + l64;
     // packed constants (-2^23, -2^23), (1/127.5, 1/127.5), (-1, -1)
     unsigned long long p_off, p_sc, p_m1;
     asm("mov.b64 %0, {%1, %1};" : "=l"(p_off) : "f"(-8388608.f));
@@ -379,8 +384,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     extern __shared__ __align__(128) unsigned char smem_raw[];
     K1Smem& s = *reinterpret_cast<K1Smem*>(smem_raw);
     K1SmemFo& sf = *reinterpret_cast<K1SmemFo*>(smem_raw);
-    K1SmemU8& s8 = *reinterpret_cast<K1SmemU8*>(smem_raw);
-    constexpr int NB = MODE == 3 ? 2 : K1_NBUF;           // float tile buffers in rotation
+    constexpr bool U8 = MODE == 3 || MODE == 4;           // input rows are RTL-SDR bytes
+    constexpr bool FO = MODE == 1 || MODE == 4;           // per-carrier freq_offset: NCO on the w samples + equaliser
+    constexpr bool ROT = FO || MODE == 2;                 // the w samples are rotated
+    uint64_t* const rawfull = MODE == 4 ? reinterpret_cast<K1SmemFoU8*>(smem_raw)->rawfull : reinterpret_cast<K1SmemU8*>(smem_raw)->rawfull;
+    constexpr int CVB = FO ? K1_CV_B_FO : K1_CV_B, CVD = FO ? K1_CV_D_FO : K1_CV_D;   // conversion steps of stage B's / stage D's threads
+    constexpr int GB = FO ? 8 : 8, GD = FO ? 6 : 6;       // loads in flight per conversion group
+    static_assert(CVB % GB == 0 && CVD % GD == 0, "whole conversion groups");
+    constexpr int NB = U8 ? 2 : K1_NBUF;                  // float tile buffers in rotation
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slots of this CTA
@@ -396,15 +407,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     for (int i = tid; i < K1_NBUF * (K1_HDR + K1_TILE); i += K1_THREADS) (&s.in[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
-        if (MODE == 3) for (int b = 0; b < K1_RAWBUF; ++b) mbar_init(&s8.rawfull[b], 1);
+        if (U8) for (int b = 0; b < K1_RAWBUF; ++b) mbar_init(&rawfull[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
-    if (MODE == 1 || MODE == 2) {
+    if (ROT) {
         const K1Slot s0 = k1_slot(a, 0);
-        if (MODE == 1 && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
-        if (MODE == 1) for (int i = tid; i < K1_RRING; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
+        if (FO && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
+        if (FO) for (int i = tid; i < K1_RRING; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
         if (MODE == 2 && tid < 2 * TB_PROTO_H + 1) sf.ptap[0][tid] = k1_modulated_tap(tid, a.fo[s0.car], a.fs);
         if (tid >= 256 && tid < 320) {                    // phasors of iteration 0: w [A0, A0 + 640) of slot 0
             K1PhasorSet ps;
@@ -414,17 +425,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     }
     __syncthreads();
     if (warp == 0) {
-        if (MODE == 3) {
-            for (int j = 0; j < 3 && j < n_load; ++j) k1_issue_stream_tile_u8(s8, a, j, k1_slot(a, j / a.t_item), j % a.t_item, lane);
+        if (U8) {
+            for (int j = 0; j < 3 && j < n_load; ++j) k1_issue_stream_tile_u8(s, rawfull, a, j, k1_slot(a, j / a.t_item), j % a.t_item, lane);
         } else {
             k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
             if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
         }
     }
     __syncthreads();                                      // rows that are not 16-byte aligned are filled by plain stores
-    if (MODE == 3) {                                      // tile 0 is converted before the roles start
-        if (warp == 8 || warp == 9) k1_convert_tile_u8<K1_CV_B, 8>(s8, 0, 0, tid - 256);
-        if (warp >= 10) k1_convert_tile_u8<K1_CV_D, 6>(s8, 0, 64 * K1_CV_B, tid - 320);
+    if (U8) {                                             // tile 0 is converted before the roles start
+        if (warp == 8 || warp == 9) k1_convert_tile_u8<CVB, GB>(s, rawfull, 0, 0, tid - 256);
+        if (warp >= 10) k1_convert_tile_u8<CVD, GD>(s, rawfull, 0, 64 * CVB, tid - 320);
         __syncthreads();
     }
 
@@ -433,22 +444,22 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     if (warp < 4) {
         // ---------------- role A: proto, 5 outputs per lane ----------------
         // (slot, tile-in-slot) of the tile being filtered and of the tile being fetched (two ahead), kept incrementally
-        constexpr int AHEAD = MODE == 3 ? 3 : 2;                 // tiles the producer runs ahead of the filter
+        constexpr int AHEAD = U8 ? 3 : 2;                        // tiles the producer runs ahead of the filter
         int q = 0, t = 0, q2 = AHEAD / a.t_item, t2 = AHEAD % a.t_item;
         K1Slot sl2 = k1_slot(a, min(q2, n_my - 1));
         int64_t slot_gx = (int64_t)k1_slot(a, 0).O * 10;      // input index of the current slot's first sample
         for (int i = 0; i < n_iter; ++i) {
             if (i < n_load) {
                 // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
-                if (MODE == 3) {                               // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
-                    if (warp == 0 && i + 3 < n_load) k1_issue_stream_tile_u8(s8, a, i + 3, sl2, t2, lane);
+                if (U8) {                                      // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
+                    if (warp == 0 && i + 3 < n_load) k1_issue_stream_tile_u8(s, rawfull, a, i + 3, sl2, t2, lane);
                 } else if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
                 if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
                 const int L5 = tid;                            // 0..127
                 const int64_t gx0 = slot_gx + (int64_t)t * K1_TILE;
                 const int q_now = q;                           // slot of the tile being filtered
                 if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
-                if (MODE != 3) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
+                if (!U8) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
                 const bool inside = gx0 < a.n && gx0 + K1_TILE > 0;
                 if (a.zero_ext && inside && (gx0 < 0 || gx0 + K1_TILE > a.n)) {
                     // a tile that straddles a block end: what lies outside the block becomes zero (the cascade then computes
@@ -461,7 +472,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     for (int k = L5; k < lo; k += 128) wb[K1_HDR + k] = zero;
                     for (int k = hi + L5; k < K1_TILE; k += 128) wb[K1_HDR + k] = zero;
                     // a bulk copy moves whole 16-byte units: the block's last samples it left out come by plain loads
-                    if (MODE == 3) {
+                    if (U8) {
                         const int done = a.aligned ? ((hi - lo) & ~7) : (hi - lo);
                         if (L5 < hi - lo - done) {
                             const uint8_t* pb = a.x8 + 2 * ((int64_t)k1_slot(a, q_now).car * a.pitch + gx0 + lo + done + L5);
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         }
                     }
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
-                    if (MODE == 1 || MODE == 2) {           // frequency_shift at the decimated rate (processor.py:259-261)
+                    if (ROT) {                              // frequency_shift at the decimated rate (processor.py:259-261)
 #pragma unroll
                         for (int g = 0; g < 5; ++g) {
                             const float2 p = sf.ph[i & 1][5 * L5 + g];
@@ -565,7 +576,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         };
         // MODE 1: slot of stream coordinate 640 i + 2 R0 + PREROLL (the kept outputs of the equalised range), kept incrementally
         int qr = k1_floordiv(2 * K1_R0 + K1_PREROLL, S), rr = 2 * K1_R0 + K1_PREROLL - qr * S;
-        if ((MODE == 1 || MODE == 2) && qn < n_my)
+        if (ROT && qn < n_my)
             open_slot(sn, tn);
         for (int i = 0; i < n_iter; ++i) {
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
@@ -583,7 +594,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         acc[r] = ffma2(xv, c_hb[d], acc[r]);
                 }
             }
-            if (MODE == 1) {
+            if (FO) {
                 // half-band output -> ring; the carrier's equaliser runs over earlier iterations' entries (no barrier in between)
 #pragma unroll
                 for (int r = 0; r < 5; ++r) sf.ur[(nu0 + r) & (K1_RRING - 1)] = acc[r];
@@ -615,12 +626,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                 for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
             }
-            if (MODE == 3 && i + 1 < n_load) k1_convert_tile_u8<K1_CV_B, 8>(s8, i + 1, 0, lb);   // its share of the tile stage A filters next
-            if ((MODE == 1 || MODE == 2) && i + 1 < n_load) {
+            if (U8 && i + 1 < n_load) k1_convert_tile_u8<CVB, GB>(s, rawfull, i + 1, 0, lb);   // its share of the tile stage A filters next
+            if (ROT && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
                 k1_phasors10(pbase, pw, &sf.ph[(i + 1) & 1][10 * lb]);
-                if (tn == 0 && MODE == 1 && lb < 2 * TB_REQ_K + 1) sf.rtap[qn & 1][lb] = k1_req_tap(lb, a.fo[sn.car]);
+                if (tn == 0 && FO && lb < 2 * TB_REQ_K + 1) sf.rtap[qn & 1][lb] = k1_req_tap(lb, a.fo[sn.car]);
                 if (tn == 0 && MODE == 2 && lb < 2 * TB_PROTO_H + 1) sf.ptap[qn & 1][lb] = k1_modulated_tap(lb, a.fo[sn.car], a.fs);
                 if (++tn == a.t_item) {
                     tn = 0; ++qn;
@@ -659,8 +670,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 a.partial[((int64_t)blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
             }
             asm volatile("bar.sync 2, 64;" ::: "memory");
-            // every y store of this item (all 64 threads, ordered by the barrier) and its partial sums are published
-            if (a.done && ld == 0) asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(a.done + sl.car) : "memory");
 #pragma unroll
             for (int j = 0; j < K1_NPH; ++j) pacc[j] = 0.0;
         };
@@ -727,7 +736,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
             r_it += K1_W;
             if (r_it >= S) { r_it -= S; ++q_it; }
-            if (MODE == 3 && i + 1 < n_load) k1_convert_tile_u8<K1_CV_D, 6>(s8, i + 1, 64 * K1_CV_B, ld);   // the rest of that tile
+            if (U8 && i + 1 < n_load) k1_convert_tile_u8<CVD, GD>(s, rawfull, i + 1, 64 * CVB, ld);   // the rest of that tile
             k1_bar_sync();
         }
         if (q_cur >= 0 && q_cur < n_my) flush(n_iter);
