@@ -28,9 +28,19 @@ sys.path.insert(0, ROOT)
 N_SAMPLES = 1 << 20
 TOTAL_CARRIERS = 4096
 BYTES_PER_SAMPLE = 8.10      # 8 B read + (1 B dibit + 8 B soft symbol + ~4 B match) per 130 samples
-# dram__bytes_read.sum + dram__bytes_write.sum of k1_channelize_demod per input sample, from the committed
-# ncu --set full capture (profiles/r01_k1_ncu_full_summary.txt: 4.9671 GB + 0.4850 GB for 592 carriers x 2^20)
-NCU_TRAFFIC_BYTES_PER_SAMPLE = (4.967148e9 + 0.484972e9) / (592 * (1 << 20))
+# dram__bytes_read.sum + dram__bytes_write.sum per input sample from the committed ncu pass AT THIS CONFIGURATION
+# (profiles/r02_traffic.json <- profiles/r02_launches_4096carriers_ncu.csv): the fused kernel alone and all kernels of a step
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
+
+
+def ncu_traffic():
+    try:
+        t = json.load(open(TRAFFIC_FILE))
+        return float(t["k1_dram_bytes_per_sample"]), float(t["step_dram_bytes_per_sample"]), "ncu at %d carriers x 2^20, profiles/r02_traffic.json" % t["carriers"]
+    except Exception:
+        return None, None, "no committed ncu capture found"
+
+
 METRIC = "IQ MS/s demodulated"
 WORKLOAD = "configs[3]: %d carriers x 2^20 complex64 samples @2.4 MS/s, sharded %d per GPU"
 
@@ -370,6 +380,7 @@ def run_ours(a):
 
     if rank == 0:
         peak, peak_src = measured_peak()
+        k1_bps, step_bps, traffic_src = ncu_traffic()
         k_avg = (k_total_ms / k_n) if k_n else None
         achieved = (BYTES_PER_SAMPLE * n_local * N_SAMPLES / (k_avg * 1e-3) / 1e9) if k_avg else None
         cpu = None
@@ -390,8 +401,9 @@ def run_ours(a):
                        "outputs": "dibits + soft symbols + best phase + TS1/TS2 match counts"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": a.traffic if a.traffic is not None else NCU_TRAFFIC_BYTES_PER_SAMPLE * n_local * N_SAMPLES,
-                         "traffic_source": "ncu --set full, profiles/r01_k1_ncu_full_summary.txt, scaled per sample",
+                         "traffic": a.traffic if a.traffic is not None else (k1_bps * n_local * N_SAMPLES if k1_bps else None),
+                         "traffic_step_all_kernels": step_bps * n_local * N_SAMPLES if step_bps else None,
+                         "traffic_source": traffic_src + " (per-sample figure x samples per launch)",
                          "kernel": "k1_channelize_demod<%d>" % (1 if fos is not None else 0), "kernel_ms": k_avg, "kernel_launches_timed": k_n,
                          "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,

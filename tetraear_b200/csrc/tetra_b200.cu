@@ -25,6 +25,7 @@
 #include "tetra_exact.cuh"
 #include "tetra_edges.cuh"
 #include "tetra_edgecorr.cuh"
+#include "tetra_pfb.cuh"
 #include "tetra_finalize.cuh"
 #include "tetra_stft.cuh"
 
@@ -68,6 +69,7 @@ struct tetra_ctx {
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
+    DevBuf pfb;                        // config 3: the 96 channelized 240 kS/s streams of one capture
     DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
     EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
@@ -132,6 +134,15 @@ int upload_tables(tetra_ctx* ctx) {
     CK(cudaFuncSetAttribute(k1_channelize_demod<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFo)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemU8)));
     CK(cudaFuncSetAttribute(k1_channelize_demod<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemFoU8)));
+    CK(cudaFuncSetAttribute(k1_channelize_demod<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1Smem)));
+    {
+        float2 w96[PFB_NCH];
+        for (int q = 0; q < PFB_NCH; ++q) {
+            const double ang = -2.0 * M_PI * q / PFB_NCH;
+            w96[q] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        CK(cudaMemcpyToSymbol(c_w96, w96, sizeof w96));
+    }
     // block-end correction tables -> one device buffer
     {
         constexpr int NT = 11;
@@ -403,7 +414,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     cudaStreamSynchronize(ctx->side);
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
-                      &ctx->etab, &ctx->ecorr, &ctx->estate};
+                      &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->pfb};
     for (DevBuf* b : bufs) b->release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -719,6 +730,27 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ka.aligned = ((reinterpret_cast<uintptr_t>(u8) & 15) == 0) && ((u8_pitch & 7) == 0);
         }
         ka.fo = d_fo; ka.fs_dec = pl.rate; ka.fs = ctx->sample_rate;
+        // config 3 on the 25 kHz grid of a 2.4 MS/s capture: the proto stage of ALL channels is one polyphase DFT (k_pfb96) and
+        // the fused kernel runs its remaining stages on the 96 channelized streams (MODE 5); TETRA_PFB=0 keeps the per-channel
+        // modulated proto (MODE 2), which is also what off-grid channel lists get
+        static const int pfb_env = getenv("TETRA_PFB") ? atoi(getenv("TETRA_PFB")) : 1;
+        bool pfb = chan_hz != nullptr && pfb_env != 0 && edge_corr;
+        for (int c = 0; c < C && pfb; ++c) {
+            const double k = chan_hz[c] * (PFB_NCH / ctx->sample_rate);
+            if (k != std::floor(k) || k < -PFB_NCH / 2 || k >= PFB_NCH / 2) pfb = false;
+        }
+        ka.w_col0 = 0;
+        if (pfb) {
+            const int64_t cols = PFB_M0 + (int64_t)n_seg * seg_len + 2 * K1_W;           // every w index a slot's tiles touch
+            const int64_t wp = (cols + PFB_MB - 1) / PFB_MB * PFB_MB;
+            CK(ctx->pfb.ensure((size_t)PFB_NCH * wp * sizeof(float2)));
+            PfbArgs pa;
+            pa.x = d_x; pa.n = N; pa.w = (float2*)ctx->pfb.p; pa.wp = wp;
+            k_pfb96<<<(unsigned)(wp / PFB_MB), PFB_THREADS, 0, st>>>(pa);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            ka.x = (const float2*)ctx->pfb.p; ka.pitch = wp; ka.w_col0 = PFB_M0; ka.aligned = 1;
+        }
         ka.zero_ext = edge_corr ? 1 : 0;
         // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
@@ -754,6 +786,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         }
         if (u8_fused && any_fo) k1_channelize_demod<4><<<k1_grid, K1_THREADS, sizeof(K1SmemFoU8), st>>>(ka);
         else if (u8_fused) k1_channelize_demod<3><<<k1_grid, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
+        else if (pfb) k1_channelize_demod<5><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
         else if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
         else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);

@@ -171,6 +171,7 @@ struct K1Args {
     int32_t y_rows;
     double* partial;        // [C][n_seg][16]
     int32_t aligned;        // 1: x (x8) base/pitch allow 16-byte bulk copies
+    int32_t w_col0;         // MODE 5: x holds channelized 240 kS/s streams [96][pitch] (tetra_pfb.cuh), w index m at column m + w_col0
     int32_t zero_ext;       // 1: the block is extended by zeros and y is written over the whole block (the block-end corrections
                             //    of tetra_edgecorr.cuh are added by the finalize kernel); 0: K1_EDGE outputs at each end are left
                             //    to the exact edge kernels and what lies beyond the block is arbitrary
@@ -277,6 +278,17 @@ __device__ __forceinline__ void k1_issue_stream_tile(K1Smem& s, const K1Args& a,
         for (int tt = lo + lane; tt < hi; tt += 32) dst[tt] = __ldg(xc + gx0 + tt);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
+    }
+}
+
+// MODE 5: the 640 w samples of tile i, already channelized (tetra_pfb.cuh), from row (channel offset / 25 kHz + 48)
+__device__ __forceinline__ void k1_issue_stream_tile_w(K1Smem& s, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
+    if (lane == 0) {
+        const int row = (int)lrint(a.fo[sl.car] * (96.0 / a.fs)) + 48;
+        const float2* src = a.x + (int64_t)row * a.pitch + (a.w_col0 + sl.O + K1_W * t + K1_A0);
+        uint64_t* bar = &s.full[i % K1_NBUF];
+        mbar_expect_tx(bar, K1_W * 8);
+        tma_load_1d(&s.in[i % K1_NBUF][K1_HDR], src, K1_W * 8, bar);
     }
 }
 
@@ -427,6 +439,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     if (warp == 0) {
         if (U8) {
             for (int j = 0; j < 3 && j < n_load; ++j) k1_issue_stream_tile_u8(s, rawfull, a, j, k1_slot(a, j / a.t_item), j % a.t_item, lane);
+        } else if (MODE == 5) {
+            k1_issue_stream_tile_w(s, a, 0, k1_slot(a, 0), 0, lane);
+            if (1 < n_load) k1_issue_stream_tile_w(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
         } else {
             k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
             if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
@@ -453,6 +468,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
                 if (U8) {                                      // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
                     if (warp == 0 && i + 3 < n_load) k1_issue_stream_tile_u8(s, rawfull, a, i + 3, sl2, t2, lane);
+                } else if (MODE == 5) {
+                    if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile_w(s, a, i + 2, sl2, t2, lane);
                 } else if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
                 if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
                 const int L5 = tid;                            // 0..127
@@ -460,7 +477,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 const int q_now = q;                           // slot of the tile being filtered
                 if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
                 if (!U8) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
-                const bool inside = gx0 < a.n && gx0 + K1_TILE > 0;
+                if (MODE == 5) {
+                    // the proto stage ran in the channelizer: the tile IS this iteration's 640 w samples
+                    const float2* wsrc = &s.in[i % NB][K1_HDR + 5 * L5];
+                    const int wbase = K1_W * i + K1_A0 + 5 * L5;
+#pragma unroll
+                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = wsrc[g];
+                }
+                const bool inside = MODE != 5 && gx0 < a.n && gx0 + K1_TILE > 0;
                 if (a.zero_ext && inside && (gx0 < 0 || gx0 + K1_TILE > a.n)) {
                     // a tile that straddles a block end: what lies outside the block becomes zero (the cascade then computes
                     // the shift-invariant response of the zero-extended block, which the block-end corrections refer to)
@@ -524,7 +548,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
                     // tail of this tile -> header of the next buffer
                     if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = buf[K1_TILE + L5];
-                } else if (a.zero_ext) {                       // a tile entirely outside the block: zeros
+                } else if (MODE != 5 && a.zero_ext) {          // a tile entirely outside the block: zeros
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
 #pragma unroll
                     for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = make_float2(0.f, 0.f);

@@ -84,8 +84,18 @@ def main():
     ms, wall = timed(lambda: sp._lib.tetra_process_wideband(sp._ctx, xw_d.data_ptr(), n, fr.ctypes.data, 96, dib3.data_ptr(), cap,
                                                             nd3.data_ptr(), sym3.data_ptr(), ph3.data_ptr(), mt3.data_ptr()), reps=10)
     sp._lib.tetra_set_stream(sp._ctx, None)
+    # fp32 work of the per-channel stages (FFMA2 per input sample: proto 4.1 [x2 with modulated complex taps],
+    # half-band 0.65, fir120 6.4, interpolation 0.8) against the measured FFMA2 issue peak (tools/microbench/pipes.cu:
+    # 0.5 warp instructions per clock and SM sub-partition)
+    pfb_on = os.environ.get("TETRA_PFB", "1") != "0"
+    ffma2_per_sample = (0.65 + 6.4 + 0.8) if pfb_on else (2 * 4.1 + 0.65 + 6.4 + 0.8)
+    ffma2_peak = 148 * 4 * 0.5 * 32 * 1.965e9
     out["config3_wideband_96ch_device_resident"] = {"ms_per_capture": ms, "wideband_MS_per_s": n / ms / 1e3,
-                                                    "channel_MS_per_s": 96 * n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3)}
+                                                    "channel_MS_per_s": 96 * n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3),
+                                                    "front_end": "k_pfb96 polyphase DFT + MODE 5" if pfb_on else "per-channel modulated proto (MODE 2)",
+                                                    "ffma2_lane_ops_per_capture": 96 * n * ffma2_per_sample,
+                                                    "fp32_pipe_utilisation": 96 * n * ffma2_per_sample / (ms * 1e-3) / ffma2_peak,
+                                                    }
 
     # ---- RTL-SDR bytes, device-resident, the configs[3] batch (4096 carriers x 2^20 samples at 2 B/sample) ----
     cu = int(os.environ.get("TETRA_U8_CARRIERS", "4096"))
