@@ -381,7 +381,10 @@ def run_ours(a):
     if rank == 0:
         peak, peak_src = measured_peak()
         k1_bps, step_bps, traffic_src = ncu_traffic()
-        k_avg = (k_total_ms / k_n) if k_n else None
+        # a large batch is cut into a few launches of the fused kernel (whole slots each, tetra_b200.cu): bytes and time are
+        # summed over the launches of a step, i.e. achieved = sum of algorithmic bytes / sum of launch durations
+        k_avg = (k_total_ms / a.steps) if k_n else None
+        k_per_step = (k_n / a.steps) if k_n else None
         achieved = (BYTES_PER_SAMPLE * n_local * N_SAMPLES / (k_avg * 1e-3) / 1e9) if k_avg else None
         cpu = None
         if world == 1 and not a.no_cpu:
@@ -405,9 +408,11 @@ def run_ours(a):
                          "traffic_step_all_kernels": step_bps * n_local * N_SAMPLES if step_bps else None,
                          "traffic_source": traffic_src + " (per-sample figure x samples per launch)",
                          "kernel": "k1_channelize_demod<%d>" % (1 if fos is not None else 0), "kernel_ms": k_avg, "kernel_launches_timed": k_n,
+                         "kernel_launches_per_step": k_per_step,
                          "kernel_share_of_step": (k_total_ms / ms_total) if k_n else None,
                          "peak_source": peak_src, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE,
-                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES,
+                         "algorithmic_bytes_per_launch": BYTES_PER_SAMPLE * n_local * N_SAMPLES / (k_per_step or 1),
+                         "algorithmic_bytes_per_step": BYTES_PER_SAMPLE * n_local * N_SAMPLES,
                          "last_step_timeline_ms": {"fused_kernel_and_edge_join": phases[0], "edge_kernel_span": phases[1],
                                                    "finalize_and_sync": phases[2]}},
             "cpu_baseline": cpu,

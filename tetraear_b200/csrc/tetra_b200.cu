@@ -31,6 +31,7 @@
 
 using namespace tetra;
 static_assert(K1_EDGE == K_EDGE, "edge width of the fused and the exact kernels must agree");
+constexpr int K1_MAX_GROUPS = 4;          // launches a large batch is cut into (finalize of group g beside the fused kernel of g + 1)
 
 namespace {
 
@@ -58,6 +59,7 @@ struct tetra_ctx {
     double sample_rate = 2.4e6;
     cudaStream_t own_stream = nullptr, stream = nullptr, side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};   // fused-kernel group g done (K1_MAX_GROUPS)
     // per-launch CUDA-event pairs around the fused kernel (bench.py's roofline leg)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
     size_t ev_used = 0;
@@ -71,6 +73,8 @@ struct tetra_ctx {
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
     DevBuf pfb;                        // config 3: the 96 channelized 240 kS/s streams of one capture
     DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
+    DevBuf emat[10], emat_unit;        // states -> corrections matrices (freq_offset = 0), one per (n - 1) mod 10; unit states
+    bool emat_built[10] = {false, false, false, false, false, false, false, false, false, false};
     EdgeTables etab_ptrs{};
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
@@ -183,11 +187,28 @@ int launch_edge_correct(tetra_ctx* ctx, cudaStream_t st, const float2* x, const 
     EdgeCorrArgs ea;
     ea.x = x; ea.x8 = x8; ea.pitch = pitch; ea.n = n; ea.L = L; ea.fo = d_fo; ea.chan = d_chan; ea.fs = fs; ea.fs_dec = fs_dec;
     ea.cf = cf; ea.t = ctx->etab_ptrs; ea.n_carriers = C; ea.states = (double2*)ctx->estate.p; ea.d = (float2*)ctx->ecorr.p;
-    const int g1 = (C + KC_THREADS / 32 - 1) / (KC_THREADS / 32);
-    const dim3 g2((C + KC2_THREADS - 1) / KC2_THREADS, 2);
-    if (x8) { k_edge_states<1><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<1><<<g2, KC2_THREADS, 0, st>>>(ea); }
-    else if (d_chan) { k_edge_states<2><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<2><<<g2, KC2_THREADS, 0, st>>>(ea); }
-    else { k_edge_states<0><<<g1, KC_THREADS, 0, st>>>(ea); k_edge_recursions<0><<<g2, KC2_THREADS, 0, st>>>(ea); }
+    ea.m_out = nullptr; ea.m = nullptr;
+    if (!d_fo) {
+        // no freq_offset: states -> corrections is one real matrix per (n - 1) mod 10, built once by the recursion kernel on unit states
+        const int k0 = (int)((n - 1) % 10);
+        if (!ctx->emat_built[k0]) {
+            CK(ctx->emat[k0].ensure((size_t)KC_NSTATE * 2 * K_EDGE * sizeof(double)));
+            CK(ctx->emat_unit.ensure((size_t)KC_NSTATE * KC_NSTATE * sizeof(double2)));
+            k_edge_unit_states<<<(KC_NSTATE * KC_NSTATE + 255) / 256, 256, 0, st>>>((double2*)ctx->emat_unit.p);
+            EdgeCorrArgs eb = ea;
+            eb.fo = nullptr; eb.n_carriers = KC_NSTATE; eb.states = (double2*)ctx->emat_unit.p; eb.m_out = (double*)ctx->emat[k0].p;
+            k_edge_recursions<<<dim3((KC_NSTATE + KC2_THREADS - 1) / KC2_THREADS, 2), KC2_THREADS, 0, st>>>(eb);
+            ctx->launches += 2;
+            CK(cudaGetLastError());
+            ctx->emat_built[k0] = true;
+        }
+        ea.m = (const double*)ctx->emat[k0].p;
+    }
+    if (x8) k_edge_states<1><<<C, KC_THREADS, 0, st>>>(ea);
+    else if (d_chan) k_edge_states<2><<<C, KC_THREADS, 0, st>>>(ea);
+    else k_edge_states<0><<<C, KC_THREADS, 0, st>>>(ea);
+    if (d_fo) k_edge_recursions<<<dim3((C + KC2_THREADS - 1) / KC2_THREADS, 2), KC2_THREADS, 0, st>>>(ea);
+    else k_edge_apply<<<dim3((C + KA_CPB - 1) / KA_CPB, 2), KA_THREADS, 0, st>>>(ea);
     ctx->launches++;
     ctx->launches++;
     CK(cudaGetLastError());
@@ -416,7 +437,10 @@ void tetra_destroy(tetra_ctx* ctx) {
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
                       &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->pfb};
     for (DevBuf* b : bufs) b->release();
+    for (DevBuf& b : ctx->emat) b.release();
+    ctx->emat_unit.release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    for (int k = 0; k < 4; ++k) if (ctx->ev_grp[k]) cudaEventDestroy(ctx->ev_grp[k]);
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int k = 0; k < 4; ++k) if (ctx->ph_ev[k]) cudaEventDestroy(ctx->ph_ev[k]);
     for (int k = 0; k < 2; ++k) if (ctx->edge_ev[k]) cudaEventDestroy(ctx->edge_ev[k]);
@@ -688,6 +712,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
 
     FinArgs fa;
     memset(&fa, 0, sizeof fa);
+    int fin_c0 = 0;                                    // first carrier the in-order finalize launch still has to do
     fa.y = (const float2*)ctx->y.p; fa.y_pitch = y_pitch; fa.y_rows = y_rows; fa.L = (int32_t)pl.L; fa.sps = pl.sps; fa.step = pl.step;
     fa.dibits = k_dib; fa.cap = cap; fa.n_dibits = k_nd; fa.symbols = k_sym; fa.best_phase = k_ph;
     fa.phase_scratch = (int32_t*)ctx->phase.p;
@@ -736,14 +761,19 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         static const int pfb_env = getenv("TETRA_PFB") ? atoi(getenv("TETRA_PFB")) : 1;
         bool pfb = chan_hz != nullptr && pfb_env != 0 && edge_corr;
         for (int c = 0; c < C && pfb; ++c) {
-            const double k = chan_hz[c] * (PFB_NCH / ctx->sample_rate);
-            if (k != std::floor(k) || k < -PFB_NCH / 2 || k >= PFB_NCH / 2) pfb = false;
+            const double k = chan_hz[c] * (PFB_NCH / ctx->sample_rate), kr = std::nearbyint(k);   // on the grid up to rounding of the product
+            if (std::fabs(k - kr) > 1e-9 || kr < -PFB_NCH / 2 || kr >= PFB_NCH / 2) pfb = false;
         }
         ka.w_col0 = 0;
+        bool forked = false;
         if (pfb) {
             const int64_t cols = PFB_M0 + (int64_t)n_seg * seg_len + 2 * K1_W;           // every w index a slot's tiles touch
             const int64_t wp = (cols + PFB_MB - 1) / PFB_MB * PFB_MB;
             CK(ctx->pfb.ensure((size_t)PFB_NCH * wp * sizeof(float2)));
+            // the block-end corrections read the capture itself: let the side stream start ahead of the channelizer
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+            forked = true;
             PfbArgs pa;
             pa.x = d_x; pa.n = N; pa.w = (float2*)ctx->pfb.p; pa.wp = wp;
             k_pfb96<<<(unsigned)(wp / PFB_MB), PFB_THREADS, 0, st>>>(pa);
@@ -770,45 +800,83 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             if (rc) return rc;
             if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], st));
         }
-        CK(cudaEventRecord(ctx->ev_fork, st));
-        CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
-        // the fused kernel goes first: its persistent CTAs (one per SM) must not queue behind the edge blocks
-        cudaEvent_t t0 = nullptr, t1 = nullptr;
-        if (ctx->timing && ctx->ev_used < 4096) {
-            if (ctx->ev_used == ctx->ev_pool.size()) {
-                cudaEvent_t a = nullptr, b = nullptr;
-                CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
-                ctx->ev_pool.emplace_back(a, b);
-            }
-            t0 = ctx->ev_pool[ctx->ev_used].first; t1 = ctx->ev_pool[ctx->ev_used].second;
-            ctx->ev_used++;
-            CK(cudaEventRecord(t0, st));
+        if (!forked) {
+            CK(cudaEventRecord(ctx->ev_fork, st));
+            CK(cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
         }
-        if (u8_fused && any_fo) k1_channelize_demod<4><<<k1_grid, K1_THREADS, sizeof(K1SmemFoU8), st>>>(ka);
-        else if (u8_fused) k1_channelize_demod<3><<<k1_grid, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
-        else if (pfb) k1_channelize_demod<5><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
-        else if (chan_hz) k1_channelize_demod<2><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
-        else if (any_fo) k1_channelize_demod<1><<<k1_grid, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
-        else k1_channelize_demod<0><<<k1_grid, K1_THREADS, sizeof(K1Smem), st>>>(ka);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        if (t1) CK(cudaEventRecord(t1, st));
-        // time-skewed sections (short critical path) unless TETRA_EDGE_MODE=2 asks for the plain sequential kernel
-        const bool side_edges = !(edge_corr && edge_serial);
-        if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
-        // batches that cannot hide a thread's serial recursion behind the fused kernel: one warp per job
-        if (!side_edges) rc = 0;
-        else if (edge_corr)
-            rc = launch_edge_correct(ctx, ctx->side, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
-                                     (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
-        else if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
-        else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
-        else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
-        if (rc) return rc;
-        if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
+        // TETRA_K1_GROUPS=g (measurement switch, default 1): cut a large batch into g launches of whole slots (multiples of the
+        // CTA count, so the cut costs no extra slot) and run the finalize kernel of group k on the side stream beside the fused
+        // kernel of group k + 1 (its 256-thread, 20 KB CTAs fit next to a fused-kernel CTA). Measured at 4096 carriers x 2^20
+        // (profiles/r02_groups_ab.txt): the serial finalize shrinks from 0.37 to 0.10 ms, the fused kernel slows by 0.19 ms
+        // (both want HBM), the step gains 0.6 % -- not worth a lower roofline fraction of the dominant kernel, so off by default.
+        static const int grp_env = getenv("TETRA_K1_GROUPS") ? atoi(getenv("TETRA_K1_GROUPS")) : 1;
+        int n_grp = 1;
+        if (n_seg == 1 && edge_corr && grp_env > 1) {
+            const int slots = (C + sms - 1) / sms;
+            n_grp = std::max(1, std::min(std::min(grp_env, K1_MAX_GROUPS), slots));
+        }
+        const int grp_slots = ((C + sms - 1) / sms + n_grp - 1) / n_grp;
+        const int grp_car = n_grp > 1 ? grp_slots * sms : C;            // carriers per group (the last one takes what is left)
+        n_grp = n_grp > 1 ? (C + grp_car - 1) / grp_car : 1;
+        for (int g = 0; g < K1_MAX_GROUPS && n_grp > 1; ++g)
+            if (!ctx->ev_grp[g]) CK(cudaEventCreateWithFlags(&ctx->ev_grp[g], cudaEventDisableTiming));
         fa.partial = (const double*)ctx->partial.p; fa.n_seg = n_seg;
         fa.bulk_lo = K1_EDGE; fa.bulk_hi = (int32_t)pl.L - K1_EDGE;
-        fa.edge_corr = edge_corr ? (const float2*)ctx->ecorr.p : nullptr;
+        if (edge_corr) {                                  // sized here: the finalize launches below take the pointer
+            CK(ctx->ecorr.ensure((size_t)C * 2 * K_EDGE * sizeof(float2)));
+            fa.edge_corr = (const float2*)ctx->ecorr.p;
+        }
+        const bool side_edges = !(edge_corr && edge_serial);
+        for (int g = 0; g < n_grp; ++g) {
+            const int c_lo = g * grp_car, c_hi = std::min(C, c_lo + grp_car);
+            ka.item0 = c_lo * n_seg; ka.n_items = (c_hi - c_lo) * n_seg;
+            const int grid_g = std::min(sms, ka.n_items);
+            // the fused kernel goes first: its persistent CTAs (one per SM) must not queue behind the edge blocks
+            cudaEvent_t t0 = nullptr, t1 = nullptr;
+            if (ctx->timing && ctx->ev_used < 4096) {
+                if (ctx->ev_used == ctx->ev_pool.size()) {
+                    cudaEvent_t a = nullptr, b = nullptr;
+                    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+                    ctx->ev_pool.emplace_back(a, b);
+                }
+                t0 = ctx->ev_pool[ctx->ev_used].first; t1 = ctx->ev_pool[ctx->ev_used].second;
+                ctx->ev_used++;
+                CK(cudaEventRecord(t0, st));
+            }
+            if (u8_fused && any_fo) k1_channelize_demod<4><<<grid_g, K1_THREADS, sizeof(K1SmemFoU8), st>>>(ka);
+            else if (u8_fused) k1_channelize_demod<3><<<grid_g, K1_THREADS, sizeof(K1SmemU8), st>>>(ka);
+            else if (pfb) k1_channelize_demod<5><<<grid_g, K1_THREADS, sizeof(K1Smem), st>>>(ka);
+            else if (chan_hz) k1_channelize_demod<2><<<grid_g, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+            else if (any_fo) k1_channelize_demod<1><<<grid_g, K1_THREADS, sizeof(K1SmemFo), st>>>(ka);
+            else k1_channelize_demod<0><<<grid_g, K1_THREADS, sizeof(K1Smem), st>>>(ka);
+            ctx->launches++;
+            CK(cudaGetLastError());
+            if (t1) CK(cudaEventRecord(t1, st));
+            if (g + 1 < n_grp) CK(cudaEventRecord(ctx->ev_grp[g], st));
+            if (g == 0) {
+                // block ends on the side stream, beside the fused kernel (TETRA_EDGE_MODE = 1 / 3 / 2: the literal recursions of
+                // round 1 -- thread per job, warp per job, plain sequential)
+                if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
+                if (!side_edges) rc = 0;
+                else if (edge_corr)
+                    rc = launch_edge_correct(ctx, ctx->side, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
+                                             (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
+                else if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
+                else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
+                else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
+                if (rc) return rc;
+                if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
+            } else {
+                // finalize of the previous group, beside this group's fused kernel
+                const int p_lo = (g - 1) * grp_car;
+                CK(cudaStreamWaitEvent(ctx->side, ctx->ev_grp[g - 1], 0));
+                fa.car0 = p_lo;
+                k_finalize<<<c_lo - p_lo, FIN_THREADS, 0, ctx->side>>>(fa);
+                ctx->launches++;
+                CK(cudaGetLastError());
+            }
+        }
+        fin_c0 = (n_grp - 1) * grp_car;
         CK(cudaEventRecord(ctx->ev_join, ctx->side));
         CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
         if (ctx->timing && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[1], st));
@@ -818,7 +886,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         fa.partial = nullptr; fa.n_seg = 0; fa.bulk_lo = 0; fa.bulk_hi = 0;
     }
     if (ctx->timing && use_fast && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[2], st));
-    k_finalize<<<C, FIN_THREADS, 0, st>>>(fa);
+    fa.car0 = fin_c0;
+    k_finalize<<<C - fin_c0, FIN_THREADS, 0, st>>>(fa);
     ctx->launches++;
     CK(cudaGetLastError());
     if (ts_match && cap > 0 && !fused_match) {

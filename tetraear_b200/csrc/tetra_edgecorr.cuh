@@ -8,10 +8,13 @@
 //        D[m] = reference(x)[m] - cascade(x zero-extended)[m]        for the K_EDGE outputs next to each end,
 // which is linear in x and is driven by a handful of IIR filter states at the block end. Those states are dot products
 // of the block's first / last ~1200 samples with fixed weight tables (edge_tables_generated.h, from tools/edge_model.py,
-// where the derivation and a float64 model of exactly these steps live): k_edge_states, one warp per carrier. A few hundred
-// literal order-4 recursion steps at 240 kS/s then give D: k_edge_recursions, one thread per (carrier, end), the lanes
-// of a warp walking 32 carriers in lockstep. Both depend on the input only, so they run beside the fused kernel; the
-// finalize kernel adds D to the fused kernel's output where it reads the block ends.
+// where the derivation and a float64 model of exactly these steps live): k_edge_states, one CTA per carrier, its four warps
+// sharing the seven table passes. A few hundred literal order-4 recursion steps at 240 kS/s then give D: k_edge_recursions,
+// one thread per (carrier, end), the lanes of a warp walking 32 carriers in lockstep. Without a freq_offset that map from
+// the states to D is one fixed real matrix per block end (it depends on (n - 1) mod 10 only): the host builds it once per
+// geometry by running k_edge_recursions on unit states, and k_edge_apply evaluates D = M s in parallel -- 168 threads per
+// (carrier group, end) instead of a 900-step serial chain. All of it depends on the input only, so it runs beside the fused
+// kernel; the finalize kernel adds D to the fused kernel's output where it reads the block ends.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -20,9 +23,21 @@
 
 namespace tetra {
 
-constexpr int KC_THREADS = 128;           // k_edge_states: one warp per carrier, four carriers per CTA
+constexpr int KC_THREADS = 128;           // k_edge_states: one CTA per carrier, the table passes spread over its four warps
 constexpr int KC2_THREADS = 64;           // k_edge_recursions: one thread per (carrier, block end)
-constexpr int KC_NSTATE = 8 + 8 + 2 * ET_NPTS + 4;   // per carrier: s_c, s_ac0, pts_r, pts_l, s2_k1 (complex128)
+// per carrier (complex128): what the right end's correction depends on, then the same for the left end
+constexpr int KS_SC = 0;                  // [8]  causal cascade state after x[n-1]
+constexpr int KS_PTR = 8;                 // [16] decimator outputs L-1-t of the zero-extended stream
+constexpr int KS_S2 = 24;                 // [4]  causal Butterworth state of the zero-extended stream at the right end
+constexpr int KS_XR = 28;                 // [28] x[n-1-j], j = 0 .. PAD1 (stage 1's odd extension)
+constexpr int KS_NR = 56;
+constexpr int KS_SAC = 56;                // [8]  backward-pass state at position 0
+constexpr int KS_PTL = 64;                // [16] decimator outputs t of the zero-extended stream
+constexpr int KS_XL = 80;                 // [28] x[j], j = 0 .. PAD1
+constexpr int KS_NL = 52;
+constexpr int KC_NSTATE = KS_NR + KS_NL;
+constexpr int KA_THREADS = 192, KA_CPB = 8;   // k_edge_apply: K_EDGE outputs x 8 carriers per CTA
+static_assert(ET_NPTS == 16 && EX_PAD1 + 1 == 28 && KA_THREADS >= K_EDGE, "state layout");
 static_assert(ET_NPTS == EX_PAD2 + 1, "stage 2's odd extension needs PAD2 + 1 decimator outputs");
 static_assert(ET_TD <= K_EDGE && ET_NRING >= 10 * ET_TD + 10, "ringing tables too short");
 static_assert(ET_G >= 10 * ET_NPTS, "pointwise windows start inside the block");
@@ -54,6 +69,8 @@ struct EdgeCorrArgs {
     int32_t n_carriers;
     double2* states;         // [C][KC_NSTATE] scratch between the two kernels
     float2* d;               // [C][2][K_EDGE]: D_left[m] (m = 0..), D_right[t] (output L-1-t)
+    double* m_out;           // k_edge_recursions on unit states: real parts [C][2][K_EDGE] in float64 instead of d (the matrix M)
+    const double* m;         // k_edge_apply: M[k][end][K_EDGE], k = state index
 };
 
 struct dcx { double x, y; };
@@ -122,9 +139,8 @@ __device__ __forceinline__ void kc_warp_sum(dcx (&acc)[NA], double2* dst, int la
 // ----------------------------------------------------------------------------------------------
 template <int IN>   // 0: complex64 rows, 1: uint8 rows, 2: channels of one shared complex64 capture
 __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int car = blockIdx.x * (KC_THREADS / 32) + (threadIdx.x >> 5);
-    if (car >= a.n_carriers) return;                          // whole warps
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int car = blockIdx.x;
     const int64_t n = a.n;
     const int L = a.L;
     const int k0 = (int)((n - 1) % 10);
@@ -141,8 +157,16 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc[k] = dcx{0.0, 0.0};
     };
+    // warp 0: cascade state + Butterworth state; warp 1: backward-pass state + the raw end samples; warps 2, 3: pointwise outputs
+    if (warp == 1) {
+        if (lane <= EX_PAD1) {
+            const dcx r = xr(lane), l = xl(lane);
+            out[KS_XR + lane] = make_double2(r.x, r.y);
+            out[KS_XL + lane] = make_double2(l.x, l.y);
+        }
+    }
     // ---- causal cascade state after x[n-1] ----
-    {
+    if (warp == 0) {
         clear();
         const double* __restrict__ wc = a.t.wc;
         for (int d0 = lane; d0 < ET_NC; d0 += 32 * UN) {
@@ -156,10 +180,10 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 for (int k = 0; k < 8; ++k) { const double w = wc[k * ET_NC + d]; acc[k].x += w * v[q].x; acc[k].y += w * v[q].y; }
             }
         }
-        kc_warp_sum(acc, out, lane);
+        kc_warp_sum(acc, out + KS_SC, lane);
     }
     // ---- backward-pass state at position 0 of the zero-extended stream ----
-    {
+    if (warp == 1) {
         clear();
         const double* __restrict__ wac = a.t.wac;
         for (int d0 = lane; d0 < ET_NAC; d0 += 32 * UN) {
@@ -173,11 +197,12 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 for (int k = 0; k < 8; ++k) { const double w = wac[k * ET_NAC + d]; acc[k].x += w * v[q].x; acc[k].y += w * v[q].y; }
             }
         }
-        kc_warp_sum(acc, out + 8, lane);
+        kc_warp_sum(acc, out + KS_SAC, lane);
     }
     // ---- pointwise decimator outputs of the zero-extended stream: at output L-1-t, sum_d g1[d - k0 - 10 t] x[n-1-d],
     //      and at output t, sum_i g1[10 t - i] x[i]   (t = 8 h + k) ----
-    for (int h = 0; h < ET_NPTS / 8; ++h) {
+    if (warp >= 2) {
+        const int h = warp - 2;
         clear();
         const int off_r = ET_G - k0 - 80 * h, cnt_r = k0 + 10 * (8 * h + 7) + ET_G + 1;
         for (int d0 = lane; d0 < cnt_r; d0 += 32 * UN) {
@@ -194,7 +219,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 }
             }
         }
-        kc_warp_sum(acc, out + 16 + 8 * h, lane);
+        kc_warp_sum(acc, out + KS_PTR + 8 * h, lane);
         clear();
         const int off_l = ET_G + 80 * h, cnt_l = 10 * (8 * h + 7) + ET_G + 1;
         for (int d0 = lane; d0 < cnt_l; d0 += 32 * UN) {
@@ -211,11 +236,12 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 }
             }
         }
-        kc_warp_sum(acc, out + 16 + ET_NPTS + 8 * h, lane);
+        kc_warp_sum(acc, out + KS_PTL + 8 * h, lane);
     }
     // ---- causal Butterworth state of the zero-extended stream at the right end ----
     // s(L) = e^{-jW(L-1)} sum_d x[n-1-d] Wv(d - k0),  Wv(u) = Bv g1[u] + e^{jW} A Wv(u - 10)  (tools/edge_model.py).
     // Without a freq_offset the weights are real and fixed: one more table pass.
+    if (warp != 0) return;
     if (fo == 0.0) {
         dcx a4[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         const double* __restrict__ w0 = a.t.w0 + 9 - k0;      // w0[k * NW0 + d] = W0[k][d - k0 + 9]
@@ -231,7 +257,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 for (int k = 0; k < 4; ++k) { const double w = w0[k * ET_NW0 + d]; a4[k].x += w * v[q].x; a4[k].y += w * v[q].y; }
             }
         }
-        kc_warp_sum(a4, out + 16 + 2 * ET_NPTS, lane);
+        kc_warp_sum(a4, out + KS_S2, lane);
         return;
     }
     // With one: in modal coordinates (A = V diag(p) V^-1, lambda_r = p_r e^{jW}):
@@ -324,7 +350,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
                 const dcx t = cmul(dcx{a.t.bv[2 * (4 * lane + r)], a.t.bv[2 * (4 * lane + r) + 1]}, sig);
                 st.x += t.x; st.y += t.y;
             }
-            out[16 + 2 * ET_NPTS + lane] = make_double2(st.x, st.y);
+            out[KS_S2 + lane] = make_double2(st.x, st.y);
         }
     }
 }
@@ -333,32 +359,32 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
 // k_edge_recursions: from the states to the corrections. Thread = one carrier, blockIdx.y = the end (0 left, 1 right):
 // a few hundred serial order-4 steps per thread, the same instruction stream in every lane.
 // ----------------------------------------------------------------------------------------------
-template <int IN>
 __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrArgs a) {
     const int car = blockIdx.x * KC2_THREADS + threadIdx.x;
     if (car >= a.n_carriers) return;
     const int64_t n = a.n;
     const int L = a.L;
     const int k0 = (int)((n - 1) % 10);
-    const double chan_hz = (IN == 2) ? a.chan[car] : 0.0;
     const double fo = a.fo ? a.fo[car] : 0.0;
-    auto xr = [&](int d) { return kc_load<IN>(a, car, chan_hz, n - 1 - d); };
-    auto xl = [&](int i) { return kc_load<IN>(a, car, chan_hz, i); };
     const ExactCoef& cf = a.cf;
     const dcx rstep = cexp_turns(fo / a.fs_dec);              // NCO rotation per 240 kS/s sample, exp(-j W)
     const dcx rstep_c{rstep.x, -rstep.y};                     // exp(+j W)
     auto rot_at = [&](int64_t j) { return cexp_turns(fo * (double)j / a.fs_dec); };
     const double2* stt = a.states + (int64_t)car * KC_NSTATE;
     auto ld = [&](int k) { const double2 v = stt[k]; return dcx{v.x, v.y}; };
+    auto xr = [&](int d) { return ld(KS_XR + d); };           // x[n-1-d], d <= PAD1
+    auto xl = [&](int i) { return ld(KS_XL + i); };           // x[i], i <= PAD1
     float2* dl = a.d + (int64_t)car * 2 * K_EDGE;
     float2* dr = dl + K_EDGE;
+    double* ml = a.m_out ? a.m_out + (int64_t)car * 2 * K_EDGE : nullptr;
+    double* mr = ml ? ml + K_EDGE : nullptr;
     KcBa st;
 
     if (blockIdx.y == 1) {
         // ================= right end =================
         dcx scv[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) scv[k] = ld(k);
+        for (int k = 0; k < 8; ++k) scv[k] = ld(KS_SC + k);
         // stage 1: forward pass over the 27-sample odd extension from the state after x[n-1] (sosfiltfilt's forward pass), then
         // the backward pass back over it from zi * (last forward output); the zero-extended stream has there the backward
         // pass's state after the forward ringing instead (U s_c)
@@ -403,7 +429,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
         dcx s2k[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            s2k[k] = ld(16 + 2 * ET_NPTS + k);
+            s2k[k] = ld(KS_S2 + k);
             st.z[k].x += s2k[k].x; st.z[k].y += s2k[k].y;
         }
         dcx y2e[EX_PAD2];
@@ -411,7 +437,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
             dcx zpe[ET_NPTS];
             dcx rot = rot_at(L - 1);
             for (int t = 0; t < ET_NPTS; ++t) {
-                const dcx p = cmul(ld(16 + t), rot);
+                const dcx p = cmul(ld(KS_PTR + t), rot);
                 zpe[t] = dcx{p.x + d1s[t].x, p.y + d1s[t].y};
                 rot = cmul(rot, rstep_c);
             }
@@ -447,13 +473,13 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll 4
         for (int t = 0; t < K_EDGE; ++t) {
             const dcx v = kc_ba_step(st, cf, t < ET_TD ? ydl[t] : dcx{0.0, 0.0});
-            dr[t] = make_float2((float)v.x, (float)v.y);
+            if (mr) mr[t] = v.x; else dr[t] = make_float2((float)v.x, (float)v.y);
         }
     } else {
         // ================= left end =================
         dcx sac[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sac[k] = ld(8 + k);
+        for (int k = 0; k < 8; ++k) sac[k] = ld(KS_SAC + k);
         // stage 1: the exact forward state at position 0 -- zi * ext[0], then the 27 odd-extension samples (positions -27 .. -1);
         // the zero-extended stream starts from a zero state
         dcx dsc[8];
@@ -488,7 +514,7 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
             dcx zpe[ET_NPTS];
             dcx rot{1.0, 0.0};
             for (int t = 0; t < ET_NPTS; ++t) {
-                const dcx p = cmul(ld(16 + ET_NPTS + t), rot);
+                const dcx p = cmul(ld(KS_PTL + t), rot);
                 zpe[t] = dcx{p.x + dy[t].x, p.y + dy[t].y};
                 rot = cmul(rot, rstep);
             }
@@ -530,9 +556,46 @@ __global__ void __launch_bounds__(KC2_THREADS) k_edge_recursions(const EdgeCorrA
 #pragma unroll 4
         for (int m = K_EDGE - 1; m >= 0; --m) {
             const dcx v = kc_ba_step(sb, cf, dy[m]);
-            dl[m] = make_float2((float)v.x, (float)v.y);
+            if (ml) ml[m] = v.x; else dl[m] = make_float2((float)v.x, (float)v.y);
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// k_edge_apply (freq_offset = 0): D = M s. blockIdx.y = the end; a CTA takes KA_CPB carriers, thread t the output t of each:
+// a row of M is read once per CTA (coalesced over t) and meets the carriers' states from shared memory.
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KA_THREADS) k_edge_apply(const EdgeCorrArgs a) {
+    __shared__ double2 s_st[KA_CPB][KS_NR];
+    const int e = blockIdx.y;                                  // 0 left, 1 right
+    const int base = e ? 0 : KS_NR, nk = e ? KS_NR : KS_NL;
+    const int c0 = blockIdx.x * KA_CPB;
+    for (int i = threadIdx.x; i < KA_CPB * nk; i += KA_THREADS) {
+        const int c = i / nk, k = i - c * nk;
+        s_st[c][k] = c0 + c < a.n_carriers ? a.states[(int64_t)(c0 + c) * KC_NSTATE + base + k] : make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    const int t = threadIdx.x;
+    if (t >= K_EDGE) return;
+    double ax[KA_CPB], ay[KA_CPB];
+#pragma unroll
+    for (int c = 0; c < KA_CPB; ++c) ax[c] = ay[c] = 0.0;
+    const double* __restrict__ mp = a.m + ((int64_t)base * 2 + e) * K_EDGE + t;
+#pragma unroll 4
+    for (int k = 0; k < nk; ++k) {
+        const double w = __ldg(mp + (int64_t)k * 2 * K_EDGE);
+#pragma unroll
+        for (int c = 0; c < KA_CPB; ++c) { ax[c] += w * s_st[c][k].x; ay[c] += w * s_st[c][k].y; }
+    }
+#pragma unroll
+    for (int c = 0; c < KA_CPB; ++c)
+        if (c0 + c < a.n_carriers) a.d[((int64_t)(c0 + c) * 2 + e) * K_EDGE + t] = make_float2((float)ax[c], (float)ay[c]);
+}
+
+// unit states for the M build: carrier k holds state k = 1
+__global__ void k_edge_unit_states(double2* st) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < KC_NSTATE * KC_NSTATE) st[i] = make_double2((i / KC_NSTATE) == (i % KC_NSTATE) ? 1.0 : 0.0, 0.0);
 }
 
 }  // namespace tetra

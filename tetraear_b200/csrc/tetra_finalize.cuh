@@ -36,6 +36,7 @@ struct FinArgs {
     int32_t* sync_pos;       // [C][max_pos] or null: sync positions of decode()'s cascade (decoder.py:845-856)
     int32_t max_pos;
     int32_t* n_sync;         // [C]
+    int32_t car0;            // first carrier of this launch (block b works on carrier car0 + b)
 };
 
 constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22 (decoder.py:196-197)
@@ -351,7 +352,7 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
 
 __global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
     __shared__ FinSmem sm;
-    finalize_carrier(a, blockIdx.x, sm);
+    finalize_carrier(a, a.car0 + blockIdx.x, sm);
 }
 
 // standalone: sync positions from dibit streams (the same device code; used when the streams come from elsewhere)

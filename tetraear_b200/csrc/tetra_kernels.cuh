@@ -164,7 +164,8 @@ struct K1Args {
     int32_t L;              // ceil(n/10)
     int32_t seg_len;        // y samples per segment (multiple of 640)
     int32_t n_seg;          // segments per carrier
-    int32_t n_items;        // carriers * n_seg work items
+    int32_t n_items;        // work items (carrier, segment) of THIS launch
+    int32_t item0;          // first work item of this launch (a batch may be cut into several launches, tetra_b200.cu)
     int32_t t_item;         // tiles per item = seg_len / 640 + 1 (pre-roll + post-roll)
     float2* y;              // [C][y_pitch], timing-phase major: y[(n % 13) * y_rows + n / 13]
     int64_t y_pitch;
@@ -243,7 +244,7 @@ struct K1Slot {
     int car, n_lo, n_hi, O;   // carrier, segment range in y samples, local origin O = n_lo - PREROLL
 };
 __device__ __forceinline__ K1Slot k1_slot(const K1Args& a, int q) {
-    const int it = blockIdx.x + q * gridDim.x;
+    const int it = a.item0 + blockIdx.x + q * gridDim.x;
     K1Slot sl;
     sl.car = it / a.n_seg;
     const int seg = it - sl.car * a.n_seg;
@@ -691,7 +692,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (ld < K1_NPH) {
                 double t = 0.0;
                 for (int j = 0; j < K1_DLANES; ++j) t += s.bins[ld][j];
-                a.partial[((int64_t)blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
+                a.partial[((int64_t)a.item0 + blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
             }
             asm volatile("bar.sync 2, 64;" ::: "memory");
 #pragma unroll

@@ -40,6 +40,11 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) * 1e3 / reps
 
+    only = [t for t in os.environ.get("TETRA_CONFIGS", "").split(",") if t]      # e.g. TETRA_CONFIGS=3 under ncu
+
+    def want(tag):
+        return not only or tag in only
+
     # ---- config 2: one carrier, 2^20 samples, device-resident (latency-bound) ----
     n = 1 << 20
     cap = sp.dibit_capacity(n)
@@ -49,98 +54,103 @@ def main():
     sym = torch.zeros((1, cap + 1, 2), dtype=torch.float32, device=dev)
     mt = torch.zeros((1, 2 * cap, 2), dtype=torch.uint8, device=dev)
     ph = torch.zeros(1, dtype=torch.int32, device=dev)
-    for name, fo in (("config2_one_carrier_fo0", None), ("config2_one_carrier_fo1234.5", [1234.5])):
+    for name, fo in (("config2_one_carrier_fo0", None), ("config2_one_carrier_fo1234.5", [1234.5])) if want("2") else ():
         ms, wall = timed(lambda: sp.process_batch_device(x.data_ptr(), 1, n, n, dib.data_ptr(), cap, nd.data_ptr(), sym.data_ptr(),
                                                          ph.data_ptr(), mt.data_ptr(), stream=0, freq_offsets=fo))
         out[name] = {"ms_per_block": ms, "host_wall_ms": wall, "MS_per_s": n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3)}
-    hx = synth.carrier_iq(n, 0, snr_db=30.0)
-    t0 = time.perf_counter()
-    for _ in range(10):
+    if want("2"):
+        hx = synth.carrier_iq(n, 0, snr_db=30.0)
         sp.process(hx)
-    out["config2_process_host_call_ms"] = (time.perf_counter() - t0) * 100
+        t0 = time.perf_counter()
+        for _ in range(10):
+            sp.process(hx)
+        out["config2_process_host_call_ms"] = (time.perf_counter() - t0) * 100
 
-    # ---- config 3: 96 channels of one 2^20-sample wideband capture ----
-    xw, active, freqs = synth.wideband_capture(n, seed=3)
-    t0 = time.perf_counter()
-    reps = 5
-    sp.process_wideband(xw, freqs, want_symbols=True, want_match=True)
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    if want("3"):
+        # ---- config 3: 96 channels of one 2^20-sample wideband capture ----
+        xw, active, freqs = synth.wideband_capture(n, seed=3)
+        t0 = time.perf_counter()
+        reps = 5
         sp.process_wideband(xw, freqs, want_symbols=True, want_match=True)
-    wall = (time.perf_counter() - t0) / reps
-    out["config3_wideband_96ch"] = {"host_call_ms": wall * 1e3, "wideband_MS_per_s": n / wall / 1e6, "channel_MS_per_s": 96 * n / wall / 1e6,
-                                    "x_real_time": (n / 2.4e6) / wall, "note": "host capture in, host dibits/symbols/match out (PCIe + 96 result rows inside)"}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            sp.process_wideband(xw, freqs, want_symbols=True, want_match=True)
+        wall = (time.perf_counter() - t0) / reps
+        out["config3_wideband_96ch"] = {"host_call_ms": wall * 1e3, "wideband_MS_per_s": n / wall / 1e6, "channel_MS_per_s": 96 * n / wall / 1e6,
+                                        "x_real_time": (n / 2.4e6) / wall, "note": "host capture in, host dibits/symbols/match out (PCIe + 96 result rows inside)"}
 
-    # device-resident variant: capture and every output already in HBM
-    xw_d = torch.view_as_real(torch.from_numpy(xw).to(dev)).contiguous()
-    fr = np.ascontiguousarray(freqs, dtype=np.float64)
-    dib3 = torch.zeros((96, cap), dtype=torch.uint8, device=dev)
-    nd3 = torch.zeros(96, dtype=torch.int32, device=dev)
-    sym3 = torch.zeros((96, cap + 1, 2), dtype=torch.float32, device=dev)
-    ph3 = torch.zeros(96, dtype=torch.int32, device=dev)
-    mt3 = torch.zeros((96, 2 * cap, 2), dtype=torch.uint8, device=dev)
-    sp._lib.tetra_set_stream(sp._ctx, 1)
-    ms, wall = timed(lambda: sp._lib.tetra_process_wideband(sp._ctx, xw_d.data_ptr(), n, fr.ctypes.data, 96, dib3.data_ptr(), cap,
-                                                            nd3.data_ptr(), sym3.data_ptr(), ph3.data_ptr(), mt3.data_ptr()), reps=10)
-    sp._lib.tetra_set_stream(sp._ctx, None)
-    # fp32 work of the per-channel stages (FFMA2 per input sample: proto 4.1 [x2 with modulated complex taps],
-    # half-band 0.65, fir120 6.4, interpolation 0.8) against the measured FFMA2 issue peak (tools/microbench/pipes.cu:
-    # 0.5 warp instructions per clock and SM sub-partition)
-    pfb_on = os.environ.get("TETRA_PFB", "1") != "0"
-    ffma2_per_sample = (0.65 + 6.4 + 0.8) if pfb_on else (2 * 4.1 + 0.65 + 6.4 + 0.8)
-    ffma2_peak = 148 * 4 * 0.5 * 32 * 1.965e9
-    out["config3_wideband_96ch_device_resident"] = {"ms_per_capture": ms, "wideband_MS_per_s": n / ms / 1e3,
-                                                    "channel_MS_per_s": 96 * n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3),
-                                                    "front_end": "k_pfb96 polyphase DFT + MODE 5" if pfb_on else "per-channel modulated proto (MODE 2)",
-                                                    "ffma2_lane_ops_per_capture": 96 * n * ffma2_per_sample,
-                                                    "fp32_pipe_utilisation": 96 * n * ffma2_per_sample / (ms * 1e-3) / ffma2_peak,
-                                                    }
+        # device-resident variant: capture and every output already in HBM
+        xw_d = torch.view_as_real(torch.from_numpy(xw).to(dev)).contiguous()
+        fr = np.ascontiguousarray(freqs, dtype=np.float64)
+        dib3 = torch.zeros((96, cap), dtype=torch.uint8, device=dev)
+        nd3 = torch.zeros(96, dtype=torch.int32, device=dev)
+        sym3 = torch.zeros((96, cap + 1, 2), dtype=torch.float32, device=dev)
+        ph3 = torch.zeros(96, dtype=torch.int32, device=dev)
+        mt3 = torch.zeros((96, 2 * cap, 2), dtype=torch.uint8, device=dev)
+        sp._lib.tetra_set_stream(sp._ctx, 1)
+        ms, wall = timed(lambda: sp._lib.tetra_process_wideband(sp._ctx, xw_d.data_ptr(), n, fr.ctypes.data, 96, dib3.data_ptr(), cap,
+                                                                nd3.data_ptr(), sym3.data_ptr(), ph3.data_ptr(), mt3.data_ptr()), reps=10)
+        sp._lib.tetra_set_stream(sp._ctx, None)
+        # fp32 work of the per-channel stages (FFMA2 per input sample: proto 4.1 [x2 with modulated complex taps],
+        # half-band 0.65, fir120 6.4, interpolation 0.8) against the measured FFMA2 issue peak (tools/microbench/pipes.cu:
+        # 0.5 warp instructions per clock and SM sub-partition)
+        pfb_on = os.environ.get("TETRA_PFB", "1") != "0"
+        ffma2_per_sample = (0.65 + 6.4 + 0.8) if pfb_on else (2 * 4.1 + 0.65 + 6.4 + 0.8)
+        ffma2_peak = 148 * 4 * 0.5 * 32 * 1.965e9
+        out["config3_wideband_96ch_device_resident"] = {"ms_per_capture": ms, "wideband_MS_per_s": n / ms / 1e3,
+                                                        "channel_MS_per_s": 96 * n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3),
+                                                        "front_end": "k_pfb96 polyphase DFT + MODE 5" if pfb_on else "per-channel modulated proto (MODE 2)",
+                                                        "ffma2_lane_ops_per_capture": 96 * n * ffma2_per_sample,
+                                                        "fp32_pipe_utilisation": 96 * n * ffma2_per_sample / (ms * 1e-3) / ffma2_peak,
+                                                        }
 
-    # ---- RTL-SDR bytes, device-resident, the configs[3] batch (4096 carriers x 2^20 samples at 2 B/sample) ----
-    cu = int(os.environ.get("TETRA_U8_CARRIERS", "4096"))
-    g = torch.Generator(device=dev); g.manual_seed(7)
-    raw = torch.randint(0, 256, (cu, n, 2), dtype=torch.uint8, device=dev, generator=g)     # timing only: any bytes will do
-    dib8 = torch.zeros((cu, cap), dtype=torch.uint8, device=dev)
-    nd8 = torch.zeros(cu, dtype=torch.int32, device=dev)
-    sym8 = torch.zeros((cu, cap + 1, 2), dtype=torch.float32, device=dev)
-    ph8 = torch.zeros(cu, dtype=torch.int32, device=dev)
-    mt8 = torch.zeros((cu, 2 * cap, 2), dtype=torch.uint8, device=dev)
-    sp._lib.tetra_set_stream(sp._ctx, 1)
-    sp._lib.tetra_enable_kernel_timing(sp._ctx, 1)
-    ms, wall = timed(lambda: sp._lib.tetra_process_batch_u8(sp._ctx, raw.data_ptr(), cu, n, n, None, dib8.data_ptr(), cap, nd8.data_ptr(),
-                                                            sym8.data_ptr(), ph8.data_ptr(), mt8.data_ptr(), None, 0, None), reps=5)
-    k1_ms = sp.kernel_time_ms()
-    sp._lib.tetra_enable_kernel_timing(sp._ctx, 0)
-    sp._lib.tetra_set_stream(sp._ctx, None)
-    out["u8_ingest_device_resident"] = {"carriers": cu, "ms_per_batch": ms, "MS_per_s": cu * n / ms / 1e3, "fused_kernel_ms": k1_ms[0] / max(k1_ms[1], 1),
-                                        "GB_per_s_at_2.1B_per_sample": 2.1 * cu * n / (ms * 1e-3) / 1e9,
-                                        "note": "2 B/sample read + the outputs' 0.1 B/sample; the fused kernel converts its tiles in shared memory"}
-    del raw, dib8, sym8, mt8
+    if want("u8"):
+        # ---- RTL-SDR bytes, device-resident, the configs[3] batch (4096 carriers x 2^20 samples at 2 B/sample) ----
+        cu = int(os.environ.get("TETRA_U8_CARRIERS", "4096"))
+        g = torch.Generator(device=dev); g.manual_seed(7)
+        raw = torch.randint(0, 256, (cu, n, 2), dtype=torch.uint8, device=dev, generator=g)     # timing only: any bytes will do
+        dib8 = torch.zeros((cu, cap), dtype=torch.uint8, device=dev)
+        nd8 = torch.zeros(cu, dtype=torch.int32, device=dev)
+        sym8 = torch.zeros((cu, cap + 1, 2), dtype=torch.float32, device=dev)
+        ph8 = torch.zeros(cu, dtype=torch.int32, device=dev)
+        mt8 = torch.zeros((cu, 2 * cap, 2), dtype=torch.uint8, device=dev)
+        sp._lib.tetra_set_stream(sp._ctx, 1)
+        sp._lib.tetra_enable_kernel_timing(sp._ctx, 1)
+        ms, wall = timed(lambda: sp._lib.tetra_process_batch_u8(sp._ctx, raw.data_ptr(), cu, n, n, None, dib8.data_ptr(), cap, nd8.data_ptr(),
+                                                                sym8.data_ptr(), ph8.data_ptr(), mt8.data_ptr(), None, 0, None), reps=5)
+        k1_ms = sp.kernel_time_ms()
+        sp._lib.tetra_enable_kernel_timing(sp._ctx, 0)
+        sp._lib.tetra_set_stream(sp._ctx, None)
+        out["u8_ingest_device_resident"] = {"carriers": cu, "ms_per_batch": ms, "MS_per_s": cu * n / ms / 1e3, "fused_kernel_ms": k1_ms[0] / max(k1_ms[1], 1),
+                                            "GB_per_s_at_2.1B_per_sample": 2.1 * cu * n / (ms * 1e-3) / 1e9,
+                                            "note": "2 B/sample read + the outputs' 0.1 B/sample; the fused kernel converts its tiles in shared memory"}
+        del raw, dib8, sym8, mt8
 
-    # ---- config 5: waterfall STFT 4096 / hop 1024 on 1 s of IQ, device-resident ----
-    ns = 2_400_000
-    xs = torch.view_as_real(torch.from_numpy(synth.stft_test_signal(ns, 5)).to(dev)).contiguous()
-    rows = (ns - 4096) // 1024 + 1
-    o = torch.zeros((rows, 4096), dtype=torch.float32, device=dev)
-    import ctypes as C
-    r64 = C.c_int64(0)
-    ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xs.data_ptr(), ns, 4096, 1024, o.data_ptr(), C.byref(r64)), reps=50)
-    by = 24.0 * ns
-    out["config5_stft_4096_hop1024"] = {"ms_per_second_of_iq": ms, "rows_per_s": rows / (ms * 1e-3), "MS_per_s": ns / ms / 1e3,
-                                        "x_real_time": 1e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
-                                        "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak, "frames_at_60fps_rows": rows / 60.0}
-    # the same on 30 s of IQ in one call: the per-call launch + synchronise cost (tens of microseconds) no longer shows
-    reps30 = 30
-    xl = xs.repeat(reps30, 1)
-    nl = ns * reps30
-    rows_l = (nl - 4096) // 1024 + 1
-    ol = torch.zeros((rows_l, 4096), dtype=torch.float32, device=dev)
-    ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xl.data_ptr(), nl, 4096, 1024, ol.data_ptr(), C.byref(r64)), reps=10)
-    by = 24.0 * nl
-    out["config5_stft_4096_hop1024_30s"] = {"ms_per_call": ms, "rows_per_s": rows_l / (ms * 1e-3), "MS_per_s": nl / ms / 1e3,
-                                            "x_real_time": 30e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
-                                            "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak}
+    if want("5"):
+        # ---- config 5: waterfall STFT 4096 / hop 1024 on 1 s of IQ, device-resident ----
+        ns = 2_400_000
+        xs = torch.view_as_real(torch.from_numpy(synth.stft_test_signal(ns, 5)).to(dev)).contiguous()
+        rows = (ns - 4096) // 1024 + 1
+        o = torch.zeros((rows, 4096), dtype=torch.float32, device=dev)
+        import ctypes as C
+        r64 = C.c_int64(0)
+        ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xs.data_ptr(), ns, 4096, 1024, o.data_ptr(), C.byref(r64)), reps=50)
+        by = 24.0 * ns
+        out["config5_stft_4096_hop1024"] = {"ms_per_second_of_iq": ms, "rows_per_s": rows / (ms * 1e-3), "MS_per_s": ns / ms / 1e3,
+                                            "x_real_time": 1e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
+                                            "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak, "frames_at_60fps_rows": rows / 60.0}
+        # the same on 30 s of IQ in one call: the per-call launch + synchronise cost (tens of microseconds) no longer shows
+        reps30 = 30
+        xl = xs.repeat(reps30, 1)
+        nl = ns * reps30
+        rows_l = (nl - 4096) // 1024 + 1
+        ol = torch.zeros((rows_l, 4096), dtype=torch.float32, device=dev)
+        ms, wall = timed(lambda: sp._lib.tetra_stft_db(sp._ctx, xl.data_ptr(), nl, 4096, 1024, ol.data_ptr(), C.byref(r64)), reps=10)
+        by = 24.0 * nl
+        out["config5_stft_4096_hop1024_30s"] = {"ms_per_call": ms, "rows_per_s": rows_l / (ms * 1e-3), "MS_per_s": nl / ms / 1e3,
+                                                "x_real_time": 30e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
+                                                "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak}
     print(json.dumps(out, indent=1))
     sp.close()
 
