@@ -243,7 +243,18 @@ def run_ours(a):
     cap = sp.dibit_capacity(N_SAMPLES)
 
     x, base_d = make_inputs(torch, dev, n_local, first_carrier)
-    packed = shard.PackedStreams(total, cap, device=dev, packer=sp) if total % world == 0 else None
+    # the exchange: the library's own two kernels over NVLink peer memory (default), or pack -> ncclAllGather -> unpack
+    transport = a.gather
+    packed = None
+    if total % world == 0:
+        try:
+            packed = shard.PackedStreams(total, cap, device=dev, packer=sp, transport=transport)
+        except Exception as e:                                # no CUDA IPC on this box: say so and use NCCL
+            if transport != "p2p":
+                raise
+            sys.stderr.write("bench.py: peer-memory exchange unavailable (%s); using NCCL\n" % e)
+            transport = "nccl"
+            packed = shard.PackedStreams(total, cap, device=dev, packer=sp, transport="nccl")
     if packed is not None:                                    # dibits + lengths in one buffer: ONE all-gather per step
         dib, nd, cap_row = packed.dibits, packed.n_dibits, packed.cap
     else:
@@ -269,7 +280,7 @@ def run_ours(a):
                                 sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream, freq_offsets=fos)
         if world > 1:
             if packed is not None:
-                packed.gather()                                       # 2-bit pack, one NCCL all-gather, unpack
+                packed.gather()                                       # 2-bit pack + exchange + unpack
             else:
                 shard.gather_dibits(dib, nd, total, all_dib, all_nd)
 
@@ -327,7 +338,9 @@ def run_ours(a):
     gather_parity = None
     if world > 1 and packed is not None and rank == 0 and fos is None:
         from oracle import ref_dsp
-        g_dib, g_nd = packed.out, packed.all.view(world, packed.block)[:, packed.packed_bytes:].view(torch.int32)
+        # what the last timed step left on rank 0
+        g_dib = packed.out
+        g_nd = packed.out_n if transport == "p2p" else packed.all.view(world, packed.block)[:, packed.packed_bytes:].view(torch.int32)
         tmp = torch.empty((N_SAMPLES, 2), dtype=torch.float32, device=dev)
         gen = torch.Generator(device=dev)
         snr = carrier_snr_db()
@@ -341,6 +354,7 @@ def run_ours(a):
             ok &= n_i == len(ref["dibits"]) and bool(np.array_equal(g_dib[r, i_r, :n_i].cpu().numpy(), ref["dibits"]))
             checked.append(f_r + i_r)
         gather_parity = {"ok": bool(ok), "carriers_checked": checked,
+                         "transport": transport, "p2p_status": sp.p2p_status() if transport == "p2p" else None,
                          "what": "dibits of one carrier per remote rank, read from rank 0's all-gather output, vs the oracle"}
 
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region ----
@@ -444,6 +458,8 @@ def main():
     ap.add_argument("--carriers", type=int, default=TOTAL_CARRIERS)
     ap.add_argument("--e2e-carriers", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange of the dibit streams -- the library's peer-memory kernels (default) or NCCL all-gather")
     ap.add_argument("--fo-max", type=float, default=0.0, help="per-carrier freq_offset drawn from +-this (Hz); 0 = BASELINE workload")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the fused kernel from an ncu --set full capture (profiles/), if known")

@@ -99,6 +99,34 @@ int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t n_carriers
 int tetra_pack_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, uint8_t* packed);
 int tetra_unpack_dibits(tetra_ctx* ctx, const uint8_t* packed, int64_t n_blocks, int64_t packed_bytes, int64_t in_stride,
                         uint8_t* dibits, int64_t out_stride);
+
+/*
+ * The one exchange of the sharded path (SURVEY.md 8b proposed tetra_allgather_dibits; BASELINE north star: "a single
+ * all-gather of decoded dibit streams over NVLink"; downstream of it is the reference's own TetraDecoder.decode(symbols),
+ * tetraear/core/decoder.py:835, on every rank) -- without NCCL or torch: two kernels over NVLink peer memory. Every rank
+ * (one process per GPU, or one context per GPU inside a process; world <= 8, one node) owns a receive buffer:
+ *   tetra_p2p_create      allocates it for blocks of block_bytes per rank (>= n / 4 + 4 * n_local, a multiple of 16) and
+ *                         writes its CUDA IPC handle (TETRA_IPC_HANDLE_BYTES) to handle_out (may be NULL);
+ *   tetra_p2p_connect     takes the handles of all ranks, [world][TETRA_IPC_HANDLE_BYTES] in rank order (exchanged by the
+ *                         caller by any means: torch.distributed, MPI, a file), and opens the peers' buffers;
+ *   tetra_p2p_connect_ptrs  the same for contexts of ONE process: buffers[r] = tetra_p2p_buffer(ctx of rank r);
+ *   tetra_allgather_dibits  asynchronous on the context's stream: packs dibits[n] (n = n_local * cap, cap % 16 == 0, values
+ *                         0..3) four to a byte, stores the words and the n_local lengths into every peer's buffer, raises
+ *                         this step's flag there, waits for the peers' flags and unpacks into all_dibits [world][n] and
+ *                         all_n [world][n_local] (may be NULL). Device buffers only. Every rank must call it the same
+ *                         number of times. A peer that does not show up within ~3 s is reported by tetra_p2p_status
+ *                         (status = 1 + its rank; 0 = fine) instead of hanging the GPU.
+ */
+#define TETRA_IPC_HANDLE_BYTES 64
+int tetra_p2p_create(tetra_ctx* ctx, int32_t rank, int32_t world, int64_t block_bytes, uint8_t* handle_out);
+void* tetra_p2p_buffer(tetra_ctx* ctx);
+int tetra_p2p_connect(tetra_ctx* ctx, const uint8_t* handles);
+int tetra_p2p_connect_ptrs(tetra_ctx* ctx, void* const* buffers);
+int tetra_allgather_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, const int32_t* n_dibits, int32_t n_local,
+                           uint8_t* all_dibits, int32_t* all_n);
+int tetra_p2p_status(tetra_ctx* ctx, int32_t* status);
+int tetra_p2p_destroy(tetra_ctx* ctx);
+
 /* The same cascade for dibit streams that are already there ([C][cap] uint8 + lengths; host or device). */
 int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits,
                          int32_t n_carriers, int32_t* sync_pos, int32_t max_positions, int32_t* n_sync);

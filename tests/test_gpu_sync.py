@@ -148,3 +148,38 @@ def test_transport_packing_kernels_match_host_form(gpu_processor):
     sp.synchronize()
     assert torch.equal(out, d)
     assert torch.equal(wire.view(world, block)[0, : n_local * cap // 4].cpu(), shard._pack_cpu(d[0].cpu()))
+
+
+@pytest.mark.parametrize("world,n_local,cap", [(1, 3, 48), (2, 5, 8080), (4, 2, 64)])
+def test_peer_memory_allgather_between_contexts_of_one_gpu(world, n_local, cap):
+    """tetra_allgather_dibits with `world` contexts ("ranks") on one device, their receive buffers handed over as plain
+    pointers (tetra_p2p_connect_ptrs): every rank ends with every rank's streams and lengths, over several steps (both
+    halves of the double buffer, flags reused). The multi-process form (CUDA IPC) runs in bench.py --gpus N."""
+    import torch
+    from tetraear_b200.processor import SignalProcessor
+    rng = np.random.default_rng(12)
+    sps = [SignalProcessor(2.4e6) for _ in range(world)]
+    try:
+        n = n_local * cap
+        block = (n // 4 + 4 * n_local + 15) & ~15
+        for r, sp in enumerate(sps):
+            assert len(sp.p2p_create(r, world, block)) == 64
+        bufs = [sp.p2p_buffer() for sp in sps]
+        for sp in sps:
+            sp.p2p_connect_ptrs(bufs)
+        outs = [torch.zeros((world, n_local, cap), dtype=torch.uint8, device="cuda") for _ in range(world)]
+        out_ns = [torch.zeros((world, n_local), dtype=torch.int32, device="cuda") for _ in range(world)]
+        for step in range(5):
+            d = torch.from_numpy(rng.integers(0, 4, size=(world, n_local, cap), dtype=np.uint8)).cuda()
+            nd = torch.from_numpy(rng.integers(0, cap, size=(world, n_local)).astype(np.int32)).cuda()
+            torch.cuda.synchronize()
+            # ranks of one process: every context has its own stream, so a rank's wait overlaps the others' pushes
+            for r, sp in enumerate(sps):
+                sp.allgather_dibits_device(d[r].data_ptr(), n, nd[r].data_ptr(), n_local, outs[r].data_ptr(), out_ns[r].data_ptr())
+            for r, sp in enumerate(sps):
+                sp.synchronize()
+                assert sp.p2p_status() == 0
+                assert torch.equal(outs[r], d) and torch.equal(out_ns[r], nd), (step, r)
+    finally:
+        for sp in sps:
+            sp.close()

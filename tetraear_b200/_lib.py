@@ -37,6 +37,13 @@ _SIGS = {
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tetra_pack_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "tetra_unpack_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
+    "tetra_p2p_create": (C.c_int, [c_ctx_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p]),
+    "tetra_p2p_buffer": (C.c_void_p, [c_ctx_p]),
+    "tetra_p2p_connect": (C.c_int, [c_ctx_p, C.c_void_p]),
+    "tetra_p2p_connect_ptrs": (C.c_int, [c_ctx_p, C.c_void_p]),
+    "tetra_allgather_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tetra_p2p_status": (C.c_int, [c_ctx_p, C.POINTER(C.c_int32)]),
+    "tetra_p2p_destroy": (C.c_int, [c_ctx_p]),
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),
     "tetra_enable_kernel_timing": (C.c_int, [c_ctx_p, C.c_int]),
     "tetra_kernel_time_ms": (C.c_double, [c_ctx_p, C.POINTER(C.c_int32)]),
@@ -56,6 +63,7 @@ _SIGS = {
     "tetra_design_cheby1_sos8": (C.c_int, [C.c_double, C.c_double, C.c_void_p]),
 }
 
+IPC_HANDLE_BYTES = 64            # TETRA_IPC_HANDLE_BYTES
 EXPORTS = tuple(_SIGS)
 
 

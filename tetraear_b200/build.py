@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libtetra_b200.so")
 SOURCES = ["tetra_b200.cu"]
-HEADERS = ["tetra_kernels.cuh", "tetra_exact.cuh", "tetra_edges.cuh", "tetra_edgecorr.cuh", "tetra_finalize.cuh", "tetra_stft.cuh",
+HEADERS = ["tetra_kernels.cuh", "tetra_exact.cuh", "tetra_edges.cuh", "tetra_edgecorr.cuh", "tetra_finalize.cuh", "tetra_stft.cuh", "tetra_gather.cuh", "tetra_pfb.cuh",
            "filter_design.h", "taps_generated.h", "edge_tables_generated.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

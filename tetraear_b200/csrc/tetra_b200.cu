@@ -28,6 +28,7 @@
 #include "tetra_pfb.cuh"
 #include "tetra_finalize.cuh"
 #include "tetra_stft.cuh"
+#include "tetra_gather.cuh"
 
 using namespace tetra;
 static_assert(K1_EDGE == K_EDGE, "edge width of the fused and the exact kernels must agree");
@@ -79,6 +80,14 @@ struct tetra_ctx {
     std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
     int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
     size_t max_scratch_bytes = (size_t)6 << 30;
+    // peer-memory all-gather (tetra_gather.cuh)
+    DevBuf p2p_buf, p2p_misc;          // receive buffer [2][world][block] + flags; ticket + status words
+    uint8_t* p2p_peer[KG_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool p2p_ipc[KG_MAX_WORLD] = {false, false, false, false, false, false, false, false};   // opened with cudaIpcOpenMemHandle
+    int p2p_rank = -1, p2p_world = 0;
+    int64_t p2p_block = 0, p2p_flag_off = 0;
+    uint32_t p2p_step = 0;
+    bool p2p_connected = false;
 };
 
 namespace {
@@ -436,6 +445,7 @@ void tetra_destroy(tetra_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->in, &ctx->y, &ctx->partial, &ctx->dib, &ctx->ndib, &ctx->sym, &ctx->phase, &ctx->match,
                       &ctx->fo, &ctx->jobs, &ctx->scr1, &ctx->scrz, &ctx->scr2, &ctx->tmp_a, &ctx->tmp_b, &ctx->tmp_c, &ctx->mats, &ctx->wide, &ctx->spos, &ctx->u8, &ctx->stft_tab,
                       &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->pfb};
+    tetra_p2p_destroy(ctx);
     for (DevBuf* b : bufs) b->release();
     for (DevBuf& b : ctx->emat) b.release();
     ctx->emat_unit.release();
@@ -1361,6 +1371,130 @@ int tetra_edge_corrections(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N
     if (rc) return rc;
     CK(cudaMemcpyAsync(out, ctx->ecorr.p, (size_t)C * 2 * K_EDGE * sizeof(float2), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// peer-memory all-gather of the dibit streams (tetra_gather.cuh)
+// ------------------------------------------------------------------------------------------------
+int tetra_p2p_create(tetra_ctx* ctx, int32_t rank, int32_t world, int64_t block_bytes, uint8_t* handle_out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (world < 1 || world > KG_MAX_WORLD || rank < 0 || rank >= world || block_bytes <= 0 || (block_bytes & 15))
+        return fail(ctx, TETRA_E_INVALID, "tetra_p2p_create: 1 <= world <= %d, 0 <= rank < world, block_bytes a positive multiple of 16", KG_MAX_WORLD);
+    CK(cudaSetDevice(ctx->device));
+    tetra_p2p_destroy(ctx);
+    const int64_t flag_off = 2 * (int64_t)world * block_bytes;
+    const size_t total = (size_t)flag_off + 2 * KG_MAX_WORLD * sizeof(uint32_t);
+    CK(ctx->p2p_buf.ensure(total));
+    CK(ctx->p2p_misc.ensure(64));
+    CK(cudaMemset(ctx->p2p_buf.p, 0, total));
+    CK(cudaMemset(ctx->p2p_misc.p, 0, 64));
+    ctx->p2p_rank = rank; ctx->p2p_world = world; ctx->p2p_block = block_bytes; ctx->p2p_flag_off = flag_off; ctx->p2p_step = 0;
+    ctx->p2p_connected = false;
+    for (int r = 0; r < KG_MAX_WORLD; ++r) { ctx->p2p_peer[r] = nullptr; ctx->p2p_ipc[r] = false; }
+    ctx->p2p_peer[rank] = (uint8_t*)ctx->p2p_buf.p;
+    if (world == 1) ctx->p2p_connected = true;
+    if (handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) <= TETRA_IPC_HANDLE_BYTES, "IPC handle does not fit");
+        memset(handle_out, 0, TETRA_IPC_HANDLE_BYTES);
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, ctx->p2p_buf.p));
+        memcpy(handle_out, &h, sizeof h);
+    }
+    return TETRA_OK;
+}
+
+void* tetra_p2p_buffer(tetra_ctx* ctx) { return ctx && ctx->p2p_rank >= 0 ? ctx->p2p_buf.p : nullptr; }
+
+int tetra_p2p_connect(tetra_ctx* ctx, const uint8_t* handles) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (ctx->p2p_rank < 0 || !handles) return fail(ctx, TETRA_E_INVALID, "tetra_p2p_connect: call tetra_p2p_create first");
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->p2p_world; ++r) {
+        if (r == ctx->p2p_rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * TETRA_IPC_HANDLE_BYTES, sizeof h);
+        void* ptr = nullptr;
+        CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->p2p_peer[r] = (uint8_t*)ptr;
+        ctx->p2p_ipc[r] = true;
+    }
+    ctx->p2p_connected = true;
+    return TETRA_OK;
+}
+
+int tetra_p2p_connect_ptrs(tetra_ctx* ctx, void* const* buffers) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (ctx->p2p_rank < 0 || !buffers) return fail(ctx, TETRA_E_INVALID, "tetra_p2p_connect_ptrs: call tetra_p2p_create first");
+    CK(cudaSetDevice(ctx->device));
+    for (int r = 0; r < ctx->p2p_world; ++r) {
+        if (r == ctx->p2p_rank) continue;
+        if (!buffers[r]) return fail(ctx, TETRA_E_INVALID, "tetra_p2p_connect_ptrs: buffer of rank %d is NULL", r);
+        cudaPointerAttributes at;
+        CK(cudaPointerGetAttributes(&at, buffers[r]));
+        if (at.type != cudaMemoryTypeDevice) return fail(ctx, TETRA_E_INVALID, "tetra_p2p_connect_ptrs: rank %d's buffer is not device memory", r);
+        if (at.device != ctx->device) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CK(e);
+        }
+        ctx->p2p_peer[r] = (uint8_t*)buffers[r];
+    }
+    ctx->p2p_connected = true;
+    return TETRA_OK;
+}
+
+int tetra_allgather_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, const int32_t* n_dibits, int32_t n_local,
+                           uint8_t* all_dibits, int32_t* all_n) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (!ctx->p2p_connected) return fail(ctx, TETRA_E_INVALID, "tetra_allgather_dibits: tetra_p2p_create / tetra_p2p_connect first");
+    if (n <= 0 || (n & 15) || n_local <= 0 || !dibits || !n_dibits || !all_dibits ||
+        (reinterpret_cast<uintptr_t>(dibits) & 15) || (reinterpret_cast<uintptr_t>(all_dibits) & 15))
+        return fail(ctx, TETRA_E_INVALID, "tetra_allgather_dibits: n a positive multiple of 16, 16-byte aligned device buffers");
+    if (n / 4 + 4 * (int64_t)n_local > ctx->p2p_block)
+        return fail(ctx, TETRA_E_INVALID, "tetra_allgather_dibits: %lld bytes per rank exceed the block of %lld the exchange was created with",
+                    (long long)(n / 4 + 4 * (int64_t)n_local), (long long)ctx->p2p_block);
+    if (!is_device_ptr(dibits) || !is_device_ptr(n_dibits) || !is_device_ptr(all_dibits) || (all_n && !is_device_ptr(all_n)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_allgather_dibits: device buffers only");
+    CK(cudaSetDevice(ctx->device));
+    GatherArgs ga;
+    memset(&ga, 0, sizeof ga);
+    for (int r = 0; r < ctx->p2p_world; ++r) ga.recv[r] = ctx->p2p_peer[r];
+    ga.rank = ctx->p2p_rank; ga.world = ctx->p2p_world; ga.block = ctx->p2p_block; ga.flag_off = ctx->p2p_flag_off;
+    ga.step = ++ctx->p2p_step;
+    ga.dibits = dibits; ga.n = n; ga.n_dibits = n_dibits; ga.n_local = n_local;
+    ga.ticket = (uint32_t*)ctx->p2p_misc.p; ga.status = (int32_t*)ctx->p2p_misc.p + 4;
+    ga.out = all_dibits; ga.out_n = all_n;
+    const int64_t thr = std::max<int64_t>(n / 64, 1);
+    const unsigned g_push = (unsigned)std::max<int64_t>(1, std::min<int64_t>((thr + KG_THREADS - 1) / KG_THREADS, 148));
+    k_gather_push<<<g_push, KG_THREADS, 0, ctx->stream>>>(ga);
+    const unsigned g_un = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 16 + KG_THREADS - 1) / KG_THREADS, (148 * 4 + ga.world - 1) / ga.world));
+    k_gather_wait_unpack<<<dim3(g_un, (unsigned)ga.world), KG_THREADS, 0, ctx->stream>>>(ga);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return TETRA_OK;
+}
+
+int tetra_p2p_status(tetra_ctx* ctx, int32_t* status) {
+    if (!ctx || !status) return TETRA_E_INVALID;
+    if (ctx->p2p_rank < 0) return fail(ctx, TETRA_E_INVALID, "tetra_p2p_status: no exchange");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(status, (int32_t*)ctx->p2p_misc.p + 4, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TETRA_OK;
+}
+
+int tetra_p2p_destroy(tetra_ctx* ctx) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (ctx->p2p_rank < 0) return TETRA_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < KG_MAX_WORLD; ++r) {
+        if (ctx->p2p_ipc[r] && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_peer[r] = nullptr; ctx->p2p_ipc[r] = false;
+    }
+    ctx->p2p_buf.release(); ctx->p2p_misc.release();
+    ctx->p2p_rank = -1; ctx->p2p_world = 0; ctx->p2p_connected = false;
     return TETRA_OK;
 }
 

@@ -379,6 +379,36 @@ class SignalProcessor:
         self._check(self._lib.tetra_unpack_dibits(self._ctx, packed_ptr, n_blocks, packed_bytes, in_stride, dibits_ptr, out_stride),
                     "unpack_dibits")
 
+    # ---- peer-memory all-gather of the dibit streams (include/tetra_b200.h: tetra_p2p_*, tetra_allgather_dibits) ----
+    def p2p_create(self, rank: int, world: int, block_bytes: int) -> bytes:
+        """Allocate this rank's receive buffer; returns its CUDA IPC handle (to be exchanged with the other ranks)."""
+        h = (C.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        self._check(self._lib.tetra_p2p_create(self._ctx, rank, world, block_bytes, C.addressof(h)), "p2p_create")
+        return bytes(h)
+
+    def p2p_buffer(self) -> int:
+        return int(self._lib.tetra_p2p_buffer(self._ctx) or 0)
+
+    def p2p_connect(self, handles: bytes):
+        """`handles`: the IPC handles of all ranks, concatenated in rank order (one process per GPU)."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self._check(self._lib.tetra_p2p_connect(self._ctx, C.addressof(buf)), "p2p_connect")
+
+    def p2p_connect_ptrs(self, buffers):
+        """`buffers[r]` = ``p2p_buffer()`` of rank r's context (contexts of one process)."""
+        arr = (C.c_void_p * len(buffers))(*[C.c_void_p(int(b)) for b in buffers])
+        self._check(self._lib.tetra_p2p_connect_ptrs(self._ctx, C.addressof(arr)), "p2p_connect_ptrs")
+
+    def allgather_dibits_device(self, dibits_ptr: int, n: int, n_dibits_ptr: int, n_local: int, all_dibits_ptr: int, all_n_ptr: int = 0):
+        """Pack, push to every peer, wait, unpack: asynchronous on the context's stream (device pointers)."""
+        self._check(self._lib.tetra_allgather_dibits(self._ctx, dibits_ptr, n, n_dibits_ptr, n_local, all_dibits_ptr,
+                                                     all_n_ptr or None), "allgather_dibits")
+
+    def p2p_status(self) -> int:
+        st = C.c_int32(0)
+        self._check(self._lib.tetra_p2p_status(self._ctx, C.byref(st)), "p2p_status")
+        return int(st.value)
+
     def launch_count(self) -> int:
         return int(self._lib.tetra_launch_count(self._ctx))
 

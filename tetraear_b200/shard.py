@@ -94,8 +94,12 @@ class PackedStreams:
     ``gather()`` packs, all-gathers the buffer and unpacks every rank's block. On the GPU the packing runs in the
     library's kernels (``packer`` = the ``SignalProcessor`` whose stream the demodulation runs on)."""
 
-    def __init__(self, n_carriers: int, cap: int, device=None, group=None, packer=None):
+    def __init__(self, n_carriers: int, cap: int, device=None, group=None, packer=None, transport: str = "nccl"):
+        """transport "nccl": pack kernel -> ``all_gather_into_tensor`` -> unpack kernel (gloo on CPU tensors);
+        "p2p": the library's own exchange over NVLink peer memory (``tetra_allgather_dibits``: two kernels, no NCCL call) --
+        the ranks' receive buffers are opened with CUDA IPC, the handles travel once through ``all_gather`` here."""
         self.group = group
+        self.transport = transport
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         if n_carriers % self.world:
@@ -113,12 +117,30 @@ class PackedStreams:
             self.out = torch.zeros((self.world, self.n_local, self.cap), dtype=torch.uint8, device=device)
         if self.dibits.is_cuda and packer is None and self.world > 1:
             raise ValueError("PackedStreams on a GPU needs the SignalProcessor as packer")
+        if transport not in ("nccl", "p2p"):
+            raise ValueError("transport must be 'nccl' or 'p2p'")
+        if transport == "p2p" and self.world > 1:
+            if not self.dibits.is_cuda:
+                raise ValueError("the peer-memory exchange needs device tensors")
+            self.out_n = torch.zeros((self.world, self.n_local), dtype=torch.int32, device=device)
+            block = (self.block + 15) & ~15
+            handle = packer.p2p_create(self.rank, self.world, block)
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=device)
+            every = torch.zeros(self.world * len(handle), dtype=torch.uint8, device=device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            packer.p2p_connect(bytes(every.cpu().tolist()))
+            dist.barrier(group=group)                      # nobody pushes before every rank has opened every buffer
 
     def gather(self):
         """Pack, one all-gather, unpack. Returns dibits ``[world, n_local, cap]`` (carrier c is
         ``[c // n_local, c % n_local]``) and lengths ``[world, n_local]``."""
         if self.world == 1:
             return self.dibits.unsqueeze(0), self.n_dibits.unsqueeze(0)
+        if self.transport == "p2p":
+            self.packer.set_stream(torch.cuda.current_stream(self.dibits.device).cuda_stream)
+            self.packer.allgather_dibits_device(self.dibits.data_ptr(), self.n_local * self.cap, self.n_dibits.data_ptr(), self.n_local,
+                                                self.out.data_ptr(), self.out_n.data_ptr())
+            return self.out, self.out_n
         if self.dibits.is_cuda:
             # the library's pack / unpack kernels and the collective must be ordered on ONE stream: torch's current one
             self.packer.set_stream(torch.cuda.current_stream(self.dibits.device).cuda_stream)
