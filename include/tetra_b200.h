@@ -153,6 +153,20 @@ int tetra_parse_bursts(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, const
  */
 int tetra_analyze_signal(tetra_ctx* ctx, const float* iq, int32_t n_captures, int64_t n_samples, int64_t pitch,
                          double* out6);
+/*
+ * The scanner's sweep in one capture (signal/scanner.py:383-445 retunes the hardware in 25 kHz steps, 0.3 s each): for every
+ * channel offset f_c of ONE wideband capture, what the reference computes after tuning there -- the six numbers above on
+ * frequency_shift(iq, f_c) (processor.py:85-100; the shift is applied as a phase step, the shifted capture is never formed)
+ * and the signal-presence / AFC block of CaptureThread.run (ui/modern.py:1945-2012) on the float64 spectrum of its first
+ * nfft samples (the reference uses 2048):
+ *   out[c][6..11] = signal_power (mean dB of the centre 25 kHz), peak_power, peak_freq_offset_hz (the AFC offset handed to
+ *                   process()), noise_floor, snr, is_signal_strong (snr > 15 and peak > -70 and peak - mean > 3).
+ * out is host memory, [n_channels][TETRA_SURVEY_FIELDS] doubles (fields 12.. are zero); iq complex64 host or device.
+ * Per-channel demodulation of the same capture is tetra_process_wideband.
+ */
+#define TETRA_SURVEY_FIELDS 16
+int tetra_survey_wideband(tetra_ctx* ctx, const float* iq, int64_t n_samples, const double* channel_hz, int32_t n_channels,
+                          int32_t nfft, double* out);
 
 /*
  * tetra_process_batch_sync for RTL-SDR native samples: iq_u8 [C][pitch][2] interleaved unsigned 8-bit I, Q
@@ -231,6 +245,13 @@ int tetra_resample(tetra_ctx* ctx, const double* in, int64_t n, int64_t n_out, d
  */
 int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n_samples, int32_t nfft, int32_t hop,
                   float* out, int64_t* rows);
+/*
+ * The same in float64 on complex128 host input, float64 host rows out: the precision of the reference's own numpy FFT.
+ * SignalProcessor.spectrum() -- the once-per-chunk spectrum block, ui/modern.py:1919-1943 -- runs this one (a 2048-point
+ * row costs microseconds either way); the waterfall at throughput stays float32. nfft a power of two in [64, 4096].
+ */
+int tetra_stft_db_f64(tetra_ctx* ctx, const double* iq, int64_t n_samples, int32_t nfft, int32_t hop,
+                      double* out, int64_t* rows);
 
 /*
  * Block-end corrections of the fused 2.4 MS/s path, exposed for testing: what SciPy's sosfiltfilt / filtfilt edge

@@ -331,3 +331,52 @@ def stft_db(samples: np.ndarray, n_fft: int = 4096, hop: int = 1024) -> np.ndarr
         f = np.fft.fftshift(np.fft.fft(x[r * hop: r * hop + n_fft] * w))
         out[r] = 20 * np.log10(np.abs(f) / n_fft + 1e-20)
     return out
+
+
+def presence_afc(samples: np.ndarray, sample_rate: float, n_fft: int = 2048) -> dict:
+    """The signal-presence / AFC block of CaptureThread.run, tetraear/ui/modern.py:1919-2003, restated (the module needs
+    PyQt6 and cannot be imported here): spectrum of the first n_fft samples (:1921-1934), mean and peak of the centre
+    25 kHz (:1948-1957), the peak's frequency = the AFC offset handed to process() (:1959-1966, :2019-2022), noise floor
+    from everything more than 10 bins outside (:1968-1984), and the verdict (:1986-1999)."""
+    x = np.asarray(samples)
+    if len(x) < n_fft:
+        return dict(signal_power=0.0, peak_power=0.0, peak_freq_offset=0.0, noise_floor=0.0, snr=0.0, is_signal_strong=False)
+    power = spectrum_db(x, n_fft)
+    freqs = np.fft.fftshift(np.fft.fftfreq(n_fft, 1 / sample_rate))
+    center_idx = len(power) // 2
+    bandwidth_bins = int(25000 / (sample_rate / n_fft))
+    start_idx = max(0, center_idx - bandwidth_bins // 2)
+    end_idx = min(len(power), center_idx + bandwidth_bins // 2)
+    signal_power = np.mean(power[start_idx:end_idx])
+    peak_power = np.max(power[start_idx:end_idx])
+    peak_idx = start_idx + int(np.argmax(power[start_idx:end_idx]))
+    noise = []
+    if max(0, start_idx - 10) > 0:
+        noise.extend(power[0:max(0, start_idx - 10)])
+    if len(power) > min(len(power), end_idx + 10):
+        noise.extend(power[min(len(power), end_idx + 10):len(power)])
+    noise_floor = np.mean(noise) if noise else -100
+    snr = signal_power - noise_floor
+    strong = bool(snr > 15 and peak_power > -70 and (peak_power - signal_power) > 3)
+    return dict(signal_power=float(signal_power), peak_power=float(peak_power), peak_freq_offset=float(freqs[peak_idx]),
+                noise_floor=float(noise_floor), snr=float(snr), is_signal_strong=strong)
+
+
+def analyze_verdict(power_db, mod_conf, sync_corr, power_stable, frames_valid=False, crc_rate=0.0, bottom_threshold=-85):
+    """TetraSignalDetector.analyze_signal's combination of its detectors, tetraear/signal/scanner.py:233-289."""
+    is_mod, has_sync = mod_conf > 0.4, sync_corr > 0.75
+    if has_sync and is_mod:
+        confidence = mod_conf * 0.4 + sync_corr * 0.4 + crc_rate * 0.2
+    elif has_sync:
+        confidence = sync_corr * 0.6
+    elif is_mod:
+        confidence = mod_conf * 0.5
+    else:
+        confidence = 0.0
+    is_tetra = bool(is_mod and has_sync and power_stable)
+    if frames_valid:
+        is_tetra = True
+        confidence = max(confidence, 0.7)
+    return dict(power_db=power_db, is_tetra=is_tetra, confidence=confidence, modulation_confidence=mod_conf,
+                sync_detected=bool(has_sync), sync_correlation=sync_corr, frames_validated=bool(frames_valid),
+                crc_pass_rate=crc_rate, power_stable=bool(power_stable), signal_present=bool(power_db > bottom_threshold))

@@ -70,8 +70,14 @@ def test_config5_waterfall_rows(gpu_processor):
     # fp32 FFT: rounding noise sits ~140 dB below the strongest bin; compare down to 80 dB below it
     mask = ref > ref.max() - 80.0
     assert mask.mean() > 0.2
-    assert np.abs(rows - ref)[mask].max() < 1e-2
-    assert np.abs(rows - ref)[ref > ref.max() - 45.0].max() < 1e-3
+    err = np.abs(rows - ref)
+    print("waterfall 4096/1024, float32 FFT: max |dB error| %.3g within 45 dB of the strongest bin, %.3g within 80 dB, %.3g over all bins "
+          "(weakest bin %.1f dBFS)" % (err[ref > ref.max() - 45.0].max(), err[mask].max(), err.max(), ref.min()))
+    assert err[mask].max() < 1e-2
+    assert err[ref > ref.max() - 45.0].max() < 1e-3
+    # the float64 kernel on the first rows: the reference's precision
+    rows64 = sp.stft_db_f64(x[: 4096 + 7 * 1024], 4096, 1024)
+    assert rows64.shape == (8, 4096) and np.abs(rows64 - ref[:8]).max() < 1e-8
 
 
 @pytest.mark.parametrize("nfft,hop,n", [(2048, 2048, 131072), (64, 16, 1000), (8192, 4096, 20000), (4096, 1024, 4095)])
@@ -93,7 +99,29 @@ def test_spectrum_block_of_capture_thread(gpu_processor):
     freqs, power = sp.spectrum(x, 2048, center_frequency=390.0e6)
     assert np.array_equal(freqs, np.fft.fftshift(np.fft.fftfreq(2048, 1 / 2.4e6)) + 390.0e6)
     ref = ref_dsp.spectrum_db(x, 2048)
-    assert power.dtype == np.float64 and np.abs(power - ref)[ref > ref.max() - 80.0].max() < 1e-2
+    # float64 FFT on the device: SURVEY 8(d)'s bound (<= 1e-3 dB above -120 dBFS) holds with five orders to spare, on every bin
+    assert power.dtype == np.float64 and np.abs(power - ref).max() < 1e-8
+    assert np.abs(power - ref)[ref > -120.0].max() < 1e-3
+
+
+def test_spectrum_block_high_dynamic_range(gpu_processor):
+    """A full-scale tone over a floor near -190 dBFS: the float64 spectrum stays within 1e-6 dB of the reference expression
+    down to -180 dBFS and within 1e-4 dB on every bin (measured on B200: 7.5e-6 at a -215 dBFS bin, two float64 FFTs
+    disagreeing in their last bits); the float32 waterfall kernel on the same row is bounded by its rounding floor
+    (~140 dB below the tone), which is why the once-per-chunk spectrum block does not use it."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    rng = np.random.default_rng(33)
+    t = np.arange(2048)
+    x = np.exp(2j * np.pi * 0.1237 * t) + 3e-8 * (rng.standard_normal(2048) + 1j * rng.standard_normal(2048))
+    _, power = sp.spectrum(x, 2048)
+    ref = ref_dsp.spectrum_db(x, 2048)
+    assert ref.min() < -180.0 and np.abs(power - ref)[ref > -180.0].max() < 1e-6 and np.abs(power - ref).max() < 1e-4
+    rows32 = sp.stft_db(x, 2048, 2048)[0]
+    err32 = np.abs(rows32 - ref)
+    print("float32 row: max |dB error| %.3g within 60 dB of the peak, %.3g within 100 dB, %.3g overall"
+          % (err32[ref > ref.max() - 60].max(), err32[ref > ref.max() - 100].max(), err32.max()))
+    assert err32[ref > ref.max() - 60].max() < 1e-3
 
 
 def test_u8_ingest_matches_reference_on_converted_samples(gpu_processor):
@@ -257,3 +285,42 @@ def test_scanner_analysis_matches_reference_golden(gpu_processor):
     batch = sp.analyze_signal(np.stack(same))                      # several captures in one launch
     for r, (name, x) in zip(batch, [c for c in caps if len(c[1]) == len(caps[0][1])]):
         assert abs(r["power_db"] - g[name][0]) < 1e-6 and abs(r["sync_correlation"] - g[name][3]) < 1e-12
+
+
+def test_survey_wideband_matches_reference_per_channel(gpu_processor):
+    """the scanner's sweep from one capture. Golden = the reference's TetraSignalDetector on its own
+    frequency_shift of the capture, per channel of the 25 kHz grid (oracle/make_golden_survey.py), plus the presence / AFC
+    block of ui/modern.py:1945-2012 (oracle restatement)."""
+    from conftest import load_golden
+    from oracle.make_golden_survey import capture, FIELDS, N_SAMPLES
+    from oracle.make_golden import input_digest
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    g = load_golden("survey")
+    x, active, freqs = capture()
+    assert input_digest(x) == str(g["input_sha256"]) and list(g["fields"]) == list(FIELDS)
+    results, found = sp.survey_wideband(x, freqs, center_frequency=392.5e6)
+    want = g["rows"]
+    col = {name: i for i, name in enumerate(FIELDS)}
+    n_pd = N_SAMPLES - 1
+    worst_db, flips = 0.0, 0
+    for k, r in enumerate(results):
+        w = want[k]
+        assert abs(r["power_db"] - w[col["power_db"]]) < 1e-6, k
+        assert abs(r["modulation_confidence"] - w[col["modulation_confidence"]]) <= 3.0 / n_pd, k     # decisions on a boundary ulp
+        assert abs(r["sync_correlation"] - w[col["sync_correlation"]]) < 1e-12, k
+        assert float(r["sync_detected"]) == w[col["sync_detected"]] and float(r["power_stable"]) == w[col["power_stable"]], k
+        for name in ("signal_power", "peak_power", "noise_floor", "snr"):
+            worst_db = max(worst_db, abs(r[name] - w[col[name]]))
+        assert abs(r["peak_freq_offset"] - w[col["peak_freq_offset"]]) < 1e-6, k          # the same bin (bins are 1171.875 Hz apart)
+        assert float(r["is_signal_strong"]) == w[col["is_signal_strong"]], k
+        assert float(r["is_tetra"]) == w[col["is_tetra"]] and float(r["signal_present"]) == w[col["signal_present"]], k
+        assert abs(r["confidence"] - w[col["confidence"]]) <= 2.0 / n_pd, k
+        assert r["frequency"] == 392.5e6 + freqs[k]
+    assert worst_db < 1e-8
+    # the presence verdict separates the occupied grid channels from the idle ones on this capture
+    strong = np.array([r["is_signal_strong"] for r in results])
+    assert strong[active].mean() > 0.9 and strong[~active].mean() < 0.1
+    want_found = [k for k in range(len(freqs)) if want[k][col["is_tetra"]] and want[k][col["power_db"]] > -70
+                  and want[k][col["confidence"]] > 0.4 and want[k][col["sync_detected"]] and want[k][col["power_stable"]]]
+    assert [d["frequency"] for d in found] == [392.5e6 + freqs[k] for k in want_found]

@@ -74,3 +74,22 @@ def test_scanner_analysis_matches_reference_golden():
         assert r["modulation_confidence"] == want[1] and float(r["is_tetra_modulation"]) == want[2], name
         assert r["sync_correlation"] == want[3] and float(r["sync_detected"]) == want[4], name
         assert float(r["power_stable"]) == want[5], name
+
+
+def test_presence_afc_restatement_on_a_centred_carrier():
+    """oracle/ref_dsp.presence_afc (ui/modern.py:1945-2012): a carrier at the centre is a strong signal whose AFC offset stays
+    inside the channel; noise alone is not; the survey golden holds both kinds."""
+    from tetraear_b200 import synth
+    x = synth.carrier_iq(8192, 71, snr_db=30.0).astype(np.complex128)
+    p = ref_dsp.presence_afc(x, 2.4e6)
+    assert p["is_signal_strong"] and abs(p["peak_freq_offset"]) <= 12500 and p["snr"] > 15
+    rng = np.random.default_rng(5)
+    noise = 0.01 * (rng.standard_normal(4096) + 1j * rng.standard_normal(4096))
+    assert not ref_dsp.presence_afc(noise, 2.4e6)["is_signal_strong"]
+    assert ref_dsp.presence_afc(noise[:100], 2.4e6)["snr"] == 0.0
+    g = load_golden("survey")
+    col = {str(n): i for i, n in enumerate(g["fields"])}
+    rows, active = g["rows"], g["active"]
+    assert rows[active, col["is_signal_strong"]].mean() > 0.9 and rows[~active, col["is_signal_strong"]].mean() < 0.1
+    v = ref_dsp.analyze_verdict(*[float(rows[0, col[k]]) for k in ("power_db", "modulation_confidence", "sync_correlation", "power_stable")])
+    assert float(v["is_tetra"]) == rows[0, col["is_tetra"]] and abs(v["confidence"] - rows[0, col["confidence"]]) < 1e-12

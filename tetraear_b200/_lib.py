@@ -28,6 +28,7 @@ _SIGS = {
     "tetra_sync_positions": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p]),
     "tetra_analyze_signal": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]),
+    "tetra_survey_wideband": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     "tetra_process_batch_u8": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_int32, C.c_void_p]),
@@ -58,12 +59,15 @@ _SIGS = {
     "tetra_resample": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "tetra_stft_db": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                 C.POINTER(C.c_int64)]),
+    "tetra_stft_db_f64": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                    C.POINTER(C.c_int64)]),
     "tetra_edge_corrections": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "tetra_design_butter4": (C.c_int, [C.c_double, C.c_void_p, C.c_void_p]),
     "tetra_design_cheby1_sos8": (C.c_int, [C.c_double, C.c_double, C.c_void_p]),
 }
 
 IPC_HANDLE_BYTES = 64            # TETRA_IPC_HANDLE_BYTES
+SURVEY_FIELDS = 16               # TETRA_SURVEY_FIELDS
 EXPORTS = tuple(_SIGS)
 
 

@@ -946,11 +946,59 @@ int tetra_analyze_signal(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, 
     if (!d_out) { CK(ctx->tmp_c.ensure(sizeof(double) * 6 * C)); dout = (double*)ctx->tmp_c.p; }
     const size_t smem = ((size_t)(n_bits + 31) / 32 + 2) * sizeof(uint32_t);
     CK(cudaFuncSetAttribute(k_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-    k_analyze<<<C, ANA_THREADS, smem, st>>>(dx, dpitch, N, ds, dout);
+    k_analyze<<<C, ANA_THREADS, smem, st>>>(dx, dpitch, N, ds, dout, nullptr, 6);
     ctx->launches++;
     CK(cudaGetLastError());
     if (!d_out) CK(cudaMemcpyAsync(out6, dout, sizeof(double) * 6 * C, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_survey_wideband(tetra_ctx* ctx, const float* iq, int64_t N, const double* channel_hz, int32_t C, int32_t nfft, double* out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (C < 0 || N < 0 || (C > 0 && (!channel_hz || !out || (N > 0 && !iq))) || nfft < 64 || nfft > 4096 || (nfft & (nfft - 1)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_survey_wideband: bad arguments (nfft a power of two in [64, 4096])");
+    if (C == 0) return TETRA_OK;
+    if (C > 65535) return fail(ctx, TETRA_E_INVALID, "tetra_survey_wideband: at most 65535 channels per call");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const double fs = ctx->sample_rate;
+    const int ds = std::max(1, (int)(fs / 18000.0 / 10.0));                   // scanner.py:108
+    const int64_t n_bits = (N + ds - 1) / ds;
+    if (n_bits > ANA_MAXBITS) return fail(ctx, TETRA_E_UNSUPPORTED, "tetra_survey_wideband: capture too long (%lld crude bits > %d)", (long long)n_bits, ANA_MAXBITS);
+    const float2* dx = (const float2*)iq;
+    if (N > 0 && !is_device_ptr(iq)) {
+        CK(ctx->in.ensure((size_t)N * sizeof(float2)));
+        CK(cudaMemcpyAsync(ctx->in.p, iq, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice, st));
+        dx = (const float2*)ctx->in.p;
+    }
+    // channel offsets and the phase step each one takes off: [C] Hz, [C] rad
+    std::vector<double> hz(2 * (size_t)C);
+    for (int c = 0; c < C; ++c) { hz[c] = channel_hz[c]; hz[C + c] = (2.0 * M_PI) * channel_hz[c] / fs; }
+    CK(ctx->fo.ensure(sizeof(double) * 2 * C));
+    CK(cudaMemcpyAsync(ctx->fo.p, hz.data(), sizeof(double) * 2 * C, cudaMemcpyHostToDevice, st));
+    const double* d_hz = (const double*)ctx->fo.p;
+    CK(ctx->tmp_c.ensure(sizeof(double) * TETRA_SURVEY_FIELDS * C));
+    double* dout = (double*)ctx->tmp_c.p;
+    CK(cudaMemsetAsync(dout, 0, sizeof(double) * TETRA_SURVEY_FIELDS * C, st));
+    const size_t smem = ((size_t)(n_bits + 31) / 32 + 2) * sizeof(uint32_t);
+    CK(cudaFuncSetAttribute(k_analyze, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    k_analyze<<<C, ANA_THREADS, smem, st>>>(dx, 0, N, ds, dout, d_hz + C, TETRA_SURVEY_FIELDS);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (N >= nfft) {                                                         // ui/modern.py:1922: only with a full FFT block
+        CK(ctx->tmp_a.ensure((size_t)C * nfft * sizeof(double2)));
+        CK(ctx->tmp_b.ensure((size_t)C * nfft * sizeof(double)));
+        k_mix_head_f64<<<dim3((nfft + 255) / 256, C), 256, 0, st>>>(dx, nfft, d_hz, fs, (double2*)ctx->tmp_a.p);
+        if (stft_f64_launch(st, (const double2*)ctx->tmp_a.p, nfft, nfft, C, (double*)ctx->tmp_b.p))
+            return fail(ctx, TETRA_E_CUDA, "tetra_survey_wideband: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        k_presence<<<C, 256, 0, st>>>((const double*)ctx->tmp_b.p, nfft, fs, dout + 6, TETRA_SURVEY_FIELDS);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(out, dout, sizeof(double) * TETRA_SURVEY_FIELDS * C, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    hz.clear();
     return TETRA_OK;
 }
 
@@ -1344,6 +1392,28 @@ int tetra_stft_db(tetra_ctx* ctx, const float* iq, int64_t n, int32_t nfft, int3
     if (rc) return fail(ctx, TETRA_E_CUDA, "tetra_stft_db: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     CK(cudaGetLastError());
     if (!d_out) CK(cudaMemcpyAsync(out, dout, (size_t)rows * nfft * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return TETRA_OK;
+}
+
+int tetra_stft_db_f64(tetra_ctx* ctx, const double* iq, int64_t n, int32_t nfft, int32_t hop, double* out, int64_t* rows_out) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (!rows_out || n < 0 || hop <= 0 || nfft < 64 || nfft > 4096 || (nfft & (nfft - 1)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_stft_db_f64: nfft must be a power of two in [64, 4096], hop > 0");
+    const int64_t rows = n >= nfft ? (n - nfft) / hop + 1 : 0;
+    *rows_out = rows;
+    if (rows == 0) return TETRA_OK;
+    if (!iq || !out) return fail(ctx, TETRA_E_INVALID, "tetra_stft_db_f64: null buffer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t used = (rows - 1) * hop + nfft;
+    CK(ctx->tmp_a.ensure((size_t)used * sizeof(double2)));
+    CK(ctx->tmp_b.ensure((size_t)rows * nfft * sizeof(double)));
+    CK(cudaMemcpyAsync(ctx->tmp_a.p, iq, (size_t)used * sizeof(double2), cudaMemcpyHostToDevice, st));
+    if (stft_f64_launch(st, (const double2*)ctx->tmp_a.p, nfft, hop, rows, (double*)ctx->tmp_b.p))
+        return fail(ctx, TETRA_E_CUDA, "tetra_stft_db_f64: launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches++;
+    CK(cudaMemcpyAsync(out, ctx->tmp_b.p, (size_t)rows * nfft * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return TETRA_OK;
 }

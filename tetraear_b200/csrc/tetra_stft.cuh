@@ -67,6 +67,79 @@ __global__ void __launch_bounds__(STFT_THREADS) k_stft_db(const float2* __restri
     }
 }
 
+// The same in float64 on complex128 input: the reference's own precision (numpy FFT of complex128, ui/modern.py:1924-1934).
+// This is what SignalProcessor.spectrum() -- the once-per-chunk spectrum block of the GUI, SURVEY 8 row a11 -- runs: a
+// 2048-point row costs microseconds either way, and float64 keeps every bin above -300 dBFS within 1e-9 dB of the reference,
+// where a float32 FFT's rounding floor sits ~140 dB below the strongest bin (tests/test_gpu_configs.py). NFFT <= 4096.
+template <int NFFT>
+__global__ void __launch_bounds__(STFT_THREADS) k_stft_db_f64(const double2* __restrict__ x, int hop, int64_t rows, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double2* buf0 = reinterpret_cast<double2*>(sm_raw);
+    double2* buf1 = buf0 + NFFT;
+    double2* tw = buf1 + NFFT;
+    double* win = reinterpret_cast<double*>(tw + NFFT / 2);
+    const int tid = threadIdx.x;
+    for (int t = tid; t < NFFT / 2; t += STFT_THREADS) {
+        double s, c;
+        sincospi(-2.0 * (double)t / (double)NFFT, &s, &c);
+        tw[t] = make_double2(c, s);
+    }
+    for (int t = tid; t < NFFT; t += STFT_THREADS) win[t] = 0.5 - 0.5 * cospi(2.0 * (double)t / (double)(NFFT - 1));
+    __syncthreads();
+    for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+        const double2* xr = x + r * hop;
+        for (int t = tid; t < NFFT; t += STFT_THREADS) {
+            const double2 v = xr[t];
+            buf0[t] = make_double2(v.x * win[t], v.y * win[t]);
+        }
+        __syncthreads();
+        double2* src = buf0;
+        double2* dst = buf1;
+#pragma unroll 1
+        for (int ns = 1; ns < NFFT; ns <<= 1) {
+            const int tw_stride = NFFT / (2 * ns);
+            for (int j = tid; j < NFFT / 2; j += STFT_THREADS) {
+                const int k = j & (ns - 1);
+                const double2 w = tw[k * tw_stride];
+                const double2 a = src[j];
+                const double2 b = src[j + NFFT / 2];
+                const double2 bw = make_double2(b.x * w.x - b.y * w.y, b.x * w.y + b.y * w.x);
+                const int j0 = ((j - k) << 1) + k;
+                dst[j0] = make_double2(a.x + bw.x, a.y + bw.y);
+                dst[j0 + ns] = make_double2(a.x - bw.x, a.y - bw.y);
+            }
+            __syncthreads();
+            double2* t = src; src = dst; dst = t;
+        }
+        double* orow = out + r * NFFT;
+        for (int k = tid; k < NFFT; k += STFT_THREADS) {
+            const double2 v = src[(k + NFFT / 2) & (NFFT - 1)];
+            orow[k] = 20.0 * log10(hypot(v.x, v.y) / (double)NFFT + 1e-20);
+        }
+        __syncthreads();
+    }
+}
+
+template <int NFFT>
+static int stft_f64_launch_t(cudaStream_t st, const double2* x, int hop, int64_t rows, double* out) {
+    const size_t smem = (size_t)NFFT * 16 * 2 + (size_t)NFFT / 2 * 16 + (size_t)NFFT * 8;
+    if (cudaFuncSetAttribute(k_stft_db_f64<NFFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    k_stft_db_f64<NFFT><<<(int)std::min<int64_t>(rows, 148), STFT_THREADS, smem, st>>>(x, hop, rows, out);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+static int stft_f64_launch(cudaStream_t st, const double2* x, int nfft, int hop, int64_t rows, double* out) {
+    switch (nfft) {
+        case 64: return stft_f64_launch_t<64>(st, x, hop, rows, out);
+        case 128: return stft_f64_launch_t<128>(st, x, hop, rows, out);
+        case 256: return stft_f64_launch_t<256>(st, x, hop, rows, out);
+        case 512: return stft_f64_launch_t<512>(st, x, hop, rows, out);
+        case 1024: return stft_f64_launch_t<1024>(st, x, hop, rows, out);
+        case 2048: return stft_f64_launch_t<2048>(st, x, hop, rows, out);
+        case 4096: return stft_f64_launch_t<4096>(st, x, hop, rows, out);
+    }
+    return -1;
+}
+
 // ----------------------------------------------------------------------------------------------
 // K3 for the waterfall size of BASELINE config 5 (4096 = 16^3): three radix-16 Stockham passes with the 16-point
 // DFTs in registers (two radix-4 stages), so a row costs 3 shared-memory exchanges instead of 12. 256 threads, one
@@ -268,14 +341,19 @@ __device__ __forceinline__ double ana_block_sum(double v, double* red) {
     return t;
 }
 
-__global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restrict__ x, int64_t pitch, int64_t n, int ds, double* __restrict__ out) {
+// dphi (or null): capture c is analysed as frequency_shift(x, f_c) (processor.py:85-100) -- the scanner retuned to channel c
+// (signal/scanner.py:383-445) -- with dphi[c] = 2 pi f_c / fs: the shift leaves every |x| alone and takes dphi off every
+// phase step (ds dphi off the steps between every ds-th sample), so the shifted capture is never formed. out_stride >= 6.
+__global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restrict__ x, int64_t pitch, int64_t n, int ds, double* __restrict__ out,
+                                                         const double* __restrict__ dphi, int out_stride) {
     extern __shared__ uint32_t s_bits[];                // ceil(nbits / 32) + 2 words
     __shared__ double red[ANA_THREADS / 32];
     __shared__ unsigned long long s_max;
     __shared__ int s_best;
     const int tid = threadIdx.x;
     const float2* xc = x + (int64_t)blockIdx.x * pitch;
-    double* o = out + 6 * (int64_t)blockIdx.x;
+    double* o = out + (int64_t)out_stride * blockIdx.x;
+    const double dph = dphi ? dphi[blockIdx.x] : 0.0;
     if (tid == 0) { s_max = 0ull; s_best = 0; }
     __syncthreads();
     // ---- power (scanner.py:42-55), per-window powers (:204-231) and max |x| (:72) ----
@@ -304,7 +382,7 @@ __global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restric
     if (n >= 1000) {
         for (int64_t i = 1 + tid; i < n; i += ANA_THREADS) {
             const float2 a = __ldg(xc + i), b = __ldg(xc + i - 1);
-            const double d = ana_wrap(atan2((double)a.y / scale, (double)a.x / scale) - atan2((double)b.y / scale, (double)b.x / scale));
+            const double d = ana_wrap(atan2((double)a.y / scale, (double)a.x / scale) - atan2((double)b.y / scale, (double)b.x / scale) - dph);
             double best = 1e9;
 #pragma unroll
             for (int k = -4; k < 4; ++k) best = fmin(best, fabs((double)k * (M_PI / 4.0) - d));
@@ -320,7 +398,7 @@ __global__ void __launch_bounds__(ANA_THREADS) k_analyze(const float2* __restric
     __syncthreads();
     for (int64_t j = tid; j < n_bits; j += ANA_THREADS) {
         const float2 a = __ldg(xc + (j + 1) * ds), b = __ldg(xc + j * ds);
-        const double d = ana_wrap(atan2((double)a.y, (double)a.x) - atan2((double)b.y, (double)b.x));
+        const double d = ana_wrap(atan2((double)a.y, (double)a.x) - atan2((double)b.y, (double)b.x) - dph * (double)ds);
         const double q = rint(d / (M_PI / 4.0)) * (M_PI / 4.0);     // numpy round: half to even
         if (fabs(q) < M_PI / 8.0) atomicOr(&s_bits[j >> 5], 0x80000000u >> (j & 31));
     }
@@ -493,6 +571,74 @@ __global__ void k_slice_c128(const double2* x, int64_t n, const double* maxabs, 
         const double im = s1.y * s0.x - s1.x * s0.y;
         const uint8_t d = slice_dqpsk(re, im);
         out[i - 1] = d;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Wideband survey: per channel, the signal-presence / AFC block of CaptureThread.run
+// (tetraear/ui/modern.py:1945-2012) on the spectrum of the first n_fft samples of the shifted capture.
+// ----------------------------------------------------------------------------------------------
+// out[c][i] = x[i] exp(-1j 2 pi f_c (i / fs)), i < len, complex128 (processor.py:97-100)
+__global__ void __launch_bounds__(256) k_mix_head_f64(const float2* __restrict__ x, int len, const double* __restrict__ freqs, double fs,
+                                                        double2* __restrict__ out) {
+    const int c = blockIdx.y;
+    const double w = (2.0 * M_PI) * freqs[c];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+        double sn, cs;
+        sincos(-(w * ((double)i / fs)), &sn, &cs);
+        const float2 v = __ldg(x + i);
+        out[(int64_t)c * len + i] = make_double2((double)v.x * cs - (double)v.y * sn, (double)v.x * sn + (double)v.y * cs);
+    }
+}
+// one CTA per channel over its dB row `power` [nfft] (fftshifted): mean and peak of the centre +-bandwidth_bins/2 bins, the
+// peak's frequency, the mean of everything more than 10 bins outside, and the verdict snr > 15 and peak > -70 and peak - mean > 3.
+//   o[0..5] = signal_power, peak_power, peak_freq_offset_hz, noise_floor, snr, is_signal_strong
+__global__ void __launch_bounds__(256) k_presence(const double* __restrict__ power, int nfft, double fs, double* __restrict__ out, int out_stride) {
+    __shared__ double r_sum[8], r_noise[8], r_max[8];
+    __shared__ int r_idx[8], r_cnt[8];
+    const double* p = power + (int64_t)blockIdx.x * nfft;
+    double* o = out + (int64_t)blockIdx.x * out_stride;
+    const int tid = threadIdx.x;
+    const int centre = nfft / 2;
+    const int bw_bins = (int)(25000.0 / (fs / (double)nfft));
+    const int start = max(0, centre - bw_bins / 2), end = min(nfft, centre + bw_bins / 2);
+    const int n_end = max(0, start - 10), n_start2 = min(nfft, end + 10);
+    double sum = 0.0, noise = 0.0, mx = -1e300;
+    int idx = nfft, cnt = 0;
+    for (int k = tid; k < nfft; k += 256) {
+        const double v = p[k];
+        if (k >= start && k < end) {
+            sum += v;
+            if (v > mx) { mx = v; idx = k; }                   // ascending k per thread: keeps its first maximum
+        }
+        if (k < n_end || k >= n_start2) { noise += v; ++cnt; }
+    }
+    for (int of = 16; of; of >>= 1) {
+        sum += __shfl_xor_sync(0xffffffffu, sum, of);
+        noise += __shfl_xor_sync(0xffffffffu, noise, of);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, of);
+        const double om = __shfl_xor_sync(0xffffffffu, mx, of);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, of);
+        if (om > mx || (om == mx && oi < idx)) { mx = om; idx = oi; }      // np.argmax: the first maximum
+    }
+    if ((tid & 31) == 0) { r_sum[tid >> 5] = sum; r_noise[tid >> 5] = noise; r_max[tid >> 5] = mx; r_idx[tid >> 5] = idx; r_cnt[tid >> 5] = cnt; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < 8; ++w) {
+            sum += r_sum[w]; noise += r_noise[w]; cnt += r_cnt[w];
+            if (r_max[w] > mx || (r_max[w] == mx && r_idx[w] < idx)) { mx = r_max[w]; idx = r_idx[w]; }
+        }
+        if (end > start) {
+            const double sig = sum / (double)(end - start);
+            const double floor_db = cnt > 0 ? noise / (double)cnt : -100.0;
+            const double snr = sig - floor_db;
+            o[0] = sig; o[1] = mx;
+            o[2] = (double)(idx - centre) * (fs / (double)nfft);      // fftshift(fftfreq(n, 1/fs))[idx]
+            o[3] = floor_db; o[4] = snr;
+            o[5] = (snr > 15.0 && mx > -70.0 && (mx - sig) > 3.0) ? 1.0 : 0.0;
+        } else {
+            for (int k = 0; k < 6; ++k) o[k] = 0.0;
+        }
     }
 }
 

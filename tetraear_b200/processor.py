@@ -335,6 +335,46 @@ class SignalProcessor:
                     modulation_matches=int(r[4])) for r in out]
         return res[0] if one else res
 
+    def survey_wideband(self, capture, channel_freqs, center_frequency=0.0, n_fft=2048, min_power=-70, min_confidence=0.4,
+                        bottom_threshold=-85):
+        """``FrequencyScanner.scan_range`` (signal/scanner.py:383-445) from ONE wideband capture instead of a hardware retune
+        per 25 kHz step: for every channel offset (Hz from the capture's centre) the dict ``TetraSignalDetector.analyze_signal``
+        builds (scanner.py:233-289) on the capture shifted to that channel, the presence / AFC numbers of
+        ``CaptureThread.run`` (ui/modern.py:1945-2012; ``peak_freq_offset`` is the AFC offset it hands to ``process``), and
+        ``frequency`` / ``frequency_mhz`` as ``scan_frequency`` adds them (:367-368). Returns ``(results, found)``: one
+        dict per channel and the ones passing ``scan_range``'s filter (:418-425). Frame validation (:149-202) needs the
+        reference's ``TetraDecoder`` on the host; feed it ``process_wideband``'s dibits where a channel is worth it."""
+        self._sync_rate()
+        x = _as_c64(capture)
+        f = np.ascontiguousarray(channel_freqs, dtype=np.float64)
+        out = np.zeros((len(f), _lib.SURVEY_FIELDS), dtype=np.float64)
+        if len(f):
+            self._check(self._lib.tetra_survey_wideband(self._ctx, x.ctypes.data, len(x), f.ctypes.data, len(f), int(n_fft),
+                                                        out.ctypes.data), "survey_wideband")
+        results, found = [], []
+        for k, r in enumerate(out):
+            mod_conf, sync_corr = float(r[1]), float(r[2])
+            is_mod, has_sync, stable = mod_conf > 0.4, sync_corr > 0.75, bool(r[3] > 0.5)
+            if has_sync and is_mod:                                  # scanner.py:258-269 (crc_rate = 0: no frame validation here)
+                confidence = mod_conf * 0.4 + sync_corr * 0.4
+            elif has_sync:
+                confidence = sync_corr * 0.6
+            elif is_mod:
+                confidence = mod_conf * 0.5
+            else:
+                confidence = 0.0
+            d = dict(power_db=float(r[0]), is_tetra=bool(is_mod and has_sync and stable), confidence=confidence,
+                     modulation_confidence=mod_conf, sync_detected=bool(has_sync), sync_correlation=sync_corr,
+                     frames_validated=False, crc_pass_rate=0.0, power_stable=stable,
+                     signal_present=bool(r[0] > bottom_threshold),
+                     frequency=float(center_frequency + f[k]), frequency_mhz=float(center_frequency + f[k]) / 1e6,
+                     signal_power=float(r[6]), peak_power=float(r[7]), peak_freq_offset=float(r[8]), noise_floor=float(r[9]),
+                     snr=float(r[10]), is_signal_strong=bool(r[11] > 0.5))
+            results.append(d)
+            if d["is_tetra"] and d["power_db"] > min_power and d["confidence"] > min_confidence and d["sync_detected"] and stable:
+                found.append(d)
+        return results, found
+
     def dibit_capacity(self, n_samples: int) -> int:
         self._sync_rate()
         return int(self._lib.tetra_dibit_capacity(self._ctx, int(n_samples)))
@@ -349,11 +389,23 @@ class SignalProcessor:
                                             out.ctypes.data, C.byref(rows)), "stft_db")
         return out[: rows.value]
 
+    def stft_db_f64(self, iq, n_fft=2048, hop=None):
+        """The same rows in the reference's own precision: complex128 in, float64 FFT on the device, float64 rows out
+        (n_fft <= 4096). What ``spectrum`` uses."""
+        x = np.ascontiguousarray(iq, dtype=np.complex128)
+        hop = int(hop or n_fft)
+        rows = C.c_int64(0)
+        n_rows = (len(x) - n_fft) // hop + 1 if len(x) >= n_fft else 0
+        out = np.empty((max(n_rows, 0), n_fft), dtype=np.float64)
+        self._check(self._lib.tetra_stft_db_f64(self._ctx, x.ctypes.data, len(x), int(n_fft), hop,
+                                                out.ctypes.data, C.byref(rows)), "stft_db_f64")
+        return out[: rows.value]
+
     def spectrum(self, samples, n_fft=2048, center_frequency=0.0):
-        """The spectrum block of CaptureThread.run (ui/modern.py:1921-1937): (freqs, power_dB)."""
-        p = self.stft_db(np.asarray(samples)[:n_fft], n_fft, n_fft)
+        """The spectrum block of CaptureThread.run (ui/modern.py:1921-1937): (freqs, power_dB), float64 like the reference."""
+        p = self.stft_db_f64(np.asarray(samples)[:n_fft], n_fft, n_fft)
         freqs = np.fft.fftshift(np.fft.fftfreq(n_fft, 1 / self.sample_rate)) + center_frequency
-        return freqs, p[0].astype(np.float64)
+        return freqs, p[0]
 
     def enable_kernel_timing(self, on=True):
         self._lib.tetra_enable_kernel_timing(self._ctx, 1 if on else 0)
