@@ -53,6 +53,21 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+struct PinBuf {                      // page-locked host staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 }  // namespace
 
 struct tetra_ctx {
@@ -72,6 +87,9 @@ struct tetra_ctx {
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
+    DevBuf k1_ctr;                     // work-item counter of the fused kernel (one word, zeroed before every launch)
+    DevBuf dout;                       // all results of a small host-side call, back to back (one D2H copy into `hout`)
+    PinBuf hout;
     DevBuf pfb;                        // config 3: the 96 channelized 240 kS/s streams of one capture
     DevBuf etab, ecorr, estate;        // block-end correction tables (edge_tables_generated.h), corrections [C][2][K_EDGE], states
     DevBuf emat[10], emat_unit;        // states -> corrections matrices (freq_offset = 0), one per (n - 1) mod 10; unit states
@@ -183,9 +201,15 @@ int upload_tables(tetra_ctx* ctx) {
     return 0;
 }
 
-int edge_serial_mode() {
-    static const int v = getenv("TETRA_EDGE_SERIAL") ? atoi(getenv("TETRA_EDGE_SERIAL")) : 0;
-    return v;
+// Where the block-end correction kernels run: beside the fused kernel on the side stream, or ahead of it on the same stream.
+// Measured on one B200 box each (profiles/r02_edges_serial_ab.txt): beside it they cost the fused kernel more than they
+// take alone once the batch is large (4096 carriers: fused kernel 6.11 -> 5.74 ms and step 6.46 -> 6.31 ms with them
+// ahead; 0.26 ms alone), while small batches hide them for less (512 carriers: step 0.855 beside, 0.874 ahead).
+// TETRA_EDGE_SERIAL = 0 / 1 forces one or the other.
+constexpr int K1_EDGES_AHEAD_FROM = 2048;      // carriers per call from which the corrections run ahead
+int edge_serial_mode(int n_carriers) {
+    static const int v = getenv("TETRA_EDGE_SERIAL") ? atoi(getenv("TETRA_EDGE_SERIAL")) : -1;
+    return v >= 0 ? v : (n_carriers >= K1_EDGES_AHEAD_FROM ? 1 : 0);
 }
 
 // block-end corrections of the fused path (k_edge_states + k_edge_recursions) for C carriers -> ctx->ecorr
@@ -213,9 +237,10 @@ int launch_edge_correct(tetra_ctx* ctx, cudaStream_t st, const float2* x, const 
         }
         ea.m = (const double*)ctx->emat[k0].p;
     }
-    if (x8) k_edge_states<1><<<C, KC_THREADS, 0, st>>>(ea);
-    else if (d_chan) k_edge_states<2><<<C, KC_THREADS, 0, st>>>(ea);
-    else k_edge_states<0><<<C, KC_THREADS, 0, st>>>(ea);
+    const int g1 = d_fo ? (C + KC_THREADS / 32 - 1) / (KC_THREADS / 32) : C;      // with freq_offsets: one warp per carrier
+    if (x8) k_edge_states<1><<<g1, KC_THREADS, 0, st>>>(ea);
+    else if (d_chan) k_edge_states<2><<<g1, KC_THREADS, 0, st>>>(ea);
+    else k_edge_states<0><<<g1, KC_THREADS, 0, st>>>(ea);
     if (d_fo) k_edge_recursions<<<dim3((C + KC2_THREADS - 1) / KC2_THREADS, 2), KC2_THREADS, 0, st>>>(ea);
     else k_edge_apply<<<dim3((C + KA_CPB - 1) / KA_CPB, 2), KA_THREADS, 0, st>>>(ea);
     ctx->launches++;
@@ -447,6 +472,7 @@ void tetra_destroy(tetra_ctx* ctx) {
                       &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->pfb};
     tetra_p2p_destroy(ctx);
     for (DevBuf* b : bufs) b->release();
+    ctx->dout.release(); ctx->hout.release(); ctx->k1_ctr.release();
     for (DevBuf& b : ctx->emat) b.release();
     ctx->emat_unit.release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -668,17 +694,34 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     float2* k_sym = d_sym ? (float2*)symbols : nullptr;
     int32_t* k_ph = d_ph ? best_phase : nullptr;
     uint8_t* k_match = d_match ? ts_match : nullptr;
-    if (!d_dib) { CK(ctx->dib.ensure((size_t)C * cap + 16)); k_dib = (uint8_t*)ctx->dib.p; }
-    if (!d_nd) { CK(ctx->ndib.ensure(sizeof(int32_t) * C)); k_nd = (int32_t*)ctx->ndib.p; }
-    if (symbols && !d_sym) { CK(ctx->sym.ensure((size_t)C * (cap + 1) * sizeof(float2))); k_sym = (float2*)ctx->sym.p; }
-    if (best_phase && !d_ph) k_ph = (int32_t*)ctx->phase.p;
-    if (ts_match && !d_match) { CK(ctx->match.ensure((size_t)C * cap * 4 + 16)); k_match = (uint8_t*)ctx->match.p; }
     int32_t* k_spos = d_spos ? sync_pos : nullptr;
     int32_t* k_nsync = d_nsync ? n_sync : nullptr;
-    if (sync_pos) {
-        // max_corr bookkeeping needs every position: the walk finds at most one per 250 bit offsets
-        if ((int64_t)max_pos < (2 * cap) / 250 + 2) return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
-        if (!d_spos) {
+    if (sync_pos && (int64_t)max_pos < (2 * cap) / 250 + 2)      // max_corr bookkeeping needs every position: the walk finds at most one per 250 bit offsets
+        return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
+    // A small call with every result in host memory (process() on one block): the results sit back to back in one device
+    // buffer and come home in ONE copy into page-locked staging -- seven pageable copies cost more than the kernels.
+    const size_t sz_dib = (size_t)C * cap, sz_nd = sizeof(int32_t) * C, sz_sym = symbols ? (size_t)C * (cap + 1) * sizeof(float2) : 0;
+    const size_t sz_match = ts_match ? (size_t)C * cap * 4 : 0, sz_spos = sync_pos ? (size_t)C * max_pos * sizeof(int32_t) : 0;
+    auto up16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_dib = 0, o_nd = o_dib + up16(sz_dib + 16), o_ph = o_nd + up16(sz_nd), o_sym = o_ph + up16(sz_nd);
+    const size_t o_match = o_sym + up16(sz_sym), o_spos = o_match + up16(sz_match + 16), o_nsync = o_spos + up16(sz_spos);
+    const size_t staged_total = o_nsync + up16(sz_nd);
+    const bool staged = !async && !d_dib && !d_nd && !d_sym && !d_ph && !d_match && !d_spos && staged_total <= ((size_t)2 << 20);
+    if (staged) {
+        CK(ctx->dout.ensure(staged_total));
+        CK(ctx->hout.ensure(staged_total));
+        uint8_t* b = (uint8_t*)ctx->dout.p;
+        k_dib = b + o_dib; k_nd = (int32_t*)(b + o_nd); k_ph = (int32_t*)(b + o_ph);
+        if (symbols) k_sym = (float2*)(b + o_sym);
+        if (ts_match) k_match = b + o_match;
+        if (sync_pos) { k_spos = (int32_t*)(b + o_spos); k_nsync = (int32_t*)(b + o_nsync); }
+    } else {
+        if (!d_dib) { CK(ctx->dib.ensure((size_t)C * cap + 16)); k_dib = (uint8_t*)ctx->dib.p; }
+        if (!d_nd) { CK(ctx->ndib.ensure(sizeof(int32_t) * C)); k_nd = (int32_t*)ctx->ndib.p; }
+        if (symbols && !d_sym) { CK(ctx->sym.ensure((size_t)C * (cap + 1) * sizeof(float2))); k_sym = (float2*)ctx->sym.p; }
+        if (best_phase && !d_ph) k_ph = (int32_t*)ctx->phase.p;
+        if (ts_match && !d_match) { CK(ctx->match.ensure((size_t)C * cap * 4 + 16)); k_match = (uint8_t*)ctx->match.p; }
+        if (sync_pos && !d_spos) {
             CK(ctx->spos.ensure((size_t)C * max_pos * sizeof(int32_t) + sizeof(int32_t) * C));
             k_spos = (int32_t*)ctx->spos.p;
             k_nsync = k_spos + (size_t)C * max_pos;
@@ -792,6 +835,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             ka.x = (const float2*)ctx->pfb.p; ka.pitch = wp; ka.w_col0 = PFB_M0; ka.aligned = 1;
         }
         ka.zero_ext = edge_corr ? 1 : 0;
+        CK(ctx->k1_ctr.ensure(64));
+        ka.counter = (uint32_t*)ctx->k1_ctr.p;
         // edge windows go to the side stream: the thread-per-job kernel runs beside the bulk kernel, the warp-per-job one behind it
         if (ctx->timing) {
             if (!ctx->ph_ev[0]) {
@@ -800,9 +845,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             }
             CK(cudaEventRecord(ctx->ph_ev[0], st));
         }
-        // TETRA_EDGE_SERIAL=1 (measurement only): the block-end corrections run ahead of the fused kernel on the same stream,
-        // so that the timeline's second entry is their stand-alone duration
-        const int edge_serial = edge_serial_mode();
+        // large batches: the block-end corrections run ahead of the fused kernel on the same stream (edge_serial_mode)
+        const int edge_serial = edge_serial_mode(C);
         if (edge_corr && edge_serial) {
             if (ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], st));
             rc = launch_edge_correct(ctx, st, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
@@ -840,6 +884,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         for (int g = 0; g < n_grp; ++g) {
             const int c_lo = g * grp_car, c_hi = std::min(C, c_lo + grp_car);
             ka.item0 = c_lo * n_seg; ka.n_items = (c_hi - c_lo) * n_seg;
+            CK(cudaMemsetAsync(ka.counter, 0, sizeof(uint32_t), st));
             const int grid_g = std::min(sms, ka.n_items);
             // the fused kernel goes first: its persistent CTAs (one per SM) must not queue behind the edge blocks
             cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -909,6 +954,18 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     }
     if (ctx->timing && use_fast && ctx->ph_ev[0]) { CK(cudaEventRecord(ctx->ph_ev[3], st)); ctx->ph_valid = true; }
     // ---- results to host buffers ----
+    if (staged) {
+        CK(cudaMemcpyAsync(ctx->hout.p, ctx->dout.p, staged_total, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint8_t* h = (const uint8_t*)ctx->hout.p;
+        if (dibits) memcpy(dibits, h + o_dib, sz_dib);
+        memcpy(n_dibits, h + o_nd, sz_nd);
+        if (best_phase) memcpy(best_phase, h + o_ph, sz_nd);
+        if (symbols) memcpy(symbols, h + o_sym, sz_sym);
+        if (ts_match) memcpy(ts_match, h + o_match, sz_match);
+        if (sync_pos) { memcpy(sync_pos, h + o_spos, sz_spos); memcpy(n_sync, h + o_nsync, sz_nd); }
+        return TETRA_OK;
+    }
     if (dibits && !d_dib) CK(cudaMemcpyAsync(dibits, k_dib, (size_t)C * cap, cudaMemcpyDeviceToHost, st));
     if (!d_nd) CK(cudaMemcpyAsync(n_dibits, k_nd, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
     if (symbols && !d_sym) CK(cudaMemcpyAsync(symbols, k_sym, (size_t)C * (cap + 1) * sizeof(float2), cudaMemcpyDeviceToHost, st));

@@ -140,7 +140,14 @@ __device__ __forceinline__ void kc_warp_sum(dcx (&acc)[NA], double2* dst, int la
 template <int IN>   // 0: complex64 rows, 1: uint8 rows, 2: channels of one shared complex64 capture
 __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int car = blockIdx.x;
+    // Without freq_offsets: one CTA per carrier, its four warps share the seven table passes (role = warp). With them the
+    // Butterworth-state pass is a serial chain ~18 table passes long that no split of the others can balance: one warp per
+    // carrier does everything (role -1), four carriers per CTA.
+    const bool wpc = a.fo != nullptr;
+    const int car = wpc ? blockIdx.x * (KC_THREADS / 32) + warp : blockIdx.x;
+    if (car >= a.n_carriers) return;                          // whole warps
+    const int role = wpc ? -1 : warp;
+    auto has = [&](int r) { return role < 0 || role == r; };
     const int64_t n = a.n;
     const int L = a.L;
     const int k0 = (int)((n - 1) % 10);
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
         for (int k = 0; k < 8; ++k) acc[k] = dcx{0.0, 0.0};
     };
     // warp 0: cascade state + Butterworth state; warp 1: backward-pass state + the raw end samples; warps 2, 3: pointwise outputs
-    if (warp == 1) {
+    if (has(1)) {
         if (lane <= EX_PAD1) {
             const dcx r = xr(lane), l = xl(lane);
             out[KS_XR + lane] = make_double2(r.x, r.y);
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
         }
     }
     // ---- causal cascade state after x[n-1] ----
-    if (warp == 0) {
+    if (has(0)) {
         clear();
         const double* __restrict__ wc = a.t.wc;
         for (int d0 = lane; d0 < ET_NC; d0 += 32 * UN) {
@@ -183,7 +190,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
         kc_warp_sum(acc, out + KS_SC, lane);
     }
     // ---- backward-pass state at position 0 of the zero-extended stream ----
-    if (warp == 1) {
+    if (has(1)) {
         clear();
         const double* __restrict__ wac = a.t.wac;
         for (int d0 = lane; d0 < ET_NAC; d0 += 32 * UN) {
@@ -201,8 +208,8 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
     }
     // ---- pointwise decimator outputs of the zero-extended stream: at output L-1-t, sum_d g1[d - k0 - 10 t] x[n-1-d],
     //      and at output t, sum_i g1[10 t - i] x[i]   (t = 8 h + k) ----
-    if (warp >= 2) {
-        const int h = warp - 2;
+    for (int h = 0; h < ET_NPTS / 8; ++h) {
+        if (!has(2 + h)) continue;
         clear();
         const int off_r = ET_G - k0 - 80 * h, cnt_r = k0 + 10 * (8 * h + 7) + ET_G + 1;
         for (int d0 = lane; d0 < cnt_r; d0 += 32 * UN) {
@@ -241,7 +248,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
     // ---- causal Butterworth state of the zero-extended stream at the right end ----
     // s(L) = e^{-jW(L-1)} sum_d x[n-1-d] Wv(d - k0),  Wv(u) = Bv g1[u] + e^{jW} A Wv(u - 10)  (tools/edge_model.py).
     // Without a freq_offset the weights are real and fixed: one more table pass.
-    if (warp != 0) return;
+    if (!has(0)) return;
     if (fo == 0.0) {
         dcx a4[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         const double* __restrict__ w0 = a.t.w0 + 9 - k0;      // w0[k * NW0 + d] = W0[k][d - k0 + 9]

@@ -80,6 +80,9 @@ constexpr int K1_U = K1_TILE / 20;        // 320 u/v (120 kS/s) samples per iter
 constexpr int K1_NBUF = 3;
 constexpr int K1_WRING = 2048, K1_URING = 2048, K1_VRING = 1024;
 constexpr int K1_RRING = 1024;            // MODE 1: ring of half-band outputs waiting for the equaliser
+// every ring repeats its first PAD entries behind its end (writers store those twice), so that a reader's window of up to PAD
+// consecutive entries is one base address plus immediate offsets -- no index mask per load
+constexpr int K1_WPAD = 32, K1_UPAD = 48, K1_VPAD = 32, K1_RPAD = 16;
 constexpr int K1_THREADS = 384;           // warps 0-3: A, 4-7: C, 8-9: B, 10-11: D
 constexpr int K1_DLANES = 64;
 constexpr int K1_CQ = 4;                  // tap quarters = iterations a C group stays in registers
@@ -116,18 +119,20 @@ static_assert((2 * K1_D0) % 2 == 0, "y pairs must start on even samples");
 
 struct K1Smem {
     float2 in[K1_NBUF][K1_HDR + K1_TILE];
-    float2 w[K1_WRING];
-    float2 u[K1_URING];
-    float2 v[K1_VRING];
+    float2 w[K1_WRING + K1_WPAD];
+    float2 u[K1_URING + K1_UPAD];
+    float2 v[K1_VRING + K1_VPAD];
     double bins[K1_NPH][K1_DLANES];
     uint64_t full[K1_NBUF];
+    int s_item[8];          // work item of slot q at [q & 7] (claimed from the launch's counter, see k1_claim)
+    int s_nmy;              // slots of this CTA once the counter has run out (K1_NMY_UNKNOWN before)
 };
 // freq_offset != 0 variant: the NCO phasors of the w samples of the current / next iteration, the half-band
 // output ring and this carrier's equaliser taps
 struct K1SmemFo {
     K1Smem base;
     float2 ph[2][K1_W];
-    float2 ur[K1_RRING];    // MODE 1: half-band output before the equaliser
+    float2 ur[K1_RRING + K1_RPAD];    // MODE 1: half-band output before the equaliser
     float2 rtap[2][16];     // MODE 1: equaliser taps r[-5..5] of the slot (by slot parity)
     float2 ptap[2][48];     // MODE 2: this channel's modulated proto taps
 };
@@ -166,6 +171,7 @@ struct K1Args {
     int32_t n_seg;          // segments per carrier
     int32_t n_items;        // work items (carrier, segment) of THIS launch
     int32_t item0;          // first work item of this launch (a batch may be cut into several launches, tetra_b200.cu)
+    uint32_t* counter;      // zero at launch: the next unclaimed work item of this launch (dynamic slot claims)
     int32_t t_item;         // tiles per item = seg_len / 640 + 1 (pre-roll + post-roll)
     float2* y;              // [C][y_pitch], timing-phase major: y[(n % 13) * y_rows + n / 13]
     int64_t y_pitch;
@@ -186,9 +192,11 @@ struct K1Args {
 // q is warp-uniform, so the taps arrive through uniform constant loads and there is one copy of this code
 __device__ __forceinline__ void k1_fir_quarter(const float2* __restrict__ u, int s0, const float* __restrict__ taps,
                                                float2 (&acc)[10]) {
+    static_assert(2 * 21 <= K1_UPAD, "fir120 quarter window exceeds the u ring's pad");
+    const float2* __restrict__ up = &u[s0 & (K1_URING - 1)];           // s0 is even: 16-byte aligned
 #pragma unroll
     for (int t2 = 0; t2 < 21; ++t2) {
-        const float4 v = *reinterpret_cast<const float4*>(&u[(s0 + 2 * t2) & (K1_URING - 1)]);
+        const float4 v = *reinterpret_cast<const float4*>(&up[2 * t2]);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int t = 2 * t2 + h;
@@ -203,6 +211,21 @@ __device__ __forceinline__ void k1_fir_quarter(const float2* __restrict__ u, int
 }
 
 __device__ __forceinline__ void k1_bar_sync() { asm volatile("bar.sync 0;" ::: "memory"); }
+
+// ring store: entry idx (unmasked stream index) and, for the first PAD entries, its copy behind the ring's end
+template <int RING, int PAD>
+__device__ __forceinline__ void k1_ring_store(float2* ring, int idx, float2 v) {
+    const int j = idx & (RING - 1);
+    ring[j] = v;
+    if (j < PAD) ring[j + RING] = v;
+}
+template <int RING, int PAD>
+__device__ __forceinline__ void k1_ring_store2(float2* ring, int idx, float4 v) {     // two entries, idx even
+    static_assert((PAD & 1) == 0, "pairs must not straddle the pad");
+    const int j = idx & (RING - 1);
+    *reinterpret_cast<float4*>(&ring[j]) = v;
+    if (j < PAD) *reinterpret_cast<float4*>(&ring[j + RING]) = v;
+}
 
 // NCO phasors exp(-j 2 pi f m / fs_dec) (processor.py:97-100 evaluated at the decimated rate). The float64 phase is reduced
 // to one turn before the sine/cosine. One out-of-line copy: it runs once per slot and thread, not once per tile.
@@ -235,16 +258,24 @@ __device__ __forceinline__ void k1_phasors10(K1Phasor base, const float2 (&pw)[1
         dst[g] = make_float2(fmaf(bc, pw[g].x, -bs * pw[g].y), fmaf(bc, pw[g].y, bs * pw[g].x));
 }
 
-// Work items and slots. An item is one (carrier, segment); CTA b of a grid of G persistent CTAs owns items
-// b, b + G, b + 2G, ... and streams them back to back as ONE continuous sample stream: slot q of the CTA's
-// stream is t_item tiles long (the segment plus 320 w samples of pre-roll and post-roll) and the four stages
-// simply keep flowing across slot boundaries -- the pipeline is filled and drained once per CTA, not once per
-// item. Only stage A (which tile of which carrier to fetch) and stage D (where an output belongs) look at slots.
+// Work items and slots. An item is one (carrier, segment); every persistent CTA streams the items it claims back to back
+// as ONE continuous sample stream: slot q of the CTA's stream is t_item tiles long (the segment plus 320 w samples of
+// pre-roll and post-roll) and the four stages simply keep flowing across slot boundaries -- the pipeline is filled and
+// drained once per CTA, not once per item. Only stage A (which tile of which carrier to fetch) and stage D (where an
+// output belongs) look at slots.
+// Items are claimed from a counter, one slot ahead: thread 0 takes the item of slot q + 1 at the END of iteration
+// q t_item + t_item - 6 (the producer first needs it three or four iterations later), and every thread re-reads the slot
+// count at the TOP of the next iteration -- one barrier after the claim, t_item - 1 >= 5 barriers before the next one, so all
+// threads of the CTA always agree on it. A CTA that shares its SM with other kernels (block-end corrections, finalize)
+// or sits on a slower SM simply claims fewer items; with a static assignment the slowest CTA set the kernel's time.
+constexpr int K1_NMY_UNKNOWN = 1 << 20;
+constexpr int K1_CLAIM_LEAD = 6;
+static_assert(K1_MIN_T_ITEM >= K1_CLAIM_LEAD, "a slot must be long enough to claim the next one inside it");
 struct K1Slot {
     int car, n_lo, n_hi, O;   // carrier, segment range in y samples, local origin O = n_lo - PREROLL
 };
-__device__ __forceinline__ K1Slot k1_slot(const K1Args& a, int q) {
-    const int it = a.item0 + blockIdx.x + q * gridDim.x;
+__device__ __forceinline__ K1Slot k1_slot(const K1Args& a, const K1Smem& s, int q) {
+    const int it = a.item0 + *reinterpret_cast<const volatile int*>(&s.s_item[q & 7]);
     K1Slot sl;
     sl.car = it / a.n_seg;
     const int seg = it - sl.car * a.n_seg;
@@ -407,28 +438,41 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     constexpr int NB = U8 ? 2 : K1_NBUF;                  // float tile buffers in rotation
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int n_my = (a.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // slots of this CTA
     const int S = a.t_item * K1_W;                        // slot length in w / y samples
-    const int n_load = n_my * a.t_item;                   // tiles of the stream
-    // last kept output sits below stream coordinate n_my S - PREROLL; D_i ends at 640 i + 2 D0 + 639
-    const int n_iter = n_load + (-2 * K1_D0 - K1_PREROLL + K1_W - 1) / K1_W;
+    // slots of this CTA, tiles of its stream, iterations: every thread keeps its own copy, refreshed by k1_tick at the top of
+    // each iteration. The last kept output sits below stream coordinate n_my S - PREROLL; D_i ends at 640 i + 2 D0 + 639.
+    constexpr int DRAIN = (-2 * K1_D0 - K1_PREROLL + K1_W - 1) / K1_W;
+    int n_my = K1_NMY_UNKNOWN, n_load = K1_NMY_UNKNOWN * a.t_item, n_iter = n_load + DRAIN;
+    int rph = a.t_item - (K1_CLAIM_LEAD - 1);             // iterations until the next re-read of the slot count
+    auto k1_tick = [&]() {
+        if (rph == 0) {
+            rph = a.t_item;
+            n_my = *reinterpret_cast<const volatile int*>(&s.s_nmy);
+            n_load = n_my * a.t_item;
+            n_iter = n_load + DRAIN;
+        }
+        --rph;
+    };
 
     // ---- prologue: zero rings/headers, init barriers, start the first two tiles ----
-    for (int i = tid; i < K1_WRING; i += K1_THREADS) s.w[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < K1_URING; i += K1_THREADS) s.u[i] = make_float2(0.f, 0.f);
-    for (int i = tid; i < K1_VRING; i += K1_THREADS) s.v[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_WRING + K1_WPAD; i += K1_THREADS) s.w[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_URING + K1_UPAD; i += K1_THREADS) s.u[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < K1_VRING + K1_VPAD; i += K1_THREADS) s.v[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_NBUF * (K1_HDR + K1_TILE); i += K1_THREADS) (&s.in[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
+        s.s_item[0] = (int)atomicAdd(a.counter, 1u);      // the grid never exceeds the item count: every CTA gets a first item
+        s.s_nmy = K1_NMY_UNKNOWN;
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
         if (U8) for (int b = 0; b < K1_RAWBUF; ++b) mbar_init(&rawfull[b], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
+    __syncthreads();                                      // slot 0's item is known to every thread
     if (ROT) {
-        const K1Slot s0 = k1_slot(a, 0);
+        const K1Slot s0 = k1_slot(a, s, 0);
         if (FO && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
-        if (FO) for (int i = tid; i < K1_RRING; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
+        if (FO) for (int i = tid; i < K1_RRING + K1_RPAD; i += K1_THREADS) sf.ur[i] = make_float2(0.f, 0.f);
         if (MODE == 2 && tid < 2 * TB_PROTO_H + 1) sf.ptap[0][tid] = k1_modulated_tap(tid, a.fo[s0.car], a.fs);
         if (tid >= 256 && tid < 320) {                    // phasors of iteration 0: w [A0, A0 + 640) of slot 0
             K1PhasorSet ps;
@@ -439,13 +483,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     __syncthreads();
     if (warp == 0) {
         if (U8) {
-            for (int j = 0; j < 3 && j < n_load; ++j) k1_issue_stream_tile_u8(s, rawfull, a, j, k1_slot(a, j / a.t_item), j % a.t_item, lane);
+            for (int j = 0; j < 3; ++j) k1_issue_stream_tile_u8(s, rawfull, a, j, k1_slot(a, s, j / a.t_item), j % a.t_item, lane);
         } else if (MODE == 5) {
-            k1_issue_stream_tile_w(s, a, 0, k1_slot(a, 0), 0, lane);
-            if (1 < n_load) k1_issue_stream_tile_w(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
+            k1_issue_stream_tile_w(s, a, 0, k1_slot(a, s, 0), 0, lane);
+            k1_issue_stream_tile_w(s, a, 1, k1_slot(a, s, 1 / a.t_item), 1 % a.t_item, lane);
         } else {
-            k1_issue_stream_tile(s, a, 0, k1_slot(a, 0), 0, lane);
-            if (1 < n_load) k1_issue_stream_tile(s, a, 1, k1_slot(a, 1 / a.t_item), 1 % a.t_item, lane);
+            k1_issue_stream_tile(s, a, 0, k1_slot(a, s, 0), 0, lane);
+            k1_issue_stream_tile(s, a, 1, k1_slot(a, s, 1 / a.t_item), 1 % a.t_item, lane);
         }
     }
     __syncthreads();                                      // rows that are not 16-byte aligned are filled by plain stores
@@ -462,9 +506,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         // (slot, tile-in-slot) of the tile being filtered and of the tile being fetched (two ahead), kept incrementally
         constexpr int AHEAD = U8 ? 3 : 2;                        // tiles the producer runs ahead of the filter
         int q = 0, t = 0, q2 = AHEAD / a.t_item, t2 = AHEAD % a.t_item;
-        K1Slot sl2 = k1_slot(a, min(q2, n_my - 1));
-        int64_t slot_gx = (int64_t)k1_slot(a, 0).O * 10;      // input index of the current slot's first sample
+        K1Slot sl2 = k1_slot(a, s, min(q2, n_my - 1));
+        int64_t slot_gx = (int64_t)k1_slot(a, s, 0).O * 10;      // input index of the current slot's first sample
+        int q_claim = 1;                                      // thread 0: the next slot to claim an item for
         for (int i = 0; i < n_iter; ++i) {
+            k1_tick();
             if (i < n_load) {
                 // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
                 if (U8) {                                      // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
@@ -472,18 +518,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 } else if (MODE == 5) {
                     if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile_w(s, a, i + 2, sl2, t2, lane);
                 } else if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile(s, a, i + 2, sl2, t2, lane);
-                if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, q2); }
+                if (++t2 == a.t_item) { t2 = 0; ++q2; if (q2 < n_my) sl2 = k1_slot(a, s, q2); }
                 const int L5 = tid;                            // 0..127
                 const int64_t gx0 = slot_gx + (int64_t)t * K1_TILE;
                 const int q_now = q;                           // slot of the tile being filtered
-                if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, q).O * 10; }
+                if (++t == a.t_item) { t = 0; ++q; if (q < n_my) slot_gx = (int64_t)k1_slot(a, s, q).O * 10; }
                 if (!U8) mbar_wait(&s.full[i % K1_NBUF], (uint32_t)((i / K1_NBUF) & 1));
                 if (MODE == 5) {
                     // the proto stage ran in the channelizer: the tile IS this iteration's 640 w samples
                     const float2* wsrc = &s.in[i % NB][K1_HDR + 5 * L5];
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
 #pragma unroll
-                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = wsrc[g];
+                    for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, wsrc[g]);
                 }
                 const bool inside = MODE != 5 && gx0 < a.n && gx0 + K1_TILE > 0;
                 if (a.zero_ext && inside && (gx0 < 0 || gx0 + K1_TILE > a.n)) {
@@ -500,11 +546,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     if (U8) {
                         const int done = a.aligned ? ((hi - lo) & ~7) : (hi - lo);
                         if (L5 < hi - lo - done) {
-                            const uint8_t* pb = a.x8 + 2 * ((int64_t)k1_slot(a, q_now).car * a.pitch + gx0 + lo + done + L5);
+                            const uint8_t* pb = a.x8 + 2 * ((int64_t)k1_slot(a, s, q_now).car * a.pitch + gx0 + lo + done + L5);
                             wb[K1_HDR + lo + done + L5] = make_float2(fmaf((float)pb[0], 1.0f / 127.5f, -1.f), fmaf((float)pb[1], 1.0f / 127.5f, -1.f));
                         }
                     } else if (a.aligned && ((hi - lo) & 1) && L5 == 0) {
-                        wb[K1_HDR + hi - 1] = __ldg(a.x + (int64_t)k1_slot(a, q_now).car * a.pitch + gx0 + hi - 1);
+                        wb[K1_HDR + hi - 1] = __ldg(a.x + (int64_t)k1_slot(a, s, q_now).car * a.pitch + gx0 + hi - 1);
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
@@ -546,15 +592,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                         }
                     }
 #pragma unroll
-                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = acc[g];
+                    for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, acc[g]);
                     // tail of this tile -> header of the next buffer
                     if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = buf[K1_TILE + L5];
                 } else if (MODE != 5 && a.zero_ext) {          // a tile entirely outside the block: zeros
                     const int wbase = K1_W * i + K1_A0 + 5 * L5;
 #pragma unroll
-                    for (int g = 0; g < 5; ++g) s.w[(wbase + g) & (K1_WRING - 1)] = make_float2(0.f, 0.f);
+                    for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, make_float2(0.f, 0.f));
                     if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = make_float2(0.f, 0.f);
                 }
+            }
+            if (tid == 0 && rph == 0 && n_my == K1_NMY_UNKNOWN) {     // the next iteration re-reads the slot count: claim now
+                const int it = (int)atomicAdd(a.counter, 1u);
+                if (it < a.n_items) s.s_item[q_claim & 7] = it;
+                else s.s_nmy = q_claim;
+                ++q_claim;
             }
             k1_bar_sync();
         }
@@ -564,6 +616,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
         for (int r = 0; r < 10; ++r) cacc[r] = make_float2(0.f, 0.f);
         for (int i = 0; i < n_iter; ++i) {
+            k1_tick();
             const int q = (i - (warp - 4)) & 3;             // this warp's group is g = i - q
             const int nu0 = K1_U * (i - q) + K1_C0 + 10 * lane;   // first output (stream v index), even
             const int s0 = nu0 - 64 + 32 * q;               // first input sample of this quarter, even
@@ -575,8 +628,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (q == 3) {
 #pragma unroll
                 for (int r = 0; r < 10; r += 2)
-                    *reinterpret_cast<float4*>(&s.v[(nu0 + r) & (K1_VRING - 1)]) =
-                        make_float4(cacc[r].x, cacc[r].y, cacc[r + 1].x, cacc[r + 1].y);
+                    k1_ring_store2<K1_VRING, K1_VPAD>(s.v, nu0 + r, make_float4(cacc[r].x, cacc[r].y, cacc[r + 1].x, cacc[r + 1].y));
             }
             k1_bar_sync();
         }
@@ -584,7 +636,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         // ---------------- role B: half-band /2, 5 outputs per lane ----------------
         const int lb = tid - 256;                           // 0..63
         int qn = 1 / a.t_item, tn = 1 % a.t_item;           // (slot, tile) of the tile stage A filters next iteration
-        K1Slot sn = k1_slot(a, qn);
+        K1Slot sn = k1_slot(a, s, qn);
         // MODE >= 1: phasor of this thread's first w sample of that tile (float64), advanced by one tile per iteration inside
         // a slot (~1e-16 per step over the <= 170 tiles of a slot) and set up afresh when a slot opens
         K1Phasor pbase = {1.0, 0.0}, pstep_tile = {1.0, 0.0};
@@ -604,14 +656,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         if (ROT && qn < n_my)
             open_slot(sn, tn);
         for (int i = 0; i < n_iter; ++i) {
+            k1_tick();
             const int nu0 = K1_U * i + K1_B0 + 5 * lb;
             float2 acc[5];
 #pragma unroll
             for (int r = 0; r < 5; ++r) acc[r] = make_float2(0.f, 0.f);
             const int w0 = 2 * nu0 - TB_HB_H;               // first w sample needed
+            static_assert(2 * 4 + 2 * TB_HB_H + 1 <= K1_WPAD, "half-band window exceeds the w ring's pad");
+            const float2* __restrict__ wp = &s.w[w0 & (K1_WRING - 1)];
 #pragma unroll
             for (int t = 0; t < 2 * 4 + 2 * TB_HB_H + 1; ++t) {
-                const float2 xv = s.w[(w0 + t) & (K1_WRING - 1)];
+                const float2 xv = wp[t];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {
                     const int d = t - 2 * r;                // tap index 0..22 (centre 11)
@@ -622,16 +677,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (FO) {
                 // half-band output -> ring; the carrier's equaliser runs over earlier iterations' entries (no barrier in between)
 #pragma unroll
-                for (int r = 0; r < 5; ++r) sf.ur[(nu0 + r) & (K1_RRING - 1)] = acc[r];
+                for (int r = 0; r < 5; ++r) k1_ring_store<K1_RRING, K1_RPAD>(sf.ur, nu0 + r, acc[r]);
                 // taps of the slot the kept outputs of this range belong to (kept outputs lie PREROLL inside their slot)
                 const float2* tp = sf.rtap[min(max(qr, 0), n_my - 1) & 1];
                 const int ne0 = K1_U * i + K1_R0 + 5 * lb;
                 float2 e[5];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) e[r] = make_float2(0.f, 0.f);
+                static_assert(5 + 2 * TB_REQ_K <= K1_RPAD, "equaliser window exceeds its ring's pad");
+                const float2* __restrict__ rp = &sf.ur[(ne0 - TB_REQ_K) & (K1_RRING - 1)];
 #pragma unroll
                 for (int t = 0; t < 5 + 2 * TB_REQ_K; ++t) {          // ur[ne0 - 5 + t]
-                    const float2 xv = sf.ur[(ne0 - TB_REQ_K + t) & (K1_RRING - 1)];
+                    const float2 xv = rp[t];
                     const float2 xs = make_float2(-xv.y, xv.x);      // j * x
 #pragma unroll
                     for (int r = 0; r < 5; ++r) {
@@ -644,12 +701,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     }
                 }
 #pragma unroll
-                for (int r = 0; r < 5; ++r) s.u[(ne0 + r) & (K1_URING - 1)] = e[r];
+                for (int r = 0; r < 5; ++r) k1_ring_store<K1_URING, K1_UPAD>(s.u, ne0 + r, e[r]);
                 rr += K1_W;
                 if (rr >= S) { rr -= S; ++qr; }
             } else {
 #pragma unroll
-                for (int r = 0; r < 5; ++r) s.u[(nu0 + r) & (K1_URING - 1)] = acc[r];
+                for (int r = 0; r < 5; ++r) k1_ring_store<K1_URING, K1_UPAD>(s.u, nu0 + r, acc[r]);
             }
             if (U8 && i + 1 < n_load) k1_convert_tile_u8<CVB, GB>(s, rawfull, i + 1, 0, lb);   // its share of the tile stage A filters next
             if (ROT && i + 1 < n_load) {
@@ -661,7 +718,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 if (++tn == a.t_item) {
                     tn = 0; ++qn;
                     if (qn < n_my) {
-                        sn = k1_slot(a, qn);
+                        sn = k1_slot(a, s, qn);
                         open_slot(sn, 0);
                     }
                 } else {
@@ -692,7 +749,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             if (ld < K1_NPH) {
                 double t = 0.0;
                 for (int j = 0; j < K1_DLANES; ++j) t += s.bins[ld][j];
-                a.partial[((int64_t)a.item0 + blockIdx.x + (int64_t)q_cur * gridDim.x) * 16 + ld] = t;
+                a.partial[((int64_t)a.item0 + *reinterpret_cast<const volatile int*>(&s.s_item[q_cur & 7])) * 16 + ld] = t;
             }
             asm volatile("bar.sync 2, 64;" ::: "memory");
 #pragma unroll
@@ -702,11 +759,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         // are PREROLL away from slot ends); that slot index is kept incrementally
         int q_it = k1_floordiv(2 * K1_D0 + K1_PREROLL, S), r_it = 2 * K1_D0 + K1_PREROLL - q_it * S;
         for (int i = 0; i < n_iter; ++i) {
+            k1_tick();
             if (q_it != q_cur) {
                 if (q_cur >= 0 && q_cur < n_my) flush(i);
                 q_cur = q_it;
                 if (q_cur >= 0 && q_cur < n_my) {
-                    sl = k1_slot(a, q_cur);
+                    sl = k1_slot(a, s, q_cur);
                     y_lo = max(sl.n_lo, K1_EDGE); y_hi = min(sl.n_hi, a.L - K1_EDGE);
                     // with the zero extension the whole block is stored (the K1_EDGE outputs at each end still lack their
                     // correction, so their power is left to the finalize kernel)
@@ -720,8 +778,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             const int n0 = 2 * nu0 - q_cur * S + sl.O;      // y index of the first output within the carrier (even)
             if (n0 + 10 > st_lo && n0 < st_hi) {
                 float2 v[5 + 2 * TB_INT_K - 1];             // v[nu0-7 .. nu0+4+8]
+                static_assert(5 + 2 * TB_INT_K - 1 <= K1_VPAD, "interpolator window exceeds the v ring's pad");
+                const float2* __restrict__ vp = &s.v[(nu0 - (TB_INT_K - 1)) & (K1_VRING - 1)];
 #pragma unroll
-                for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) v[t] = s.v[(nu0 - (TB_INT_K - 1) + t) & (K1_VRING - 1)];
+                for (int t = 0; t < 5 + 2 * TB_INT_K - 1; ++t) v[t] = vp[t];
                 float2 yv[10];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) {

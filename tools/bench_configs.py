@@ -59,12 +59,33 @@ def main():
                                                          ph.data_ptr(), mt.data_ptr(), stream=0, freq_offsets=fo))
         out[name] = {"ms_per_block": ms, "host_wall_ms": wall, "MS_per_s": n / ms / 1e3, "x_real_time": (n / 2.4e6) / (ms * 1e-3)}
     if want("2"):
-        hx = synth.carrier_iq(n, 0, snr_db=30.0)
-        sp.process(hx)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            sp.process(hx)
-        out["config2_process_host_call_ms"] = (time.perf_counter() - t0) * 100
+        # the class-level call a TetraEar user makes (host numpy in, host numpy out, H2D + D2H + Python inside), at the block
+        # of config 2 and at the GUI's chunk (ui/modern.py:1912 reads 128*1024 samples), for the three input forms
+        def host_call_ms(fn, reps=20):
+            fn(); fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            return (time.perf_counter() - t0) * 1e3 / reps
+
+        calls = {}
+        for label, ns in (("2^20", n), ("gui_chunk_131072", 128 * 1024)):
+            hx = synth.carrier_iq(ns, 0, snr_db=30.0)
+            hx128 = hx.astype(np.complex128)
+            z = hx / np.abs(hx).max() * 0.9
+            raw = np.stack([np.clip(np.round((z.real + 1.0) * 127.5), 0, 255), np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)],
+                           axis=-1).astype(np.uint8)[None]
+            hp = torch.from_numpy(hx).pin_memory().numpy()
+            calls[label] = {
+                "process_complex64_ms": host_call_ms(lambda: sp.process(hx)),
+                "process_complex64_afc_ms": host_call_ms(lambda: sp.process(hx, freq_offset=1234.5)),
+                "process_complex64_pinned_ms": host_call_ms(lambda: sp.process(hp)),
+                "process_complex128_ms": host_call_ms(lambda: sp.process(hx128)),
+                "process_batch_u8_afc_ms": host_call_ms(lambda: sp.process_batch_u8(raw, [1234.5])),
+                "block_duration_ms": ns / 2.4e3,
+            }
+        out["config2_host_calls"] = calls
+        out["config2_process_host_call_ms"] = calls["2^20"]["process_complex64_ms"]
 
     if want("3"):
         # ---- config 3: 96 channels of one 2^20-sample wideband capture ----
