@@ -433,6 +433,21 @@ def run_ours(a):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "parity_spot_check": parity,
             "gather_parity": gather_parity,
         }
+        if world == 1 and not a.no_extra:
+            # the other BASELINE configs on the same box, same process (not the bench metric; tools/bench_configs.py):
+            # configs[2] (96-channel wideband capture) and configs[4] (waterfall STFT), device-resident, CUDA-event timed
+            del x, sym, mt
+            torch.cuda.empty_cache()
+            try:
+                import importlib.util
+                spec = importlib.util.spec_from_file_location("bench_configs", os.path.join(ROOT, "tools", "bench_configs.py"))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                oc = mod.run(only=["2", "3", "5"], device=local)
+                out["other_configs"] = {k: oc[k] for k in ("config2_one_carrier_fo0", "config2_host_calls", "config3_wideband_96ch_device_resident",
+                                                           "config5_stft_4096_hop1024", "config5_stft_4096_hop1024_30s") if k in oc}
+            except Exception as e:                            # never lose the bench line over the extras
+                out["other_configs"] = {"error": repr(e)}
         a.out.write(json.dumps(out) + "\n")
         a.out.flush()
     if world > 1:
@@ -458,6 +473,7 @@ def main():
     ap.add_argument("--carriers", type=int, default=TOTAL_CARRIERS)
     ap.add_argument("--e2e-carriers", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs appended to the N = 1 line")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange of the dibit streams -- the library's peer-memory kernels (default) or NCCL all-gather")
     ap.add_argument("--fo-max", type=float, default=0.0, help="per-carrier freq_offset drawn from +-this (Hz); 0 = BASELINE workload")

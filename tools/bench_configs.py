@@ -18,13 +18,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
+def run(only=None, device=0):
+    """Measure the selected configs ("2", "3", "u8", "5"; None = TETRA_CONFIGS or all) on `device`; returns the dict."""
     import torch
     from tetraear_b200 import synth
     from tetraear_b200.processor import SignalProcessor
     out = {}
-    dev = torch.device("cuda", 0)
-    sp = SignalProcessor(2.4e6, device=0)
+    dev = torch.device("cuda", device)
+    sp = SignalProcessor(2.4e6, device=device)
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
 
     def timed(fn, reps=20, warm=3):
@@ -40,7 +41,8 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps, (time.perf_counter() - t0) * 1e3 / reps
 
-    only = [t for t in os.environ.get("TETRA_CONFIGS", "").split(",") if t]      # e.g. TETRA_CONFIGS=3 under ncu
+    if only is None:
+        only = [t for t in os.environ.get("TETRA_CONFIGS", "").split(",") if t]      # e.g. TETRA_CONFIGS=3 under ncu
 
     def want(tag):
         return not only or tag in only
@@ -172,9 +174,9 @@ def main():
         out["config5_stft_4096_hop1024_30s"] = {"ms_per_call": ms, "rows_per_s": rows_l / (ms * 1e-3), "MS_per_s": nl / ms / 1e3,
                                                 "x_real_time": 30e3 / ms, "GB_per_s_at_24B_per_sample": by / (ms * 1e-3) / 1e9,
                                                 "frac_of_measured_hbm_peak": by / (ms * 1e-3) / 1e9 / peak}
-    print(json.dumps(out, indent=1))
     sp.close()
+    return out
 
 
 if __name__ == "__main__":
-    main()
+    print(json.dumps(run(), indent=1))
