@@ -265,6 +265,176 @@ __global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db(const float2* __
     }
 }
 
+// ----------------------------------------------------------------------------------------------
+// K3, two rows per thread: the same three radix-16 passes with every value held as a PACKED PAIR (row r, row r + 1) --
+// Blackwell's fp32x2 instructions (SASS FADD2 / FMUL2 / FFMA2; twiddles and constants enter as broadcast scalar operands,
+// which the packed forms take for free) do each butterfly step of both rows in one issue slot. Real and imaginary parts
+// live in separate register pairs, so the +-j rotations of the radix-4 butterflies stay free. The kernel above is
+// issue-bound (1099 instructions per thread and row, 59 % of the issue slots, 43 % of the FMA pipes); this one needs about
+// half the issue slots per row. Shared memory: one row-pair buffer of float4 {re_A, re_B, im_A, im_B} (padded), the
+// twiddle tables, half of the symmetric window: 110 KB, two CTAs per SM.
+// ----------------------------------------------------------------------------------------------
+typedef unsigned long long pk2;                                      // two floats: (row A, row B)
+__device__ __forceinline__ pk2 pk_add(pk2 a, pk2 b) { pk2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk_sub(pk2 a, pk2 b) { pk2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk_mul(pk2 a, pk2 b) { pk2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ pk2 pk_fma(pk2 a, pk2 b, pk2 c) { pk2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ pk2 pk_dup(float x) { pk2 d; asm("mov.b64 %0, {%1, %1};" : "=l"(d) : "f"(x)); return d; }   // folds into a scalar operand
+__device__ __forceinline__ pk2 pk_make(float a, float b) { pk2 d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(a), "f"(b)); return d; }
+__device__ __forceinline__ void pk_split(pk2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+struct pkc { pk2 re, im; };                                          // a complex value of both rows
+__device__ __forceinline__ pkc pkc_add(pkc a, pkc b) { return pkc{pk_add(a.re, b.re), pk_add(a.im, b.im)}; }
+__device__ __forceinline__ pkc pkc_sub(pkc a, pkc b) { return pkc{pk_sub(a.re, b.re), pk_sub(a.im, b.im)}; }
+__device__ __forceinline__ pkc pkc_add_mj(pkc a, pkc b) { return pkc{pk_add(a.re, b.im), pk_sub(a.im, b.re)}; }   // a + (-j) b
+__device__ __forceinline__ pkc pkc_add_pj(pkc a, pkc b) { return pkc{pk_sub(a.re, b.im), pk_add(a.im, b.re)}; }   // a + (+j) b
+__device__ __forceinline__ pkc pkc_mulc(pkc a, float c, float s) {                                                 // a * (c + j s)
+    const pk2 cc = pk_dup(c), ss = pk_dup(s);
+    return pkc{pk_sub(pk_mul(a.re, cc), pk_mul(a.im, ss)), pk_fma(a.re, ss, pk_mul(a.im, cc))};
+}
+// b[k] = sum_n a[n] exp(-2 pi j n k / 16), in place (the butterfly network of dft16 above)
+__device__ __forceinline__ void dft16_pk(pkc (&a)[16]) {
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, h = 0.70710678118654752f;
+    pkc t[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const pkc s02 = pkc_add(a[i], a[i + 8]), d02 = pkc_sub(a[i], a[i + 8]);
+        const pkc s13 = pkc_add(a[i + 4], a[i + 12]), d13 = pkc_sub(a[i + 4], a[i + 12]);
+        t[i][0] = pkc_add(s02, s13);
+        t[i][1] = pkc_add_mj(d02, d13);
+        t[i][2] = pkc_sub(s02, s13);
+        t[i][3] = pkc_add_pj(d02, d13);
+    }
+    // y[i] = t[i][q] W16^(i q): q = 0 none; the others by value (i q = 1, 2, 3 | 2, 4, 6 | 3, 6, 9)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        pkc y0 = t[0][q], y1, y2, y3;
+        if (q == 0) { y1 = t[1][0]; y2 = t[2][0]; y3 = t[3][0]; }
+        else if (q == 1) { y1 = pkc_mulc(t[1][1], c1, -s1); y2 = pkc_mulc(t[2][1], h, -h); y3 = pkc_mulc(t[3][1], s1, -c1); }
+        else if (q == 2) { y1 = pkc_mulc(t[1][2], h, -h); y2 = t[2][2]; y3 = pkc_mulc(t[3][2], -h, -h); }     // y2 still needs its -j
+        else { y1 = pkc_mulc(t[1][3], s1, -c1); y2 = pkc_mulc(t[2][3], -h, -h); y3 = pkc_mulc(t[3][3], -c1, s1); }
+        pkc s02, d02;
+        if (q == 2) { s02 = pkc_add_mj(y0, y2); d02 = pkc_add_pj(y0, y2); }      // y0 +- (-j) t
+        else { s02 = pkc_add(y0, y2); d02 = pkc_sub(y0, y2); }
+        const pkc s13 = pkc_add(y1, y3), d13 = pkc_sub(y1, y3);
+        a[q] = pkc_add(s02, s13);
+        a[q + 4] = pkc_add_mj(d02, d13);
+        a[q + 8] = pkc_sub(s02, s13);
+        a[q + 12] = pkc_add_pj(d02, d13);
+    }
+}
+
+struct S4kPairSmem {
+    float4 buf[S4K_N + S4K_N / 16];      // {re_A, re_B, im_A, im_B}
+    float2 tw3[16][256];
+    float2 tw2[16][16];
+    float win[S4K_N / 2];                // symmetric: win[t] = win[N - 1 - t]
+};
+static_assert(2 * (sizeof(S4kPairSmem) + 1024) <= 227 * 1024, "two CTAs per SM");
+
+__global__ void __launch_bounds__(S4K_THREADS, 2) k_stft4096_db2(const float2* __restrict__ x, int hop, int64_t rows, float* __restrict__ out,
+                                                                 const S4kTables* __restrict__ tab) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    S4kPairSmem& sm = *reinterpret_cast<S4kPairSmem*>(sm_raw);
+    const int j = threadIdx.x;
+    {
+        const float4* src = reinterpret_cast<const float4*>(tab);          // tw3 and tw2 lie first in S4kTables
+        float4* dst = reinterpret_cast<float4*>(&sm.tw3[0][0]);
+        for (int t = j; t < (int)((sizeof(sm.tw3) + sizeof(sm.tw2)) / 16); t += S4K_THREADS) dst[t] = __ldg(src + t);
+        for (int t = j; t < S4K_N / 2; t += S4K_THREADS) sm.win[t] = __ldg(&tab->win[t]);
+    }
+    __syncthreads();
+    const int k = j & 15;
+    const int64_t pairs = (rows + 1) / 2;
+    for (int64_t p = blockIdx.x; p < pairs; p += gridDim.x) {
+        const int64_t ra = 2 * p;
+        const bool has_b = ra + 1 < rows;
+        const float2* xa = x + ra * hop;
+        const float2* xb = has_b ? xa + hop : xa;
+        pkc a[16];
+        // pass 1 (sub-transform size 1): inputs j + 256 q of both rows straight from global memory, windowed
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int t = j + 256 * q;
+            const float2 va = __ldg(xa + t), vb = __ldg(xb + t);
+            const float w = sm.win[q < 8 ? t : S4K_N - 1 - t];
+            a[q].re = pk_make(va.x * w, vb.x * w);
+            a[q].im = pk_make(va.y * w, vb.y * w);
+        }
+        dft16_pk(a);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            float4 v;
+            pk_split(a[q].re, v.x, v.y); pk_split(a[q].im, v.z, v.w);
+            sm.buf[s4k_pad(16 * j + q)] = v;
+        }
+        __syncthreads();
+        // pass 2 (sub-transform size 16): twiddle W_256^(q k), k = j mod 16
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 v = sm.buf[s4k_pad(j + 256 * q)];
+            const pkc c{pk_make(v.x, v.y), pk_make(v.z, v.w)};
+            if (q == 0) a[q] = c;
+            else { const float2 w = sm.tw2[q][k]; a[q] = pkc_mulc(c, w.x, w.y); }
+        }
+        __syncthreads();
+        dft16_pk(a);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            float4 v;
+            pk_split(a[q].re, v.x, v.y); pk_split(a[q].im, v.z, v.w);
+            sm.buf[s4k_pad((j - k) * 16 + k + 16 * q)] = v;
+        }
+        __syncthreads();
+        // pass 3 (sub-transform size 256): twiddle W_4096^(q j); outputs X[j + 256 q]
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const float4 v = sm.buf[s4k_pad(j + 256 * q)];
+            const pkc c{pk_make(v.x, v.y), pk_make(v.z, v.w)};
+            if (q == 0) a[q] = c;
+            else { const float2 w = sm.tw3[q][j]; a[q] = pkc_mulc(c, w.x, w.y); }
+        }
+        __syncthreads();                                 // the buffer is free for the next pair's pass 1
+        dft16_pk(a);
+        float* oa = out + ra * S4K_N;
+        float* ob = has_b ? oa + S4K_N : oa;             // an odd last row is simply written twice
+        // 20 log10(sqrt(p) / N + 1e-20) = 10 log10(p) - 20 log10(N) while the 1e-20 stays below 4e-9 of the magnitude (3.6e-8 dB);
+        // bins below that (an all-zero row, 160 dB under full scale) are redone with the literal expression afterwards
+        bool small = false;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int col = (j + 256 * q + S4K_N / 2) & (S4K_N - 1);       // fftshift
+            float pa, pb;
+            pk_split(pk_fma(a[q].re, a[q].re, pk_mul(a[q].im, a[q].im)), pa, pb);
+            small |= fminf(pa, pb) < 1e-16f;
+            float la, lb;                                  // bare MUFU.LG2: values below 1e-16 (denormals included) are redone below
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(la) : "f"(pa));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lb) : "f"(pb));
+            oa[col] = fmaf(3.010299956639812f, la, -72.24719895935549f);
+            ob[col] = fmaf(3.010299956639812f, lb, -72.24719895935549f);
+        }
+        if (small) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int col = (j + 256 * q + S4K_N / 2) & (S4K_N - 1);
+                float pa, pb;
+                pk_split(pk_fma(a[q].re, a[q].re, pk_mul(a[q].im, a[q].im)), pa, pb);
+                if (pa < 1e-16f) oa[col] = 6.020599913f * __log2f(sqrtf(pa) * (1.0f / (float)S4K_N) + 1e-20f);
+                if (pb < 1e-16f) ob[col] = 6.020599913f * __log2f(sqrtf(pb) * (1.0f / (float)S4K_N) + 1e-20f);
+            }
+        }
+    }
+}
+
+static int stft4096_pair_launch(cudaStream_t st, const float2* x, int hop, int64_t rows, float* out, const S4kTables* tab) {
+    if (cudaFuncSetAttribute(k_stft4096_db2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S4kPairSmem)) != cudaSuccess) return -1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)std::min<int64_t>((rows + 1) / 2, (int64_t)sms * 2);
+    k_stft4096_db2<<<grid, S4K_THREADS, sizeof(S4kPairSmem), st>>>(x, hop, rows, out, tab);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;
+}
+
 static int stft4096_launch(cudaStream_t st, const float2* x, int hop, int64_t rows, float* out, const S4kTables* tab) {
     if (cudaFuncSetAttribute(k_stft4096_db, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(S4kSmem)) != cudaSuccess) return -1;
     int dev = 0, sms = 148;
@@ -296,7 +466,10 @@ static int stft_launch(cudaStream_t st, const float2* x, int64_t n, int nfft, in
         case 512: return stft_launch_t<512>(st, x, n, hop, rows, out);
         case 1024: return stft_launch_t<1024>(st, x, n, hop, rows, out);
         case 2048: return stft_launch_t<2048>(st, x, n, hop, rows, out);
-        case 4096: return stft4096_launch(st, x, hop, rows, out, tab4k);
+        case 4096: {
+            static const int pair = getenv("TETRA_STFT_PAIR") ? atoi(getenv("TETRA_STFT_PAIR")) : 1;   // 0: the one-row kernel (A/B)
+            return pair ? stft4096_pair_launch(st, x, hop, rows, out, tab4k) : stft4096_launch(st, x, hop, rows, out, tab4k);
+        }
         case 8192: return stft_launch_t<8192>(st, x, n, hop, rows, out);
     }
     return -1;
