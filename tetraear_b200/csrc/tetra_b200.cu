@@ -156,6 +156,19 @@ int upload_tables(tetra_ctx* ctx) {
     memset(fir, 0, sizeof fir);
     memcpy(fir + 1, TB_FIR120_TAPS, sizeof(float) * (2 * TB_FIR_H + 1));   // 127 taps behind one zero
     CK(cudaMemcpyToSymbol(c_proto, TB_PROTO_TAPS, sizeof(float) * (2 * TB_PROTO_H + 1)));
+    {
+        // byte input (MODE 3 / 4): taps / 127.5 and 127.5 x their running sums (tetra_kernels.cuh)
+        float p8[2 * TB_PROTO_H + 1], pre[2 * TB_PROTO_H + 3];
+        double run = 0.0;
+        for (int d = 0; d <= 2 * TB_PROTO_H; ++d) p8[d] = (float)((double)TB_PROTO_TAPS[d] / 127.5);
+        for (int k = 0; k <= 2 * TB_PROTO_H + 1; ++k) {
+            pre[k] = (float)(127.5 * run);
+            if (k <= 2 * TB_PROTO_H) run += (double)p8[k];
+        }
+        pre[2 * TB_PROTO_H + 2] = pre[2 * TB_PROTO_H + 1];
+        CK(cudaMemcpyToSymbol(c_proto8, p8, sizeof p8));
+        CK(cudaMemcpyToSymbol(c_proto8_pre, pre, sizeof pre));
+    }
     CK(cudaMemcpyToSymbol(c_hb, TB_HB_TAPS, sizeof(float) * (2 * TB_HB_H + 1)));
     CK(cudaMemcpyToSymbol(c_fir, fir, sizeof fir));
     CK(cudaMemcpyToSymbol(c_interp, TB_INTERP_TAPS, sizeof(float) * TB_INT_K));

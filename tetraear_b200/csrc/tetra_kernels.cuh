@@ -141,6 +141,8 @@ struct K1SmemFo {
 // byte tiles (2 bytes per sample) the bulk copies fill three tiles ahead
 constexpr int K1_RAWBUF = 4;
 constexpr int K1_RAW_BYTES = 2 * K1_TILE;
+constexpr int K1_RAW_HDR = 2 * K1_HDR;                      // bytes of the previous tile kept in front of each raw slot
+constexpr int K1_RAW_SLOT = K1_RAW_HDR + K1_RAW_BYTES;      // slot stride: [header | tile]
 struct K1SmemU8 {
     K1Smem base;
     uint64_t rawfull[K1_RAWBUF];
@@ -150,12 +152,14 @@ struct K1SmemFoU8 {
     K1SmemFo fo;
     uint64_t rawfull[K1_RAWBUF];
 };
-static_assert(K1_RAWBUF * K1_RAW_BYTES <= (int)sizeof(float2) * (K1_HDR + K1_TILE), "raw byte ring does not fit the third tile buffer");
-static_assert((sizeof(float2) * (K1_HDR + K1_TILE)) % 16 == 0 && K1_RAW_BYTES % 16 == 0, "bulk copies need 16-byte aligned slots");
+static_assert(K1_RAWBUF * K1_RAW_SLOT <= (int)sizeof(float2) * K1_NBUF * (K1_HDR + K1_TILE), "raw byte ring does not fit the tile buffers");
+static_assert(K1_RAW_SLOT % 16 == 0 && K1_RAW_HDR % 16 == 0 && (50 * 2) % 4 == 0, "bulk copies need 16-byte aligned slot bodies, windows start on words");
 static_assert(sizeof(K1SmemFo) <= 227 * 1024 && sizeof(K1SmemU8) <= 227 * 1024 && sizeof(K1SmemFoU8) <= 227 * 1024,
               "K1 shared memory exceeds the 227 KB a CTA may use");
 
 __constant__ float c_proto[2 * TB_PROTO_H + 1];
+__constant__ float c_proto8[2 * TB_PROTO_H + 1];          // c_proto / 127.5 (byte input)
+__constant__ float c_proto8_pre[2 * TB_PROTO_H + 3];      // c_proto8_pre[k] = 127.5 * sum_{d < k} c_proto8[d], k = 0 .. 41
 __constant__ float c_hb[2 * TB_HB_H + 1];
 __constant__ float c_fir[128];                    // c_fir[0] = 0, c_fir[1 + k] = fir120 tap k (127 taps): v[n] = sum_k c_fir[k] u[n - 64 + k]
 __constant__ float c_interp[TB_INT_K];
@@ -324,11 +328,15 @@ __device__ __forceinline__ void k1_issue_stream_tile_w(K1Smem& s, const K1Args& 
     }
 }
 
+// MODE 3 / 4: the byte ring lives where the float tile buffers are (stage A filters the bytes as they are)
+__device__ __forceinline__ uint8_t* k1_raw_slot(K1Smem& sb, int i) {          // body of slot i % RAWBUF (its header lies in front)
+    return reinterpret_cast<uint8_t*>(&sb.in[0][0]) + (i % K1_RAWBUF) * K1_RAW_SLOT + K1_RAW_HDR;
+}
 // MODE 3: raw byte tile i of this CTA's stream -> slot i % RAWBUF of the byte ring
 __device__ __forceinline__ void k1_issue_stream_tile_u8(K1Smem& sb, uint64_t* rawfull, const K1Args& a, int i, const K1Slot& sl, int t, int lane) {
     const uint8_t* xc = a.x8 + 2 * (int64_t)sl.car * a.pitch;
     const int64_t gx0 = (int64_t)sl.O * 10 + (int64_t)t * K1_TILE;        // a multiple of 8 (segments are multiples of 640 outputs)
-    uint8_t* dst = reinterpret_cast<uint8_t*>(&sb.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES;
+    uint8_t* dst = k1_raw_slot(sb, i);
     uint64_t* bar = &rawfull[i % K1_RAWBUF];
     const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
     const int hi = (int)max((int64_t)lo, min((int64_t)K1_TILE, a.n - gx0));
@@ -348,53 +356,13 @@ __device__ __forceinline__ void k1_issue_stream_tile_u8(K1Smem& sb, uint64_t* ra
         if (lane == 0) mbar_arrive(bar);
     }
 }
-// MODE 3: raw slot -> float tile, (byte / 127.5) - 1 per component (pyrtlsdr packed_bytes_to_iq, signal/capture.py:143-158).
-// The byte is placed in the mantissa of 2^23 (one PRMT), so no integer-to-float conversion is issued; the result is
-// within one float32 ulp of the float64 expression. Words [k0, k0 + 64 STEPS) of the tile by 64 threads: two samples
-// (one 32-bit word -> one 16-byte store) per thread and step, all loads of a group issued before the first use.
-constexpr int K1_CV_B = 32, K1_CV_D = 18;     // steps taken by stage B's / stage D's 64 threads (B has more slack)
-constexpr int K1_CV_B_FO = 8, K1_CV_D_FO = 42;   // with a freq_offset stage B also runs the equaliser: stage D takes most of the tile
-static_assert(64 * (K1_CV_B + K1_CV_D) == K1_TILE / 2 && 64 * (K1_CV_B_FO + K1_CV_D_FO) == K1_TILE / 2, "the conversion must cover the tile");
-// G loads in flight per group; the group loop stays rolled (the kernel's code must keep fitting the instruction cache)
-template <int STEPS, int G>
-__device__ __forceinline__ void k1_convert_tile_u8(K1Smem& sb, uint64_t* rawfull, int i, int k0, int l64) {
-    static_assert(STEPS % G == 0, "whole groups");
-    mbar_wait(&rawfull[i % K1_RAWBUF], (uint32_t)((i / K1_RAWBUF) & 1));
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(&sb.in[2][0]) + (i % K1_RAWBUF) * K1_RAW_BYTES) + k0 + l64;
-    float4* dst = reinterpret_cast<float4*>(&sb.in[i & 1][K1_HDR]) + k0 + l64;
-    // packed constants (-2^23, -2^23), (1/127.5, 1/127.5), (-1, -1)
-    unsigned long long p_off, p_sc, p_m1;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(p_off) : "f"(-8388608.f));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(p_sc) : "f"(1.0f / 127.5f));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(p_m1) : "f"(-1.f));
-#pragma unroll 1
-    for (int g0 = 0; g0 < STEPS; g0 += G, src += 64 * G, dst += 64 * G) {
-        uint32_t w[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) w[g] = src[64 * g];
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-            float4 v;
-            asm("{\n\t.reg .b32 a0, a1, a2, a3;\n\t.reg .b64 q0, q1;\n\t"
-                "prmt.b32 a0, %4, 0x4B000000, 0x7440;\n\t"
-                "prmt.b32 a1, %4, 0x4B000000, 0x7441;\n\t"
-                "prmt.b32 a2, %4, 0x4B000000, 0x7442;\n\t"
-                "prmt.b32 a3, %4, 0x4B000000, 0x7443;\n\t"
-                "mov.b64 q0, {a0, a1};\n\t"
-                "mov.b64 q1, {a2, a3};\n\t"
-                "add.rn.f32x2 q0, q0, %5;\n\t"
-                "add.rn.f32x2 q1, q1, %5;\n\t"
-                "fma.rn.f32x2 q0, q0, %6, %7;\n\t"
-                "fma.rn.f32x2 q1, q1, %6, %7;\n\t"
-                "mov.b64 {%0, %1}, q0;\n\t"
-                "mov.b64 {%2, %3}, q1;\n\t}"
-                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                : "r"(w[g]), "l"(p_off), "l"(p_sc), "l"(p_m1));
-            dst[64 * g] = v;
-        }
-    }
-}
-
+// MODE 3 / 4: stage A filters the raw bytes. A sample is (byte / 127.5) - 1 per component (pyrtlsdr packed_bytes_to_iq,
+// signal/capture.py:143-158), so  sum_d p[d] (b[d] / 127.5 - 1) = sum_d (p[d] / 127.5) b[d] - sum_d p[d]:  the taps are
+// scaled once (c_proto8), every output starts from -sum p, and a byte only has to become the float b -- one PRMT puts it
+// into the mantissa of 2^23, one packed add per sample takes the 2^23 off again (exact). Nothing is expanded in shared
+// memory: 2 bytes per sample are read where the float path reads 8. Samples outside the block are zero in the reference's
+// zero-extended stream, i.e. b = 127.5, which no byte holds: their bytes are set to 0 and each output gets back what its
+// taps over them took away, 127.5 * sum_{d outside} p8[d] (c_proto8_pre holds the running sums).
 // modulated proto taps of a channel at offset f: q[d] = c_proto[d] exp(-j 2 pi f (d - 20) / fs). With them and the w rotation
 // exp(-j 2 pi f 10 m / fs) stage A computes proto(x[n] exp(-j 2 pi f n / fs)) without ever forming the shifted stream.
 __device__ __forceinline__ float2 k1_modulated_tap(int d, double f, double fs) {
@@ -432,10 +400,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     constexpr bool FO = MODE == 1 || MODE == 4;           // per-carrier freq_offset: NCO on the w samples + equaliser
     constexpr bool ROT = FO || MODE == 2;                 // the w samples are rotated
     uint64_t* const rawfull = MODE == 4 ? reinterpret_cast<K1SmemFoU8*>(smem_raw)->rawfull : reinterpret_cast<K1SmemU8*>(smem_raw)->rawfull;
-    constexpr int CVB = FO ? K1_CV_B_FO : K1_CV_B, CVD = FO ? K1_CV_D_FO : K1_CV_D;   // conversion steps of stage B's / stage D's threads
-    constexpr int GB = FO ? 8 : 8, GD = FO ? 6 : 6;       // loads in flight per conversion group
-    static_assert(CVB % GB == 0 && CVD % GD == 0, "whole conversion groups");
-    constexpr int NB = U8 ? 2 : K1_NBUF;                  // float tile buffers in rotation
+    constexpr int NB = K1_NBUF;                           // float tile buffers in rotation (the byte ring takes their place in MODE 3 / 4)
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int S = a.t_item * K1_W;                        // slot length in w / y samples
@@ -493,11 +458,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         }
     }
     __syncthreads();                                      // rows that are not 16-byte aligned are filled by plain stores
-    if (U8) {                                             // tile 0 is converted before the roles start
-        if (warp == 8 || warp == 9) k1_convert_tile_u8<CVB, GB>(s, rawfull, 0, 0, tid - 256);
-        if (warp >= 10) k1_convert_tile_u8<CVD, GD>(s, rawfull, 0, 64 * CVB, tid - 320);
-        __syncthreads();
-    }
 
     // Each role runs its own loop (own loop-carried registers); all of them meet once per iteration at
     // barrier 0 (bar.sync with the full CTA thread count is well defined from divergent code paths).
@@ -532,6 +492,92 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, wsrc[g]);
                 }
                 const bool inside = MODE != 5 && gx0 < a.n && gx0 + K1_TILE > 0;
+                if (U8) {
+                    mbar_wait(&rawfull[i % K1_RAWBUF], (uint32_t)((i / K1_RAWBUF) & 1));
+                    uint8_t* body = k1_raw_slot(s, i);
+                    uint32_t* next_hdr = reinterpret_cast<uint32_t*>(k1_raw_slot(s, i + 1) - K1_RAW_HDR);
+                    const bool edge_tile = inside && (gx0 < 0 || gx0 + K1_TILE > a.n);
+                    if (a.zero_ext && edge_tile) {
+                        // a tile that straddles a block end: bytes outside the block become 0 (corrected for below); the block's
+                        // last samples a bulk copy of whole 16-byte units left out come by plain loads
+                        const int lo = gx0 < 0 ? (int)min((int64_t)K1_TILE, -gx0) : 0;
+                        const int hi = (int)min((int64_t)K1_TILE, a.n - gx0);
+                        uint16_t* b16 = reinterpret_cast<uint16_t*>(body);
+                        if (gx0 <= 0 && L5 < K1_HDR) b16[L5 - K1_HDR] = 0;              // the header precedes the block as well
+                        for (int k = L5; k < lo; k += 128) b16[k] = 0;
+                        for (int k = hi + L5; k < K1_TILE; k += 128) b16[k] = 0;
+                        const int done = a.aligned ? ((hi - lo) & ~7) : (hi - lo);
+                        if (L5 < hi - lo - done)
+                            b16[lo + done + L5] = __ldg(reinterpret_cast<const uint16_t*>(a.x8 + 2 * ((int64_t)k1_slot(a, s, q_now).car * a.pitch + gx0)) + lo + done + L5);
+                        asm volatile("bar.sync 1, 128;" ::: "memory");
+                    }
+                    if (inside) {
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(body) + 25 * L5 - K1_RAW_HDR / 4;   // sample 50 L5 - 40 of the tile
+                        float2 acc[5];
+                        const float dc = -c_proto8_pre[2 * TB_PROTO_H + 1];        // -sum p: the "-1" of every sample
+#pragma unroll
+                        for (int g = 0; g < 5; ++g) acc[g] = make_float2(dc, dc);
+                        unsigned long long p_off;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(p_off) : "f"(-8388608.f));
+#pragma unroll
+                        for (int t2 = 0; t2 < 41; ++t2) {
+                            const uint32_t wv = wp[t2];                             // I0 Q0 I1 Q1
+                            float2 x0, x1;
+                            asm("{\n\t.reg .b32 a0, a1, a2, a3;\n\t.reg .b64 q0, q1;\n\t"
+                                "prmt.b32 a0, %4, 0x4B000000, 0x7440;\n\t"
+                                "prmt.b32 a1, %4, 0x4B000000, 0x7441;\n\t"
+                                "prmt.b32 a2, %4, 0x4B000000, 0x7442;\n\t"
+                                "prmt.b32 a3, %4, 0x4B000000, 0x7443;\n\t"
+                                "mov.b64 q0, {a0, a1};\n\t"
+                                "mov.b64 q1, {a2, a3};\n\t"
+                                "add.rn.f32x2 q0, q0, %5;\n\t"
+                                "add.rn.f32x2 q1, q1, %5;\n\t"
+                                "mov.b64 {%0, %1}, q0;\n\t"
+                                "mov.b64 {%2, %3}, q1;\n\t}"
+                                : "=f"(x0.x), "=f"(x0.y), "=f"(x1.x), "=f"(x1.y)
+                                : "r"(wv), "l"(p_off));
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int tt = 2 * t2 + h;
+                                const float2 xv = h ? x1 : x0;
+#pragma unroll
+                                for (int g = 0; g < 5; ++g) {
+                                    const int d = tt - 10 * g;
+                                    if (d >= 0 && d <= 40) acc[g] = ffma2(xv, c_proto8[d], acc[g]);
+                                }
+                            }
+                        }
+                        if (a.zero_ext && (edge_tile || gx0 == 0)) {
+                            // taps over samples outside the block saw byte 0 instead of 127.5
+                            const int64_t s0 = gx0 + 50 * L5 - K1_HDR;              // input index of this thread's first window sample
+#pragma unroll
+                            for (int g = 0; g < 5; ++g) {
+                                const int64_t first = s0 + 10 * g;                  // input index under tap 0 of output g
+                                const int d0 = (int)min((int64_t)(2 * TB_PROTO_H + 1), max((int64_t)0, -first));          // taps d < d0 lie before the block
+                                const int d1 = (int)min((int64_t)(2 * TB_PROTO_H + 1), max((int64_t)0, a.n - first));     // taps d >= d1 lie behind it
+                                const float c = c_proto8_pre[d0] + (c_proto8_pre[2 * TB_PROTO_H + 1] - c_proto8_pre[d1]);
+                                acc[g].x += c; acc[g].y += c;
+                            }
+                        }
+                        const int wbase = K1_W * i + K1_A0 + 5 * L5;
+                        if (ROT) {
+#pragma unroll
+                            for (int g = 0; g < 5; ++g) {
+                                const float2 p = sf.ph[i & 1][5 * L5 + g];
+                                acc[g] = make_float2(acc[g].x * p.x - acc[g].y * p.y, acc[g].x * p.y + acc[g].y * p.x);
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, acc[g]);
+                        // tail of this tile -> header of the next slot
+                        if (L5 < K1_RAW_HDR / 4) next_hdr[L5] = reinterpret_cast<const uint32_t*>(body)[K1_RAW_BYTES / 4 - K1_RAW_HDR / 4 + L5];
+                    } else if (a.zero_ext) {                   // a tile entirely outside the block: zeros
+                        const int wbase = K1_W * i + K1_A0 + 5 * L5;
+#pragma unroll
+                        for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, make_float2(0.f, 0.f));
+                        if (L5 < K1_RAW_HDR / 4) next_hdr[L5] = 0u;
+                    }
+                } else {
                 if (a.zero_ext && inside && (gx0 < 0 || gx0 + K1_TILE > a.n)) {
                     // a tile that straddles a block end: what lies outside the block becomes zero (the cascade then computes
                     // the shift-invariant response of the zero-extended block, which the block-end corrections refer to)
@@ -542,14 +588,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     if (gx0 < 0 && L5 < K1_HDR) wb[L5] = zero;                  // the header precedes the block as well
                     for (int k = L5; k < lo; k += 128) wb[K1_HDR + k] = zero;
                     for (int k = hi + L5; k < K1_TILE; k += 128) wb[K1_HDR + k] = zero;
-                    // a bulk copy moves whole 16-byte units: the block's last samples it left out come by plain loads
-                    if (U8) {
-                        const int done = a.aligned ? ((hi - lo) & ~7) : (hi - lo);
-                        if (L5 < hi - lo - done) {
-                            const uint8_t* pb = a.x8 + 2 * ((int64_t)k1_slot(a, s, q_now).car * a.pitch + gx0 + lo + done + L5);
-                            wb[K1_HDR + lo + done + L5] = make_float2(fmaf((float)pb[0], 1.0f / 127.5f, -1.f), fmaf((float)pb[1], 1.0f / 127.5f, -1.f));
-                        }
-                    } else if (a.aligned && ((hi - lo) & 1) && L5 == 0) {
+                    // a bulk copy moves whole 16-byte units: the block's last sample it left out comes by a plain load
+                    if (a.aligned && ((hi - lo) & 1) && L5 == 0) {
                         wb[K1_HDR + hi - 1] = __ldg(a.x + (int64_t)k1_slot(a, s, q_now).car * a.pitch + gx0 + hi - 1);
                     }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -601,6 +641,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                     for (int g = 0; g < 5; ++g) k1_ring_store<K1_WRING, K1_WPAD>(s.w, wbase + g, make_float2(0.f, 0.f));
                     if (L5 < K1_HDR) s.in[(i + 1) % NB][L5] = make_float2(0.f, 0.f);
                 }
+                }   // float input
             }
             if (tid == 0 && rph == 0 && n_my == K1_NMY_UNKNOWN) {     // the next iteration re-reads the slot count: claim now
                 const int it = (int)atomicAdd(a.counter, 1u);
@@ -708,7 +749,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
 #pragma unroll
                 for (int r = 0; r < 5; ++r) k1_ring_store<K1_URING, K1_UPAD>(s.u, nu0 + r, acc[r]);
             }
-            if (U8 && i + 1 < n_load) k1_convert_tile_u8<CVB, GB>(s, rawfull, i + 1, 0, lb);   // its share of the tile stage A filters next
             if (ROT && i + 1 < n_load) {
                 // for the tile stage A filters next iteration: the NCO phasors of its w samples and, when it opens
                 // a new slot, that carrier's taps (the buffer's previous owner left stage C a whole slot ago)
@@ -821,7 +861,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             }
             r_it += K1_W;
             if (r_it >= S) { r_it -= S; ++q_it; }
-            if (U8 && i + 1 < n_load) k1_convert_tile_u8<CVD, GD>(s, rawfull, i + 1, 64 * CVB, ld);   // the rest of that tile
             k1_bar_sync();
         }
         if (q_cur >= 0 && q_cur < n_my) flush(n_iter);
