@@ -324,3 +324,27 @@ def test_survey_wideband_matches_reference_per_channel(gpu_processor):
     want_found = [k for k in range(len(freqs)) if want[k][col["is_tetra"]] and want[k][col["power_db"]] > -70
                   and want[k][col["confidence"]] > 0.4 and want[k][col["sync_detected"]] and want[k][col["power_stable"]]]
     assert [d["frequency"] for d in found] == [392.5e6 + freqs[k] for k in want_found]
+
+
+def test_survey_wideband_short_capture_and_off_grid_channels(gpu_processor):
+    """Fewer samples than the FFT block: the presence / AFC numbers stay zero (ui/modern.py:1922 only runs them on a full block)
+    while the detector numbers follow the reference's own early returns; channel offsets need not sit on the 25 kHz grid."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    x = synth.carrier_iq(1500, 77, snr_db=20.0)
+    freqs = np.array([0.0, 1234.5, -333333.3])
+    results, found = sp.survey_wideband(x, freqs)
+    x128 = x.astype(np.complex128)
+    for f, r in zip(freqs, results):
+        xs = ref_dsp.nco(x128, f, 2.4e6)
+        assert abs(r["power_db"] - 10 * np.log10(np.mean(np.abs(xs) ** 2) + 1e-10)) < 1e-6
+        assert r["signal_power"] == 0.0 and r["peak_freq_offset"] == 0.0 and not r["is_signal_strong"]
+        assert not r["power_stable"]                                 # fewer than 5 x 1000 samples (scanner.py:215-216)
+    assert found == []
+    # a full block at an off-grid offset: the presence block equals the oracle's on the shifted capture
+    x = synth.carrier_iq(8192, 78, snr_db=25.0)
+    results, _ = sp.survey_wideband(x, [777.7])
+    want = ref_dsp.presence_afc(ref_dsp.nco(x.astype(np.complex128), 777.7, 2.4e6), 2.4e6)
+    for k in ("signal_power", "peak_power", "noise_floor", "snr"):
+        assert abs(results[0][k] - want[k]) < 1e-8, k
+    assert abs(results[0]["peak_freq_offset"] - want["peak_freq_offset"]) < 1e-6 and results[0]["is_signal_strong"] == want["is_signal_strong"]

@@ -183,3 +183,32 @@ def test_peer_memory_allgather_between_contexts_of_one_gpu(world, n_local, cap):
     finally:
         for sp in sps:
             sp.close()
+
+
+def test_peer_memory_allgather_argument_checks():
+    """Misuse is an error code with a message, not a launch: no exchange yet, a block too small for the streams, bad sizes."""
+    import torch
+    from tetraear_b200 import _lib
+    from tetraear_b200.processor import SignalProcessor
+    sp = SignalProcessor(2.4e6)
+    try:
+        d = torch.zeros(4 * 64, dtype=torch.uint8, device="cuda")
+        nd = torch.zeros(4, dtype=torch.int32, device="cuda")
+        out = torch.zeros(4 * 64, dtype=torch.uint8, device="cuda")
+        with pytest.raises(_lib.TetraError, match="tetra_p2p_create"):
+            sp.allgather_dibits_device(d.data_ptr(), 256, nd.data_ptr(), 4, out.data_ptr())
+        with pytest.raises(_lib.TetraError):
+            sp.p2p_create(0, 9, 64)                               # world > 8
+        with pytest.raises(_lib.TetraError):
+            sp.p2p_create(0, 1, 60)                               # block not a multiple of 16
+        sp.p2p_create(0, 1, 64)                                   # room for 64 bytes per rank: 256 dibits need 64 + 16
+        with pytest.raises(_lib.TetraError, match="exceed the block"):
+            sp.allgather_dibits_device(d.data_ptr(), 256, nd.data_ptr(), 4, out.data_ptr())
+        sp.p2p_create(0, 1, 80)
+        with pytest.raises(_lib.TetraError):
+            sp.allgather_dibits_device(d.data_ptr(), 250, nd.data_ptr(), 4, out.data_ptr())     # n not a multiple of 16
+        sp.allgather_dibits_device(d.data_ptr(), 256, nd.data_ptr(), 4, out.data_ptr())
+        sp.synchronize()
+        assert sp.p2p_status() == 0
+    finally:
+        sp.close()

@@ -180,3 +180,20 @@ def test_sync_replay_and_c_oracle_agree_on_random_streams():
             th = float(rng.choice([0.9, 0.85, 0.8, 0.77]))
             assert sync.find_sync(mc, n_bits // 2, th, True) == ref_dsp.find_sync(bits, th), (trial, th)
             assert c_oracle.find_sync(bits.astype(np.uint8), th) == ref_dsp.find_sync(bits, th), (trial, th)
+
+
+def test_entry_points_reject_a_null_context_without_a_device():
+    """The C ABI never dereferences a NULL context: every compute entry point returns TETRA_E_INVALID (no GPU needed)."""
+    import ctypes as C
+    lib = _lib.load()
+    buf = (C.c_uint8 * 64)()
+    st = C.c_int32(0)
+    rows = C.c_int64(0)
+    assert lib.tetra_p2p_create(None, 0, 1, 64, C.addressof(buf)) < 0
+    assert lib.tetra_p2p_connect(None, C.addressof(buf)) < 0
+    assert lib.tetra_allgather_dibits(None, None, 16, None, 1, None, None) < 0
+    assert lib.tetra_p2p_status(None, C.byref(st)) < 0
+    assert lib.tetra_p2p_destroy(None) < 0
+    assert lib.tetra_survey_wideband(None, None, 0, None, 0, 2048, None) < 0
+    assert lib.tetra_stft_db_f64(None, None, 0, 2048, 2048, None, C.byref(rows)) < 0
+    assert lib.tetra_p2p_buffer(None) is None

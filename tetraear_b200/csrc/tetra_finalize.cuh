@@ -13,7 +13,7 @@ namespace tetra {
 // ----------------------------------------------------------------------------------------------
 constexpr int FIN_THREADS = 256;
 constexpr int FIN_MAXPH = 32;
-constexpr int FIN_B = 8;                  // symbols per thread and batch in k_finalize
+constexpr int FIN_B = 4;                  // symbols per thread and batch in k_finalize
 
 struct FinArgs {
     const float2* y;         // [C][y_pitch] filtered samples at the decimated rate, layout y_index(n, sps, y_rows)
@@ -297,17 +297,41 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     // symbol k is sample best + stride k: in the phase-major layout that is row `best`, contiguous in k
     const float2* ys = a.y_rows > 0 ? y + (int64_t)best * a.y_rows : y + best;
     const int64_t ks = a.y_rows > 0 ? 1 : stride;
-    for (int k0 = tid; k0 < n_sym; k0 += FIN_B * FIN_THREADS) {
+    // The block-end corrections touch the first and last few symbols only (sample n = best + stride k with n < K_EDGE or
+    // n >= L - K_EDGE): those symbols are prepared in shared memory first, so that the main loop's loads are unconditional
+    // and a batch's loads all issue before the first use.
+    const int k_head = ec ? min(n_sym, (K_EDGE - 1 - best) / stride + 1) : 0;            // symbols k < k_head need D_left
+    const int k_tail = ec ? max(k_head, (L - K_EDGE - best + stride - 1) / stride) : n_sym;   // symbols k >= k_tail need D_right
+    float2* s_fix = reinterpret_cast<float2*>(sm.s_sync.mask);                              // free until the sync front end
+    const int n_fix_tail = n_sym - min(k_tail, n_sym);
+    if (ec) {
+        for (int i = tid; i < k_head + n_fix_tail; i += FIN_THREADS) {
+            const int k = i < k_head ? i : k_tail + (i - k_head);
+            s_fix[i] = y_at(best + stride * k, __ldcg(ys + ks * k));
+        }
+        __syncthreads();
+    }
+    auto sym_at = [&](int k) {
+        float2 v = __ldcg(ys + ks * k);
+        if (k < k_head) v = s_fix[k];
+        else if (k >= k_tail) v = s_fix[k_head + (k - k_tail)];
+        return v;
+    };
+    // every warp runs the same number of batches (the previous symbol comes from the neighbouring lane by shuffle; only lane 0
+    // loads its own)
+    for (int base = 0; base < n_sym; base += FIN_B * FIN_THREADS) {
         float2 s1[FIN_B], s0[FIN_B];
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
-            const int k = min(k0 + j * FIN_THREADS, n_sym - 1), kp = max(k - 1, 0);
-            s1[j] = y_at(best + stride * k, __ldcg(ys + ks * k));
-            s0[j] = y_at(best + stride * kp, __ldcg(ys + ks * kp));
+            const int k = min(base + tid + j * FIN_THREADS, n_sym - 1);
+            s1[j] = sym_at(k);
+            if ((tid & 31) == 0) s0[j] = sym_at(max(k - 1, 0));
         }
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
-            const int k = k0 + j * FIN_THREADS;
+            const float px = __shfl_up_sync(0xffffffffu, s1[j].x, 1), py = __shfl_up_sync(0xffffffffu, s1[j].y, 1);
+            if ((tid & 31) != 0) s0[j] = make_float2(px, py);
+            const int k = base + tid + j * FIN_THREADS;
             if (k < n_sym) {
                 if (sym) sym[k] = s1[j];
                 if (k >= 1) {
@@ -350,7 +374,7 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS) k_finalize(const FinArgs a) {
+__global__ void __launch_bounds__(FIN_THREADS, 5) k_finalize(const FinArgs a) {
     __shared__ FinSmem sm;
     finalize_carrier(a, a.car0 + blockIdx.x, sm);
 }
