@@ -217,3 +217,22 @@ def test_full_size_properties(gpu_processor):
     d = res["dibits"][0, :nd]
     best = max(np.mean(d[200:6000] == inc[200 + lag: 6000 + lag]) for lag in range(0, 20))
     assert best == 1.0
+
+
+@pytest.mark.parametrize("fs,sps,fo", [(2.048e6, 112, -1500.0), (1.8e6, 98, 0.0), (2.88e6, 156, 3000.0)])
+def test_other_sample_rates_full_blocks(gpu_processor, fs, sps, fo):
+    """The RTL-SDR rates the fused kernel does not cover (signal/capture.py:83-87; q = 8, 7, 12) at the full block size:
+    the chunk-parallel exact kernel (k_exact_block, one CTA per carrier) against the oracle, three carriers per call."""
+    sp = gpu_processor
+    sp.sample_rate = fs
+    n = 1 << 20
+    x = np.stack([synth.carrier_iq(n, 700 + c, snr_db=28.0, alphabet="centred" if c & 1 else "pi4", sps=sps) for c in range(3)])
+    res = sp.process_batch(x, [fo, 0.0, -fo], want_symbols=True, want_match=True)
+    for c, f in enumerate((fo, 0.0, -fo)):
+        r = ref_dsp.process(x[c].astype(np.complex128), f, fs)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], c
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), c
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (c, err)
+    sp.sample_rate = 2.4e6

@@ -288,8 +288,73 @@ void exact_extents(int mode, int64_t n, int64_t L, int q, int E, bool has_s1, in
     *w1 = e_hi - e_lo;
 }
 
+// ---- zero-input chunk transitions (shared by k_exact_edges_warp and k_exact_block, see tetra_exact.cuh) ----
+void sos_transition_powers(const ExactCoef& cf, int steps, double* out);
+void ba_transition_powers(const ExactCoef& cf, int steps, double* out);
+template <int DIM>
+double mat_norm_inf(const double* m) {
+    double best = 0.0;
+    for (int i = 0; i < DIM; ++i) {
+        double r = 0.0;
+        for (int j = 0; j < DIM; ++j) r += std::fabs(m[i * DIM + j]);
+        best = std::max(best, r);
+    }
+    return best;
+}
+
+// whole blocks, one CTA per carrier, chunk-parallel passes (k_exact_block)
+int launch_exact_block(tetra_ctx* ctx, cudaStream_t st, ExactArgs a, const std::vector<int2>& jobs) {
+    const int64_t w1 = a.has_s1 ? a.n + 2 * EX_PAD1 : 1, wz = a.L, w2 = (int64_t)a.L + 2 * EX_PAD2;
+    ExactBlockArgs b;
+    memset(&b, 0, sizeof b);
+    b.s1_stride = w1; b.sz_stride = wz; b.s2_stride = w2;
+    // chunk lengths: as short as the thread count allows, as long as the transition over one chunk needs to die out
+    auto pick = [&](int64_t T, bool sos, double* m_out) {
+        int64_t lc = std::max<int64_t>(1, (T + EXB_THREADS - 1) / EXB_THREADS);
+        double pw[5 * 64];
+        for (;;) {
+            if (sos) sos_transition_powers(a.cf, (int)lc, pw); else ba_transition_powers(a.cf, (int)lc, pw);
+            const double nrm = sos ? mat_norm_inf<8>(pw) : mat_norm_inf<4>(pw);
+            if (nrm <= 3e-3 || lc >= T) break;                // EXB_T = 8 terms: what is dropped is below 1e-20
+            lc = std::min<int64_t>(T, lc * 2);
+        }
+        memcpy(m_out, pw, sizeof(double) * (sos ? 64 : 16));
+        return (int32_t)lc;
+    };
+    b.lc1 = a.has_s1 ? pick(w1, true, b.m1) : 1;
+    b.lc2 = a.has_s2 ? pick(w2, false, b.m2) : 1;
+    const size_t per_job = (size_t)(w1 + wz + w2) * sizeof(double2);
+    size_t chunk = std::max<size_t>(1, ctx->max_scratch_bytes / per_job);
+    chunk = std::min(chunk, jobs.size());
+    CK(ctx->scr1.ensure((size_t)w1 * chunk * sizeof(double2)));
+    CK(ctx->scrz.ensure((size_t)wz * chunk * sizeof(double2)));
+    CK(ctx->scr2.ensure((size_t)w2 * chunk * sizeof(double2)));
+    CK(ctx->jobs.ensure(jobs.size() * sizeof(int2)));
+    CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), jobs.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+    CK(cudaFuncSetAttribute(k_exact_block, cudaFuncAttributeMaxDynamicSharedMemorySize, EXB_SMEM));
+    a.scr1 = (double2*)ctx->scr1.p; a.scrz = (double2*)ctx->scrz.p; a.scr2 = (double2*)ctx->scr2.p;
+    for (size_t off = 0; off < jobs.size(); off += chunk) {
+        const int nj = (int)std::min(chunk, jobs.size() - off);
+        a.jobs = (const int2*)ctx->jobs.p + off;
+        a.n_jobs = nj;
+        b.e = a;
+        k_exact_block<<<nj, EXB_THREADS, EXB_SMEM, st>>>(b);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+constexpr int64_t EXB_MIN_N = 4096;        // shorter blocks: one thread per carrier is as fast as a CTA
+
 int launch_exact(tetra_ctx* ctx, cudaStream_t st, ExactArgs a, const std::vector<int2>& jobs, int mode_hint) {
     if (jobs.empty()) return 0;
+    {
+        static const int blk_env = getenv("TETRA_EXACT_BLOCK") ? atoi(getenv("TETRA_EXACT_BLOCK")) : 1;   // 0: the serial kernel (A/B)
+        bool all_full = true;
+        for (auto& j : jobs) if (j.y != EX_FULL) { all_full = false; break; }
+        if (blk_env && all_full && a.n >= EXB_MIN_N) return launch_exact_block(ctx, st, a, jobs);
+    }
     // extents: all jobs of one launch share the worst-case window
     int64_t w1 = 1, wz = 1;
     for (int m = 0; m < 3; ++m) {

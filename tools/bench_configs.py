@@ -87,6 +87,16 @@ def run(only=None, device=0):
                 "block_duration_ms": ns / 2.4e3,
             }
         out["config2_host_calls"] = calls
+        # the other RTL-SDR rates (signal/capture.py:83-87) take the exact-recursion kernel (KX), one thread per carrier
+        other = {}
+        for rate in (2.048e6, 1.8e6):
+            sp.sample_rate = rate
+            for label, ns in (("2^20", n), ("gui_chunk_131072", 128 * 1024)):
+                hx = synth.carrier_iq(ns, 0, snr_db=30.0)
+                other["%.3f MS/s %s" % (rate / 1e6, label)] = {"process_complex64_ms": host_call_ms(lambda: sp.process(hx), reps=3),
+                                                               "block_duration_ms": ns / rate * 1e3}
+        sp.sample_rate = 2.4e6
+        out["config2_other_rates_exact_path"] = other
         out["config2_process_host_call_ms"] = calls["2^20"]["process_complex64_ms"]
 
     if want("3"):
