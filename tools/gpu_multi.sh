@@ -1,5 +1,5 @@
 #!/bin/bash
-# N-GPU visit: bench.py under torchrun with the peer-memory exchange and with NCCL
+# N-GPU visit (gpurun --gpus N -- bash tools/gpu_multi.sh N tag): bench.py under torchrun with the peer-memory exchange and with NCCL
 set -u
 N=${1:-2}; TAG=${2:-r02_n$N}
 OUT=gpurun_out/$TAG
