@@ -444,7 +444,7 @@ def run_ours(a):
                 mod = importlib.util.module_from_spec(spec)
                 spec.loader.exec_module(mod)
                 oc = mod.run(only=["2", "3", "5"], device=local)
-                out["other_configs"] = {k: oc[k] for k in ("config2_one_carrier_fo0", "config2_host_calls", "config3_wideband_96ch_device_resident",
+                out["other_configs"] = {k: oc[k] for k in ("config2_one_carrier_fo0", "config2_host_calls", "config2_other_rates_exact_path", "config3_wideband_96ch_device_resident",
                                                            "config5_stft_4096_hop1024", "config5_stft_4096_hop1024_30s") if k in oc}
             except Exception as e:                            # never lose the bench line over the extras
                 out["other_configs"] = {"error": repr(e)}

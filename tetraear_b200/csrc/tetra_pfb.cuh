@@ -37,7 +37,14 @@ __device__ __forceinline__ float2 pfb_cmul(float2 a, float2 b) { return make_flo
 __global__ void __launch_bounds__(PFB_THREADS) k_pfb96(const PfbArgs a) {
     __shared__ float2 xs[10 * PFB_MB + 48];
     __shared__ float2 outs[PFB_NCH][PFB_MB + 1];
+    __shared__ float s_proto[2 * TB_PROTO_H + 1];            // lanes index the taps by different d: shared, not constant, memory
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid <= 2 * TB_PROTO_H) s_proto[tid] = c_proto[tid];
+    // the twiddles a lane uses never change: read the (lane-indexed, hence serialised) constant bank once, not per instant
+    const float2 w_l1 = c_w96[lane], w_l2 = c_w96[2 * lane];
+    float2 w_st[5];
+#pragma unroll
+    for (int st = 0; st < 5; ++st) w_st[st] = c_w96[3 * ((lane & ((16 >> st) - 1)) << st)];   // W32^{(lane mod half) 2^s}
     const int col0 = blockIdx.x * PFB_MB;                    // first column of this CTA; m = col - PFB_M0
     const int64_t i0 = 10 * ((int64_t)col0 - PFB_M0) - TB_PROTO_H;   // input index of xs[0]
     for (int t = tid; t < 10 * PFB_MB + 41; t += PFB_THREADS) {
@@ -62,7 +69,7 @@ __global__ void __launch_bounds__(PFB_THREADS) k_pfb96(const PfbArgs a) {
             u[g] = make_float2(0.f, 0.f);
             if (d <= 2 * TB_PROTO_H) {
                 const float2 v = xs[10 * ml + d];
-                const float p = c_proto[d];
+                const float p = s_proto[d];
                 u[g] = make_float2(p * v.x, p * v.y);
             }
         }
@@ -72,14 +79,14 @@ __global__ void __launch_bounds__(PFB_THREADS) k_pfb96(const PfbArgs a) {
         {
             const float2 a1 = pfb_cmul(u[1], w3_1), a2 = pfb_cmul(u[2], w3_2);
             const float2 b1 = pfb_cmul(u[1], w3_2), b2 = pfb_cmul(u[2], w3_1);      // W3^2 and W3^4 = W3
-            t[1] = pfb_cmul(make_float2(u[0].x + a1.x + a2.x, u[0].y + a1.y + a2.y), c_w96[lane]);
-            t[2] = pfb_cmul(make_float2(u[0].x + b1.x + b2.x, u[0].y + b1.y + b2.y), c_w96[2 * lane]);
+            t[1] = pfb_cmul(make_float2(u[0].x + a1.x + a2.x, u[0].y + a1.y + a2.y), w_l1);
+            t[2] = pfb_cmul(make_float2(u[0].x + b1.x + b2.x, u[0].y + b1.y + b2.y), w_l2);
         }
         // three 32-point FFTs across the lanes: decimation in frequency, results in bit-reversed lane order
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
             const int half = 16 >> s;
-            const float2 tw = c_w96[3 * ((lane & (half - 1)) << s)];          // W32^{(lane mod half) 2^s}
+            const float2 tw = w_st[s];                                        // W32^{(lane mod half) 2^s}
             const bool upper = (lane & half) != 0;
 #pragma unroll
             for (int f = 0; f < 3; ++f) {
