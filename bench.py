@@ -244,7 +244,7 @@ def run_ours(a):
 
     x, base_d = make_inputs(torch, dev, n_local, first_carrier)
     # the exchange: the library's own two kernels over NVLink peer memory (default), or pack -> ncclAllGather -> unpack
-    transport = a.gather
+    transport = "nccl" if a.gather == "nccl" else "p2p"
     packed = None
     if total % world == 0:
         try:
@@ -275,7 +275,14 @@ def run_ours(a):
     if a.fo_max > 0:          # not the BASELINE workload: per-carrier AFC-style offsets exercise the freq_offset != 0 kernel
         fos = np.random.default_rng(6).uniform(-a.fo_max, a.fo_max, size=total)[first_carrier:first_carrier + n_local]
 
+    fused = world > 1 and packed is not None and transport == "p2p" and a.gather == "p2p-fused"
+
     def step():
+        if fused:                                                     # slicer + push in one kernel, then wait + unpack
+            sp.process_batch_allgather_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
+                                              sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), packed.out.data_ptr(),
+                                              packed.out_n.data_ptr(), stream=work.cuda_stream, freq_offsets=fos)
+            return
         sp.process_batch_device(x.data_ptr(), n_local, N_SAMPLES, N_SAMPLES, dib.data_ptr(), cap, nd.data_ptr(),
                                 sym.data_ptr(), ph.data_ptr(), mt.data_ptr(), stream=work.cuda_stream, freq_offsets=fos)
         if world > 1:
@@ -354,7 +361,7 @@ def run_ours(a):
             ok &= n_i == len(ref["dibits"]) and bool(np.array_equal(g_dib[r, i_r, :n_i].cpu().numpy(), ref["dibits"]))
             checked.append(f_r + i_r)
         gather_parity = {"ok": bool(ok), "carriers_checked": checked,
-                         "transport": transport, "p2p_status": sp.p2p_status() if transport == "p2p" else None,
+                         "transport": a.gather if transport == "p2p" else transport, "p2p_status": sp.p2p_status() if transport == "p2p" else None,
                          "what": "dibits of one carrier per remote rank, read from rank 0's all-gather output, vs the oracle"}
 
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region ----
@@ -474,8 +481,9 @@ def main():
     ap.add_argument("--e2e-carriers", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs appended to the N = 1 line")
-    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: exchange of the dibit streams -- the library's peer-memory kernels (default) or NCCL all-gather")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "p2p-fused", "nccl"],
+                    help="N > 1: exchange of the dibit streams over NVLink peer memory -- a pack + push kernel behind finalize (p2p, default: "
+                         "the fastest measured), the push inside the finalize kernel (p2p-fused) -- or pack -> NCCL all-gather -> unpack (nccl)")
     ap.add_argument("--fo-max", type=float, default=0.0, help="per-carrier freq_offset drawn from +-this (Hz); 0 = BASELINE workload")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the fused kernel from an ncu --set full capture (profiles/), if known")

@@ -124,6 +124,16 @@ int tetra_p2p_connect(tetra_ctx* ctx, const uint8_t* handles);
 int tetra_p2p_connect_ptrs(tetra_ctx* ctx, void* const* buffers);
 int tetra_allgather_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, const int32_t* n_dibits, int32_t n_local,
                            uint8_t* all_dibits, int32_t* all_n);
+/*
+ * tetra_process_batch (asynchronous, device buffers, cap % 16 == 0) with the exchange fused behind the slicer: the CTA that
+ * has sliced a carrier packs its dibits and stores them, with the stream length, straight into every peer's receive buffer;
+ * the last CTA of the batch raises the step's flag; then the peers' blocks are awaited and unpacked as above. One compute
+ * kernel does slicing and push -- no separate pack / all-gather pass over the streams.
+ */
+int tetra_process_batch_allgather(tetra_ctx* ctx, const float* iq, int32_t n_carriers, int64_t n_samples, int64_t pitch,
+                                  const double* freq_offset_hz, uint8_t* dibits, int64_t cap, int32_t* n_dibits,
+                                  float* symbols, int32_t* best_phase, uint8_t* ts_match,
+                                  uint8_t* all_dibits, int32_t* all_n);
 int tetra_p2p_status(tetra_ctx* ctx, int32_t* status);
 int tetra_p2p_destroy(tetra_ctx* ctx);
 

@@ -212,3 +212,54 @@ def test_peer_memory_allgather_argument_checks():
         assert sp.p2p_status() == 0
     finally:
         sp.close()
+
+
+def test_process_batch_allgather_fused_push(gpu_processor):
+    """tetra_process_batch_allgather between two contexts ("ranks") of one GPU: the finalize kernel pushes every carrier's
+    packed stream into both receive buffers; each rank ends with both ranks' dibit streams and lengths, equal to what the
+    plain call produces, over several steps."""
+    import torch
+    from tetraear_b200 import synth
+    from tetraear_b200.processor import SignalProcessor
+    n, n_car, world = 20000, 3, 2
+    sps_ = [SignalProcessor(2.4e6) for _ in range(world)]
+    try:
+        cap = (sps_[0].dibit_capacity(n) + 15) & ~15
+        block = (n_car * cap // 4 + 4 * n_car + 15) & ~15
+        for r, sp in enumerate(sps_):
+            sp.p2p_create(r, world, block)
+        bufs = [sp.p2p_buffer() for sp in sps_]
+        for sp in sps_:
+            sp.p2p_connect_ptrs(bufs)
+        for step in range(3):
+            xs, want_d, want_n = [], [], []
+            for r in range(world):
+                x = np.stack([synth.carrier_iq(n, 900 + 10 * step + 3 * r + c, snr_db=25.0, alphabet="centred" if c & 1 else "pi4")
+                              for c in range(n_car)])
+                ref = gpu_processor.process_batch(x, None, want_symbols=False)
+                xs.append(torch.view_as_real(torch.from_numpy(x).cuda()).contiguous())
+                want_d.append(ref["dibits"]); want_n.append(ref["n_dibits"])
+            outs, out_ns, keep = [], [], []
+            for r in range(world):
+                keep.append((torch.zeros((n_car, cap), dtype=torch.uint8, device="cuda"), torch.zeros(n_car, dtype=torch.int32, device="cuda"),
+                             torch.zeros((n_car, 2 * cap, 2), dtype=torch.uint8, device="cuda")))
+                outs.append(torch.zeros((world, n_car, cap), dtype=torch.uint8, device="cuda"))
+                out_ns.append(torch.zeros((world, n_car), dtype=torch.int32, device="cuda"))
+            torch.cuda.synchronize()
+            # both ranks are enqueued back to back (no host synchronisation in between: a rank's wait needs the other's push)
+            for r, sp in enumerate(sps_):
+                dib, nd, mt = keep[r]
+                sp.process_batch_allgather_device(xs[r].data_ptr(), n_car, n, n, dib.data_ptr(), cap, nd.data_ptr(), 0, 0, mt.data_ptr(),
+                                                  outs[r].data_ptr(), out_ns[r].data_ptr())
+            for r, sp in enumerate(sps_):
+                sp.synchronize()
+                assert sp.p2p_status() == 0
+                for src in range(world):
+                    assert np.array_equal(out_ns[r][src].cpu().numpy(), want_n[src]), (step, r, src)
+                    for c in range(n_car):
+                        k = int(want_n[src][c])
+                        got = outs[r][src, c].cpu().numpy()
+                        assert np.array_equal(got[:k], want_d[src][c, :k]) and not got[k:].any(), (step, r, src, c)
+    finally:
+        for sp in sps_:
+            sp.close()

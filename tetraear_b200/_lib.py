@@ -43,6 +43,9 @@ _SIGS = {
     "tetra_p2p_connect": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tetra_p2p_connect_ptrs": (C.c_int, [c_ctx_p, C.c_void_p]),
     "tetra_allgather_dibits": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
+    "tetra_process_batch_allgather": (C.c_int, [c_ctx_p, C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_void_p,
+                                                C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "tetra_p2p_status": (C.c_int, [c_ctx_p, C.POINTER(C.c_int32)]),
     "tetra_p2p_destroy": (C.c_int, [c_ctx_p]),
     "tetra_launch_count": (C.c_int64, [c_ctx_p]),

@@ -106,6 +106,7 @@ struct tetra_ctx {
     int64_t p2p_block = 0, p2p_flag_off = 0;
     uint32_t p2p_step = 0;
     bool p2p_connected = false;
+    bool fg_active = false;            // tetra_process_batch_allgather: the finalize kernel pushes the streams to the peers
 };
 
 namespace {
@@ -847,6 +848,14 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     fa.y = (const float2*)ctx->y.p; fa.y_pitch = y_pitch; fa.y_rows = y_rows; fa.L = (int32_t)pl.L; fa.sps = pl.sps; fa.step = pl.step;
     fa.dibits = k_dib; fa.cap = cap; fa.n_dibits = k_nd; fa.symbols = k_sym; fa.best_phase = k_ph;
     fa.phase_scratch = (int32_t*)ctx->phase.p;
+    if (ctx->fg_active) {
+        for (int r = 0; r < ctx->p2p_world; ++r) fa.push.recv[r] = ctx->p2p_peer[r];
+        fa.push.world = ctx->p2p_world; fa.push.rank = ctx->p2p_rank; fa.push.n_local = C;
+        fa.push.step = ctx->p2p_step;
+        fa.push.slot_off = ((int64_t)(ctx->p2p_step & 1) * ctx->p2p_world + ctx->p2p_rank) * ctx->p2p_block;
+        fa.push.flag_off = ctx->p2p_flag_off;
+        fa.push.ticket = (uint32_t*)ctx->p2p_misc.p;
+    }
 
     const bool fused_match = ts_match && cap > 0 && cap <= FIN_DIB_SMEM;
     fa.match = fused_match ? k_match : nullptr;
@@ -1676,6 +1685,41 @@ int tetra_allgather_dibits(tetra_ctx* ctx, const uint8_t* dibits, int64_t n, con
     const unsigned g_un = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 16 + KG_THREADS - 1) / KG_THREADS, (148 * 4 + ga.world - 1) / ga.world));
     k_gather_wait_unpack<<<dim3(g_un, (unsigned)ga.world), KG_THREADS, 0, ctx->stream>>>(ga);
     ctx->launches += 2;
+    CK(cudaGetLastError());
+    return TETRA_OK;
+}
+
+int tetra_process_batch_allgather(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                                  uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                                  uint8_t* ts_match, uint8_t* all_dibits, int32_t* all_n) {
+    if (!ctx) return TETRA_E_INVALID;
+    if (!ctx->p2p_connected) return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_allgather: tetra_p2p_create / tetra_p2p_connect first");
+    if (C <= 0 || cap <= 0 || (cap & 15) || !dibits || !n_dibits || !all_dibits ||
+        (reinterpret_cast<uintptr_t>(dibits) & 15) || (reinterpret_cast<uintptr_t>(all_dibits) & 15))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_allgather: cap a multiple of 16, 16-byte aligned device buffers");
+    const int64_t n = (int64_t)C * cap;
+    if (n / 4 + 4 * (int64_t)C > ctx->p2p_block)
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_allgather: %lld bytes per rank exceed the block of %lld the exchange was created with",
+                    (long long)(n / 4 + 4 * (int64_t)C), (long long)ctx->p2p_block);
+    if (!is_device_ptr(dibits) || !is_device_ptr(n_dibits) || !is_device_ptr(all_dibits) || (all_n && !is_device_ptr(all_n)))
+        return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_allgather: device buffers only");
+    // the finalize kernel pushes (fa.push); then every source rank's block is awaited and unpacked
+    ++ctx->p2p_step;
+    ctx->fg_active = true;
+    const int rc = tetra_process_batch(ctx, iq, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, 1);
+    ctx->fg_active = false;
+    if (rc != TETRA_OK) { --ctx->p2p_step; return rc; }
+    GatherArgs ga;
+    memset(&ga, 0, sizeof ga);
+    for (int r = 0; r < ctx->p2p_world; ++r) ga.recv[r] = ctx->p2p_peer[r];
+    ga.rank = ctx->p2p_rank; ga.world = ctx->p2p_world; ga.block = ctx->p2p_block; ga.flag_off = ctx->p2p_flag_off;
+    ga.step = ctx->p2p_step;
+    ga.n = n; ga.n_local = C;
+    ga.status = (int32_t*)ctx->p2p_misc.p + 4;
+    ga.out = all_dibits; ga.out_n = all_n;
+    const unsigned g_un = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n / 16 + KG_THREADS - 1) / KG_THREADS, (148 * 4 + ga.world - 1) / ga.world));
+    k_gather_wait_unpack<<<dim3(g_un, (unsigned)ga.world), KG_THREADS, 0, ctx->stream>>>(ga);
+    ctx->launches++;
     CK(cudaGetLastError());
     return TETRA_OK;
 }

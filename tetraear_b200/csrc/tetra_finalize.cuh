@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "tetra_exact.cuh"
+#include "tetra_gather.cuh"
 
 namespace tetra {
 
@@ -37,6 +38,17 @@ struct FinArgs {
     int32_t max_pos;
     int32_t* n_sync;         // [C]
     int32_t car0;            // first carrier of this launch (block b works on carrier car0 + b)
+    // the exchange fused behind the slicer (tetra_process_batch_allgather): every CTA packs its carrier's dibits four to a byte
+    // and stores them, with the stream length, into slot `rank` of every peer's receive buffer; the last CTA of the batch
+    // publishes the step (see tetra_gather.cuh). push.world == 0: off.
+    struct Push {
+        uint8_t* recv[KG_MAX_WORLD];
+        int32_t world, rank, n_local;
+        int64_t slot_off;    // byte offset of this rank's slot of this step's half of the receive buffers
+        int64_t flag_off;
+        uint32_t step;
+        uint32_t* ticket;    // local: carriers of this batch whose push is complete
+    } push;
 };
 
 constexpr uint32_t TS1_BITS = 0x343A74u;   // 1101000011101001110100, first bit = MSB of 22 (decoder.py:196-197)
@@ -345,7 +357,7 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
             }
         }
     }
-    if (!fuse) return;
+    if (fuse) {
     // ---- fused frame-sync front end (decoder.py:140-169 bit expansion, :237-240 agreement counts, :171-295 + :845-856) ----
     __syncthreads();
     pack_dibits(s_dib, nd, s_bits);
@@ -371,6 +383,34 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     if (a.sync_pos) {
         const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
         if (tid == 0) a.n_sync[car] = n;
+    }
+    }   // fuse
+    // ---- the exchange, fused: this carrier's packed stream and its length go to every peer ----
+    if (a.push.world > 0) {
+        __syncthreads();                                    // this CTA's dibits are in global memory (its own stores)
+        const int words = (int)(a.cap / 16);               // cap is a multiple of 16 here
+        const int64_t row = a.push.slot_off + (int64_t)(car - 0) * (a.cap / 4);
+        for (int j = tid; j < words; j += FIN_THREADS) {
+            const uint4 v = *reinterpret_cast<const uint4*>(dib + 16 * j);
+            uint32_t w = kg_pack4(v.x) | (kg_pack4(v.y) << 8) | (kg_pack4(v.z) << 16) | (kg_pack4(v.w) << 24);
+            const int valid = nd - 16 * j;                  // dibits of this word that belong to the stream
+            if (valid < 16) w = valid <= 0 ? 0u : (w & ((1u << (2 * valid)) - 1u));
+            for (int p = 0; p < a.push.world; ++p) *reinterpret_cast<uint32_t*>(a.push.recv[p] + row + 4 * j) = w;
+        }
+        if (tid == 0) {
+            const int64_t off = a.push.slot_off + (int64_t)a.push.n_local * (a.cap / 4) + 4 * (int64_t)(car - 0);
+            for (int p = 0; p < a.push.world; ++p) *reinterpret_cast<int32_t*>(a.push.recv[p] + off) = nd;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            if (atomicAdd(a.push.ticket, 1u) == (uint32_t)a.push.n_local - 1u) {
+                __threadfence_system();
+                for (int p = 0; p < a.push.world; ++p)
+                    kg_st_release_sys(reinterpret_cast<uint32_t*>(a.push.recv[p] + a.push.flag_off) + (a.push.step & 1) * KG_MAX_WORLD + a.push.rank, a.push.step);
+                *a.push.ticket = 0u;
+            }
+        }
     }
 }
 

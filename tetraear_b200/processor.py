@@ -456,6 +456,21 @@ class SignalProcessor:
         self._check(self._lib.tetra_allgather_dibits(self._ctx, dibits_ptr, n, n_dibits_ptr, n_local, all_dibits_ptr,
                                                      all_n_ptr or None), "allgather_dibits")
 
+    def process_batch_allgather_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int, cap: int,
+                                       n_dibits_ptr: int, symbols_ptr: int, best_phase_ptr: int, ts_match_ptr: int,
+                                       all_dibits_ptr: int, all_n_ptr: int = 0, stream=None, freq_offsets=None):
+        """``process_batch_device`` with the exchange fused behind the slicer (``tetra_process_batch_allgather``): the
+        finalize kernel itself stores every carrier's packed stream into all peers' receive buffers."""
+        self._sync_rate()
+        self.set_stream(stream)
+        fo = None
+        if freq_offsets is not None:
+            fo = np.ascontiguousarray(freq_offsets, dtype=np.float64)
+        self._check(self._lib.tetra_process_batch_allgather(
+            self._ctx, iq_ptr, n_carriers, n_samples, pitch, fo.ctypes.data if fo is not None else None,
+            dibits_ptr, cap, n_dibits_ptr, symbols_ptr or None, best_phase_ptr or None, ts_match_ptr or None,
+            all_dibits_ptr, all_n_ptr or None), "process_batch_allgather")
+
     def p2p_status(self) -> int:
         st = C.c_int32(0)
         self._check(self._lib.tetra_p2p_status(self._ctx, C.byref(st)), "p2p_status")
