@@ -137,8 +137,8 @@ struct K1SmemFo {
     float2 ptap[2][48];     // MODE 2: this channel's modulated proto taps
 };
 
-// uint8 ingest (MODE 3): in[0] / in[1] hold the converted tile being filtered / being prepared, in[2] is the ring of raw
-// byte tiles (2 bytes per sample) the bulk copies fill three tiles ahead
+// uint8 ingest (MODE 3 / 4): the float tile buffers are not used; their space holds the ring of raw byte tiles (2 bytes per
+// sample, each slot behind an 80-byte header with the previous tile's tail) that the bulk copies fill three tiles ahead
 constexpr int K1_RAWBUF = 4;
 constexpr int K1_RAW_BYTES = 2 * K1_TILE;
 constexpr int K1_RAW_HDR = 2 * K1_HDR;                      // bytes of the previous tile kept in front of each raw slot
@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
             k1_tick();
             if (i < n_load) {
                 // producer: tile i+2 goes into the buffer tile i-1 just left (its tail is already copied)
-                if (U8) {                                      // raw bytes, three ahead: stage B converts tile i + 1 meanwhile
+                if (U8) {                                      // raw bytes, three tiles ahead into the 4-slot byte ring
                     if (warp == 0 && i + 3 < n_load) k1_issue_stream_tile_u8(s, rawfull, a, i + 3, sl2, t2, lane);
                 } else if (MODE == 5) {
                     if (warp == 0 && i + 2 < n_load) k1_issue_stream_tile_w(s, a, i + 2, sl2, t2, lane);

@@ -157,7 +157,7 @@ def run(only=None, device=0):
         sp._lib.tetra_set_stream(sp._ctx, None)
         out["u8_ingest_device_resident"] = {"carriers": cu, "ms_per_batch": ms, "MS_per_s": cu * n / ms / 1e3, "fused_kernel_ms": k1_ms[0] / max(k1_ms[1], 1),
                                             "GB_per_s_at_2.1B_per_sample": 2.1 * cu * n / (ms * 1e-3) / 1e9,
-                                            "note": "2 B/sample read + the outputs' 0.1 B/sample; the fused kernel converts its tiles in shared memory"}
+                                            "note": "2 B/sample read + the outputs' 0.1 B/sample; stage A of the fused kernel filters the bytes as they are"}
         del raw, dib8, sym8, mt8
 
     if want("5"):
