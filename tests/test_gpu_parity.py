@@ -236,3 +236,37 @@ def test_other_sample_rates_full_blocks(gpu_processor, fs, sps, fo):
         err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
         assert err <= SOFT_TOL, (c, err)
     sp.sample_rate = 2.4e6
+
+
+@pytest.mark.parametrize("kind", ["c64", "c64_fo", "u8", "u8_fo"])
+def test_large_batch_with_block_end_kernels_ahead(gpu_processor, kind):
+    """From 2048 carriers per call the block-end kernels run ahead of the fused kernel on the same stream (tetra_b200.cu:
+    edge_serial_mode) instead of beside it; 2100 short blocks of each input form, a dozen carriers against the oracle."""
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    n, n_car = 16384 + 1280, 2100
+    base = [synth.carrier_iq(n, 820 + k, snr_db=22.0 + k, alphabet="centred" if k & 1 else "pi4") for k in range(5)]
+    fos = None
+    if kind.endswith("_fo"):
+        fos = np.random.default_rng(21).uniform(-9000.0, 9000.0, size=n_car)
+        fos[::5] = 0.0
+    if kind.startswith("u8"):
+        b8 = []
+        for x in base:
+            z = x / np.abs(x).max() * 0.9
+            b8.append(np.stack([np.clip(np.round((z.real + 1.0) * 127.5), 0, 255), np.clip(np.round((z.imag + 1.0) * 127.5), 0, 255)],
+                               axis=-1).astype(np.uint8))
+        raw = np.stack([b8[c % 5] for c in range(n_car)])
+        res = sp.process_batch_u8(raw, fos, want_symbols=True)
+        ref_in = [(b[:, 0].astype(np.float64) / 127.5 - 1.0) + 1j * (b[:, 1].astype(np.float64) / 127.5 - 1.0) for b in b8]
+    else:
+        x = np.stack([base[c % 5] for c in range(n_car)])
+        res = sp.process_batch(x, fos, want_symbols=True)
+        ref_in = [b.astype(np.complex128) for b in base]
+    for c in (0, 1, 2, 3, 4, 147, 148, 1000, 2047, 2048, 2099):
+        r = ref_dsp.process(ref_in[c % 5], float(fos[c]) if fos is not None else 0.0, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(r["dibits"]) and int(res["best_phase"][c]) == r["best_phase"], (kind, c)
+        assert np.array_equal(res["dibits"][c, :nd], r["dibits"]), (kind, c)
+        err = np.abs(res["symbols"][c, : nd + 1] - r["symbols"]).max() / np.abs(r["symbols"]).max()
+        assert err <= SOFT_TOL, (kind, c, err)
