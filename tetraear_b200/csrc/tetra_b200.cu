@@ -95,8 +95,6 @@ struct tetra_ctx {
     DevBuf emat[10], emat_unit;        // states -> corrections matrices (freq_offset = 0), one per (n - 1) mod 10; unit states
     bool emat_built[10] = {false, false, false, false, false, false, false, false, false, false};
     EdgeTables etab_ptrs{};
-    std::vector<double> edge_mats;     // host copy of the chunk transitions (must outlive the async upload)
-    int64_t mats_n = -1; int mats_q = -1, mats_L = -1;   // geometry the device copy was computed for
     size_t max_scratch_bytes = (size_t)6 << 30;
     // peer-memory all-gather (tetra_gather.cuh)
     DevBuf p2p_buf, p2p_misc;          // receive buffer [2][world][block] + flags; ticket + status words
@@ -289,7 +287,7 @@ void exact_extents(int mode, int64_t n, int64_t L, int q, int E, bool has_s1, in
     *w1 = e_hi - e_lo;
 }
 
-// ---- zero-input chunk transitions (shared by k_exact_edges_warp and k_exact_block, see tetra_exact.cuh) ----
+// ---- zero-input chunk transitions for k_exact_block (see tetra_exact.cuh) ----
 void sos_transition_powers(const ExactCoef& cf, int steps, double* out);
 void ba_transition_powers(const ExactCoef& cf, int steps, double* out);
 template <int DIM>
@@ -413,7 +411,7 @@ int launch_edges(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std
 }
 
 
-// ---- zero-input chunk transitions for k_exact_edges_warp (see tetra_exact.cuh) ----
+// ---- zero-input chunk transitions over `steps` samples and their powers M^(2^r), r < 5 ----
 template <int DIM>
 void mat_mul(const double* a, const double* b, double* c) {
     for (int i = 0; i < DIM; ++i)
@@ -457,55 +455,6 @@ void ba_transition_powers(const ExactCoef& cf, int steps, double* out) {
     }
     memcpy(out, m, sizeof m);
     for (int r = 1; r < 5; ++r) mat_mul<4>(out + (r - 1) * 16, out + (r - 1) * 16, out + r * 16);
-}
-
-// small batches: one warp per edge job, chunk-parallel recursion (k_exact_edges_warp)
-int launch_edges_warp(tetra_ctx* ctx, cudaStream_t st, const ExactArgs& ea, const std::vector<int2>& jobs) {
-    if (jobs.empty()) return 0;
-    int64_t w1 = 1, wz = 1;
-    for (int m = EX_LEFT; m <= EX_RIGHT; ++m) {
-        int64_t a1, az; exact_extents(m, ea.n, ea.L, ea.q, ea.edge, true, &a1, &az);
-        w1 = std::max(w1, a1); wz = std::max(wz, az);
-    }
-    const size_t nj = jobs.size();
-    CK(ctx->scr1.ensure((size_t)w1 * nj * sizeof(double2)));
-    CK(ctx->scrz.ensure((size_t)wz * nj * sizeof(double2)));
-    CK(ctx->scr2.ensure((size_t)(wz + 2 * EX_PAD2) * nj * sizeof(double2)));
-    CK(ctx->jobs.ensure(nj * sizeof(int2)));
-    CK(cudaMemcpyAsync(ctx->jobs.p, jobs.data(), nj * sizeof(int2), cudaMemcpyHostToDevice, st));
-    // transitions for the four (mode, direction) variants of each stage (they depend on the block geometry only)
-    const bool mats_cached = ctx->mats_n == ea.n && ctx->mats_q == ea.q && ctx->mats_L == ea.L && ctx->mats.p &&
-                             ctx->edge_mats.size() == 4 * 5 * 64 + 4 * 5 * 16;
-    if (!mats_cached) ctx->edge_mats.assign(4 * 5 * 64 + 4 * 5 * 16, 0.0);
-    for (int m = EX_LEFT; m <= EX_RIGHT && !mats_cached; ++m) {
-        const EdgeRange rg = edge_range(m, ea.n, ea.L, ea.q, ea.edge);
-        const int var = m == EX_LEFT ? 0 : 2;
-        const int nf = (int)(rg.e_hi - rg.e_lo), nb = (int)(rg.e_hi - rg.e_stop);
-        const int n2 = (int)(rg.f_hi - rg.f_lo), nb2 = (int)(rg.f_hi - rg.f_stop);
-        if (n2 > 32 * EXW_S2MAX || nb2 > 32 * EXW_S2MAX) return fail(ctx, TETRA_E_UNSUPPORTED, "edge window too long for the warp kernel");
-        sos_transition_powers(ea.cf, exw_chunk_len(nf), ctx->edge_mats.data() + (var + 0) * 5 * 64);
-        sos_transition_powers(ea.cf, exw_chunk_len(nb), ctx->edge_mats.data() + (var + 1) * 5 * 64);
-        ba_transition_powers(ea.cf, (n2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 0) * 5 * 16);
-        ba_transition_powers(ea.cf, (nb2 + 31) / 32, ctx->edge_mats.data() + 4 * 5 * 64 + (var + 1) * 5 * 16);
-    }
-    if (!mats_cached) {
-        CK(ctx->mats.ensure(ctx->edge_mats.size() * sizeof(double)));
-        CK(cudaMemcpyAsync(ctx->mats.p, ctx->edge_mats.data(), ctx->edge_mats.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-        ctx->mats_n = ea.n; ctx->mats_q = ea.q; ctx->mats_L = ea.L;
-    }
-    EdgeWarpArgs g;
-    g.e.x = ea.x32; g.e.pitch = ea.pitch; g.e.right_shift = ea.x_right_shift; g.e.n = ea.n; g.e.q = ea.q; g.e.L = ea.L; g.e.edge = ea.edge; g.e.cf = ea.cf;
-    g.e.y = ea.y32; g.e.y_pitch = ea.y_pitch; g.e.y_sps = ea.y_sps; g.e.y_rows = ea.y_rows; g.e.jobs = (const int2*)ctx->jobs.p; g.e.n_jobs = (int32_t)nj;
-    g.e.scr1 = (double2*)ctx->scr1.p; g.e.scrz = (double2*)ctx->scrz.p; g.e.scr2 = (double2*)ctx->scr2.p;
-    g.e.w1 = w1; g.e.wz = wz; g.e.fo = ea.fo; g.e.fs_dec = ea.fs_dec;
-    g.m1 = (const double*)ctx->mats.p;
-    g.m2 = (const double*)ctx->mats.p + 4 * 5 * 64;
-    // one warp = one job = one block. (Its 248 registers do not fit the 6400 a fused-kernel CTA leaves free in an SM
-    // sub-partition: the blocks start as those CTAs retire. Capped to fit, it slowed the fused kernel by more than it hid.)
-    k_exact_edges_warp<<<(int)nj, 32, 0, st>>>(g);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
 }
 
 }  // namespace
@@ -813,7 +762,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     ea.has_s1 = pl.has_s1; ea.has_s2 = pl.has_s2;
     fill_coef(ea.cf, pl.has_s1 ? pl.q : 1, pl.wn);
     ea.fo = chan_hz ? nullptr : d_fo; ea.fs_dec = pl.rate;
-    // block ends of the fused path: corrections from the input alone (default), or -- TETRA_EDGE_MODE = 1 / 3 / 2 -- the
+    // block ends of the fused path: corrections from the input alone (default), or -- TETRA_EDGE_MODE = 1 / 2 -- the
     // literal recursions of round 1 over windows at each end (kept for A/B measurements)
     const bool edge_corr = edge_mode == 0;
     if (chan_hz && !edge_corr) {
@@ -996,15 +945,14 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
             if (t1) CK(cudaEventRecord(t1, st));
             if (g + 1 < n_grp) CK(cudaEventRecord(ctx->ev_grp[g], st));
             if (g == 0) {
-                // block ends on the side stream, beside the fused kernel (TETRA_EDGE_MODE = 1 / 3 / 2: the literal recursions of
-                // round 1 -- thread per job, warp per job, plain sequential)
+                // block ends on the side stream, beside the fused kernel (TETRA_EDGE_MODE = 1 / 2: the literal recursions of
+                // round 1 -- thread per job with time-skewed sections, or the plain sequential kernel)
                 if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[0], ctx->side));
                 if (!side_edges) rc = 0;
                 else if (edge_corr)
                     rc = launch_edge_correct(ctx, ctx->side, u8_fused ? nullptr : d_x, u8_fused ? u8 : nullptr, u8_fused ? u8_pitch : x_pitch, N,
                                              (int32_t)pl.L, chan_hz ? nullptr : d_fo, chan_hz ? d_fo : nullptr, ctx->sample_rate, pl.rate, ea.cf, C);
                 else if (edge_mode == 2) rc = launch_exact(ctx, ctx->side, ea, edge_jobs, 0);
-                else if (edge_mode == 3 || (edge_mode == 0 && C <= 1536)) rc = launch_edges_warp(ctx, ctx->side, ea, edge_jobs);
                 else rc = launch_edges(ctx, ctx->side, ea, edge_jobs);
                 if (rc) return rc;
                 if (side_edges && ctx->timing && ctx->edge_ev[0]) CK(cudaEventRecord(ctx->edge_ev[1], ctx->side));
