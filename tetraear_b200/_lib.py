@@ -84,7 +84,10 @@ def load():
     if _LIB is not None:
         return _LIB
     path = _build.LIB_PATH
-    if _build.is_stale():
+    alt = os.environ.get("TETRA_B200_LIB")               # an explicitly built variant of the library (A/B measurements)
+    if alt:
+        path = alt
+    elif _build.is_stale():
         try:
             path = _build.build()
         except Exception as e:

@@ -385,6 +385,36 @@ __device__ __forceinline__ float2 k1_req_tap(int k, double fo) {
     return make_float2((float)(x * br1 - br2 + c_req[2 * k]), (float)(x * bi1 - bi2 + c_req[2 * k + 1]));
 }
 
+// outputs [R_LO, R_HI) of a thread's five equalised samples ne0 .. ne0 + 4: out[n] = sum_lag r[lag] ur[n - lag], |lag| <= 5,
+// from the half-band ring window rp[t] = ur[ne0 - 5 + t]. Stage B's threads take three of the five, stage D's the other two
+// (the two roles sit on different SM sub-partitions; the whole equaliser on stage B made its two the busiest of the four).
+template <int R_LO, int R_HI>
+__device__ __forceinline__ void k1_equalise(const float2* __restrict__ rp, const float2* __restrict__ tp, float2* __restrict__ u_ring, int ne0) {
+    float2 e[5];
+#pragma unroll
+    for (int r = R_LO; r < R_HI; ++r) e[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int t = R_LO; t < R_HI + 2 * TB_REQ_K; ++t) {
+        const float2 xv = rp[t];
+        const float2 xs = make_float2(-xv.y, xv.x);          // j * x
+#pragma unroll
+        for (int r = R_LO; r < R_HI; ++r) {
+            const int k = r + TB_REQ_K - (t - TB_REQ_K);     // lag = r - (t - 5), tap index lag + 5
+            if (k >= 0 && k <= 2 * TB_REQ_K) {
+                const float2 c = tp[k];
+                e[r] = ffma2(xv, c.x, e[r]);
+                e[r] = ffma2(xs, c.y, e[r]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = R_LO; r < R_HI; ++r) k1_ring_store<K1_URING, K1_UPAD>(u_ring, ne0 + r, e[r]);
+}
+#ifndef TETRA_K1_EQ_SPLIT
+#define TETRA_K1_EQ_SPLIT 3
+#endif
+constexpr int K1_EQ_SPLIT = TETRA_K1_EQ_SPLIT;   // stage B equalises outputs 0 .. 2, stage D outputs 3, 4 (5: all on stage B, for A/B builds)
+
 // MODE 0: freq_offset == 0. MODE 1: freq_offset != 0, |f| <= 12.5 kHz: the w samples are rotated by the NCO phasor (stage
 // B's warps prepare them one iteration ahead), which leaves proto and the Chebyshev response acting at f + f_off; stage B
 // makes up the difference R(f) = [C2(f+f_off)/P(f+f_off)] / [C2(f)/P(f)] with an 11-tap complex equaliser on its half-band
@@ -722,27 +752,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
                 // taps of the slot the kept outputs of this range belong to (kept outputs lie PREROLL inside their slot)
                 const float2* tp = sf.rtap[min(max(qr, 0), n_my - 1) & 1];
                 const int ne0 = K1_U * i + K1_R0 + 5 * lb;
-                float2 e[5];
-#pragma unroll
-                for (int r = 0; r < 5; ++r) e[r] = make_float2(0.f, 0.f);
                 static_assert(5 + 2 * TB_REQ_K <= K1_RPAD, "equaliser window exceeds its ring's pad");
-                const float2* __restrict__ rp = &sf.ur[(ne0 - TB_REQ_K) & (K1_RRING - 1)];
-#pragma unroll
-                for (int t = 0; t < 5 + 2 * TB_REQ_K; ++t) {          // ur[ne0 - 5 + t]
-                    const float2 xv = rp[t];
-                    const float2 xs = make_float2(-xv.y, xv.x);      // j * x
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) {
-                        const int k = r + TB_REQ_K - (t - TB_REQ_K);    // out[n] += r_lag u[n - lag], lag = r - (t - 5) ... index lag + 5
-                        if (k >= 0 && k <= 2 * TB_REQ_K) {
-                            const float2 c = tp[k];
-                            e[r] = ffma2(xv, c.x, e[r]);
-                            e[r] = ffma2(xs, c.y, e[r]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 5; ++r) k1_ring_store<K1_URING, K1_UPAD>(s.u, ne0 + r, e[r]);
+                k1_equalise<0, K1_EQ_SPLIT>(&sf.ur[(ne0 - TB_REQ_K) & (K1_RRING - 1)], tp, s.u, ne0);
                 rr += K1_W;
                 if (rr >= S) { rr -= S; ++qr; }
             } else {
@@ -798,8 +809,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
         // every output an iteration keeps lies in the slot of stream coordinate 640 i + 2 D0 + PREROLL (kept outputs
         // are PREROLL away from slot ends); that slot index is kept incrementally
         int q_it = k1_floordiv(2 * K1_D0 + K1_PREROLL, S), r_it = 2 * K1_D0 + K1_PREROLL - q_it * S;
+        // MODE 1 / 4: this role's share of the equaliser (the slot of the equalised range is tracked as stage B tracks it)
+        int qr = k1_floordiv(2 * K1_R0 + K1_PREROLL, S), rr = 2 * K1_R0 + K1_PREROLL - qr * S;
         for (int i = 0; i < n_iter; ++i) {
             k1_tick();
+            if (FO) {
+                const float2* tp = sf.rtap[min(max(qr, 0), n_my - 1) & 1];
+                const int ne0 = K1_U * i + K1_R0 + 5 * ld;
+                k1_equalise<K1_EQ_SPLIT, 5>(&sf.ur[(ne0 - TB_REQ_K) & (K1_RRING - 1)], tp, s.u, ne0);
+                rr += K1_W;
+                if (rr >= S) { rr -= S; ++qr; }
+            }
             if (q_it != q_cur) {
                 if (q_cur >= 0 && q_cur < n_my) flush(i);
                 q_cur = q_it;
