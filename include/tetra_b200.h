@@ -44,6 +44,11 @@ int tetra_set_sample_rate(tetra_ctx* ctx, double sample_rate);
 int tetra_set_stream(tetra_ctx* ctx, void* cuda_stream);
 /* Block until everything enqueued by this context has finished. */
 int tetra_synchronize(tetra_ctx* ctx);
+/* Host batches (tetra_process_batch[_sync|_u8] with the IQ in host memory) larger than two chunks go through in
+ * chunks of carriers: the host-to-device copy of the chunks ahead runs on a copy stream beside the kernels and the
+ * result copies of the current chunk. bytes = chunk size (0: the default, 32 MiB; < 0: never chunk). The reference
+ * has no counterpart: SignalProcessor.process takes one block at a time (processor.py:221). */
+int tetra_set_h2d_chunk(tetra_ctx* ctx, int64_t bytes);
 
 /* Upper bound on dibits produced for an N-sample block at the context's sample rate
  * (n_symbols - 1, signal/processor.py:213-215 and :135). */

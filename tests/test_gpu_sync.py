@@ -263,3 +263,42 @@ def test_process_batch_allgather_fused_push(gpu_processor):
     finally:
         for sp in sps_:
             sp.close()
+
+
+def test_sync_positions_on_streams_longer_than_shared_memory(gpu_processor):
+    """Streams of 40 000 dibits (a few seconds of signal in one call): the packed bits and the hit mask live in global
+    scratch (k_sync_positions_long); same positions as the oracle's cascade."""
+    sp = gpu_processor
+    rng = np.random.default_rng(15)
+    n_bits = 80000
+    cases = [
+        [],                                                        # nothing planted: adaptive path
+        [(1, 20, 0), (2, 30001, 0), (1, 79978, 0)],                # first / odd / last window
+        [(2, 45000, 3)],                                           # 19/22: found at 0.85 only
+        [(1, 100, 5), (2, 70000, 5)],                              # 17/22: only the adaptive pass
+        [(1, 12, 0), (1, 200, 0), (2, 262, 0), (1, 40000, 1), (2, 40249, 0), (2, 40250, 0)],   # inside / at the 250 jump
+    ]
+    streams = np.stack([_bits_to_dibits(_planted(rng, n_bits, pl)) for pl in cases])
+    nd = np.array([40000, 40000, 39999, 40000, 25001], dtype=np.int32)   # ragged: the last stream ends before its late plants
+    got = sp.sync_positions(streams, nd)
+    for c, pl in enumerate(cases):
+        bits = ref_dsp.symbols_to_bits(streams[c, : nd[c]])
+        assert got[c] == ref_dsp.sync_cascade(bits), (c, pl)
+
+
+def test_process_batch_sync_on_a_block_longer_than_shared_memory(gpu_processor):
+    """2^21 samples -> 16 130 dibits, more than the fused front end keeps in shared memory: the positions come from the
+    separate launch behind the finalize kernel and equal the oracle's cascade on the oracle's dibits."""
+    from tetraear_b200 import synth
+    sp = gpu_processor
+    sp.sample_rate = 2.4e6
+    x = np.stack([synth.carrier_iq(1 << 21, seed=40 + c, alphabet="pi4", snr_db=12.0 if c else 30.0).astype(np.complex64) for c in range(2)])
+    res = sp.process_batch(x, None, want_symbols=False, want_match=True, want_sync=True)
+    for c in range(2):
+        ref = ref_dsp.process(x[c].astype(np.complex128), 0.0, 2.4e6)
+        nd = int(res["n_dibits"][c])
+        assert nd == len(ref["dibits"]) > 12288 and np.array_equal(res["dibits"][c, :nd], ref["dibits"])
+        want = ref_dsp.sync_cascade(ref_dsp.symbols_to_bits(ref["dibits"]))
+        got = [int(p) for p in res["sync_pos"][c, : res["n_sync"][c]]]
+        assert got == want
+        assert got == sync.sync_cascade(res["ts_match"][c], nd)

@@ -16,6 +16,7 @@ _SIGS = {
     "tetra_last_error": (C.c_char_p, [c_ctx_p]),
     "tetra_set_sample_rate": (C.c_int, [c_ctx_p, C.c_double]),
     "tetra_set_stream": (C.c_int, [c_ctx_p, C.c_void_p]),
+    "tetra_set_h2d_chunk": (C.c_int, [c_ctx_p, C.c_int64]),
     "tetra_synchronize": (C.c_int, [c_ctx_p]),
     "tetra_dibit_capacity": (C.c_int64, [c_ctx_p, C.c_int64]),
     "tetra_symbol_count": (C.c_int64, [c_ctx_p, C.c_int64, C.c_int32]),

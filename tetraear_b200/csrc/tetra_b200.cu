@@ -74,6 +74,9 @@ struct tetra_ctx {
     int device = 0;
     double sample_rate = 2.4e6;
     cudaStream_t own_stream = nullptr, stream = nullptr, side = nullptr;
+    cudaStream_t copy = nullptr;       // H2D copies of a chunked host batch (process_chunked)
+    cudaEvent_t ev_h2d[3] = {nullptr, nullptr, nullptr};
+    int64_t h2d_chunk_bytes = 0;       // tetra_set_h2d_chunk: 0 = default chunk, < 0 = host batches are not chunked
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_grp[4] = {nullptr, nullptr, nullptr, nullptr};   // fused-kernel group g done (K1_MAX_GROUPS)
     // per-launch CUDA-event pairs around the fused kernel (bench.py's roofline leg)
@@ -87,6 +90,7 @@ struct tetra_ctx {
     std::string err;
     bool tables_uploaded = false;
     DevBuf in, y, partial, dib, ndib, sym, phase, match, fo, jobs, scr1, scrz, scr2, tmp_a, tmp_b, tmp_c, mats, wide, spos, u8, stft_tab;
+    DevBuf sync_scr;                   // k_sync_positions_long: packed bits and hit masks of blocks longer than FIN_DIB_SMEM dibits
     DevBuf k1_ctr;                     // work-item counter of the fused kernel (one word, zeroed before every launch)
     DevBuf dout;                       // all results of a small host-side call, back to back (one D2H copy into `hout`)
     PinBuf hout;
@@ -457,6 +461,27 @@ void ba_transition_powers(const ExactCoef& cf, int steps, double* out) {
     for (int r = 1; r < 5; ++r) mat_mul<4>(out + (r - 1) * 16, out + (r - 1) * 16, out + r * 16);
 }
 
+// decode()'s sync search over device-resident dibit streams: blocks up to FIN_DIB_SMEM dibits in shared memory, longer ones
+// through global scratch
+int launch_sync_positions(tetra_ctx* ctx, cudaStream_t st, const uint8_t* dibits, int64_t cap, const int32_t* n_dibits, int32_t C,
+                          int32_t* sync_pos, int32_t max_pos, int32_t* n_sync) {
+    if (cap <= FIN_DIB_SMEM) {
+        SyncPosArgs a;
+        a.dibits = dibits; a.cap = cap; a.n_dibits = n_dibits; a.sync_pos = sync_pos; a.max_pos = max_pos; a.n_sync = n_sync;
+        k_sync_positions<<<C, FIN_THREADS, 0, st>>>(a);
+    } else {
+        SyncPosLongArgs a;
+        a.dibits = dibits; a.cap = cap; a.n_dibits = n_dibits; a.sync_pos = sync_pos; a.max_pos = max_pos; a.n_sync = n_sync;
+        a.words = cap / 16 + 2;
+        CK(ctx->sync_scr.ensure((size_t)C * a.words * 2 * sizeof(uint32_t)));
+        a.bits = (uint32_t*)ctx->sync_scr.p; a.mask = a.bits + (size_t)C * a.words;
+        k_sync_positions_long<<<C, FIN_THREADS, 0, st>>>(a);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TETRA_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -486,6 +511,10 @@ int tetra_create(tetra_ctx** out, int device, double sample_rate) {
         return TETRA_E_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    if (const char* e = getenv("TETRA_H2D_CHUNK_MB")) {   // measurement switch: chunk size of host batches in MiB (< 0: never chunk)
+        const long long mb = atoll(e);
+        ctx->h2d_chunk_bytes = mb < 0 ? -1 : (int64_t)mb << 20;
+    }
     *out = ctx;
     return TETRA_OK;
 }
@@ -500,7 +529,7 @@ void tetra_destroy(tetra_ctx* ctx) {
                       &ctx->etab, &ctx->ecorr, &ctx->estate, &ctx->pfb};
     tetra_p2p_destroy(ctx);
     for (DevBuf* b : bufs) b->release();
-    ctx->dout.release(); ctx->hout.release(); ctx->k1_ctr.release();
+    ctx->dout.release(); ctx->hout.release(); ctx->k1_ctr.release(); ctx->sync_scr.release();
     for (DevBuf& b : ctx->emat) b.release();
     ctx->emat_unit.release();
     cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -508,6 +537,8 @@ void tetra_destroy(tetra_ctx* ctx) {
     for (auto& pr : ctx->ev_pool) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int k = 0; k < 4; ++k) if (ctx->ph_ev[k]) cudaEventDestroy(ctx->ph_ev[k]);
     for (int k = 0; k < 2; ++k) if (ctx->edge_ev[k]) cudaEventDestroy(ctx->edge_ev[k]);
+    if (ctx->copy) { cudaStreamSynchronize(ctx->copy); cudaStreamDestroy(ctx->copy); }
+    for (int k = 0; k < 3; ++k) if (ctx->ev_h2d[k]) cudaEventDestroy(ctx->ev_h2d[k]);
     cudaStreamDestroy(ctx->own_stream); cudaStreamDestroy(ctx->side);
     delete ctx;
 }
@@ -596,9 +627,103 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
                         uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async,
                         const double* chan_hz, const uint8_t* u8 = nullptr, int64_t u8_pitch = 0);
 
+// A batch in chunks of carriers (carriers are independent: every per-carrier buffer is simply offset).
+//  * Large HOST batches: the H2D copy of the chunks ahead runs on the context's copy stream beside the kernels and the D2H
+//    copies of the current chunk, so the call costs the PCIe transfer plus ONE chunk's kernels instead of transfer + kernels
+//    + result copies back to back (process_impl alone enqueues them in that order on one stream).
+//  * More than CHUNK_MAX_CARRIERS carriers (the carrier index is a grid dimension of several kernels): host or device buffers.
+// Returns CHUNK_NOT_APPLICABLE when the call should go through process_impl as it is.
+constexpr int CHUNK_NOT_APPLICABLE = -1000;
+constexpr int CHUNK_MAX_CARRIERS = 32768;
+static int process_chunked(tetra_ctx* ctx, const void* in, bool is_u8, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
+                           uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
+                           uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async) {
+    if (!ctx || !in || C < 2 || N <= 0 || pitch < N || !n_dibits || cap < 0 || (cap > 0 && !dibits) || ctx->fg_active) return CHUNK_NOT_APPLICABLE;
+    if ((sync_pos != nullptr) != (n_sync != nullptr)) return CHUNK_NOT_APPLICABLE;       // process_impl reports it
+    const int64_t bps = is_u8 ? 2 : (int64_t)sizeof(float2);
+    const bool host_in = !is_device_ptr(in);
+    if (host_in && async) return CHUNK_NOT_APPLICABLE;
+    int64_t Cc = C;
+    bool pipelined = false;
+    if (host_in && ctx->h2d_chunk_bytes >= 0) {
+        // 32 MiB: measured on 2 GiB of complex64 / 512 MiB of bytes (profiles/r02_h2d_chunk_ab.txt): 16 ... 128 MiB chunks are within
+        // 1 % of each other for complex64, bytes gain 8 % from 32 MiB over 128 MiB (the last chunk's kernels are what is left exposed)
+        const int64_t chunk_bytes = ctx->h2d_chunk_bytes > 0 ? ctx->h2d_chunk_bytes : ((int64_t)32 << 20);
+        const int64_t per = std::max<int64_t>(1, chunk_bytes / (N * bps));
+        if ((C + per - 1) / per >= 2) { Cc = per; pipelined = true; }
+    }
+    Cc = std::min<int64_t>(Cc, CHUNK_MAX_CARRIERS);
+    if (Cc >= C) return CHUNK_NOT_APPLICABLE;
+    const int n_chunks = (int)((C + Cc - 1) / Cc);
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return CHUNK_NOT_APPLICABLE;
+    auto call = [&](int64_t c0, int32_t cc, const void* chunk_in, int64_t chunk_pitch) {
+        return process_impl(ctx, is_u8 ? nullptr : (const float*)chunk_in, cc, N, chunk_pitch, fo_hz ? fo_hz + c0 : nullptr,
+                            dibits ? dibits + c0 * cap : nullptr, cap, n_dibits + c0, symbols ? symbols + c0 * (cap + 1) * 2 : nullptr,
+                            best_phase ? best_phase + c0 : nullptr, ts_match ? ts_match + c0 * cap * 4 : nullptr,
+                            sync_pos ? sync_pos + c0 * max_pos : nullptr, max_pos, n_sync ? n_sync + c0 : nullptr, async, nullptr,
+                            is_u8 ? (const uint8_t*)chunk_in : nullptr, chunk_pitch);
+    };
+    if (!host_in) {
+        for (int g = 0; g < n_chunks; ++g) {
+            const int64_t c0 = (int64_t)g * Cc;
+            const int rc = call(c0, (int32_t)std::min<int64_t>(Cc, C - c0), (const uint8_t*)in + c0 * pitch * bps, pitch);
+            if (rc) return rc;
+        }
+        return TETRA_OK;
+    }
+    if (!pipelined) {                                       // host input, copy beside the kernels switched off: chunk by chunk
+        for (int g = 0; g < n_chunks; ++g) {
+            const int64_t c0 = (int64_t)g * Cc;
+            const int rc = call(c0, (int32_t)std::min<int64_t>(Cc, C - c0), (const uint8_t*)in + c0 * pitch * bps, pitch);
+            if (rc) return rc;
+        }
+        return TETRA_OK;
+    }
+    DevBuf& buf = is_u8 ? ctx->u8 : ctx->in;
+    CK(buf.ensure((size_t)C * N * bps));
+    if (!ctx->copy) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+        for (int k = 0; k < 3; ++k) CK(cudaEventCreateWithFlags(&ctx->ev_h2d[k], cudaEventDisableTiming));
+    }
+    // the staging buffer may still be read by work enqueued earlier on the context's stream
+    CK(cudaEventRecord(ctx->ev_h2d[2], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_h2d[2], 0));
+    auto issue = [&](int g) -> cudaError_t {
+        const int64_t c0 = (int64_t)g * Cc, cc = std::min<int64_t>(Cc, C - c0);
+        uint8_t* dst = (uint8_t*)buf.p + c0 * N * bps;
+        const uint8_t* src = (const uint8_t*)in + c0 * pitch * bps;
+        cudaError_t e = pitch == N ? cudaMemcpyAsync(dst, src, (size_t)(cc * N * bps), cudaMemcpyHostToDevice, ctx->copy)
+                                   : cudaMemcpy2DAsync(dst, (size_t)(N * bps), src, (size_t)(pitch * bps), (size_t)(N * bps), (size_t)cc,
+                                                       cudaMemcpyHostToDevice, ctx->copy);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_h2d[g % 3], ctx->copy);
+        return e;
+    };
+    CK(issue(0));
+    CK(issue(1));
+    int rc = TETRA_OK;
+    for (int g = 0; g < n_chunks && rc == TETRA_OK; ++g) {
+        const int64_t c0 = (int64_t)g * Cc;
+        cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[g % 3], 0);
+        if (e == cudaSuccess && g + 2 < n_chunks) e = issue(g + 2);     // two chunks ahead of the kernels
+        if (e != cudaSuccess) { rc = fail(ctx, TETRA_E_CUDA, "chunked host batch: %s", cudaGetErrorString(e)); break; }
+        rc = call(c0, (int32_t)std::min<int64_t>(Cc, C - c0), (const uint8_t*)buf.p + c0 * N * bps, N);
+    }
+    if (rc != TETRA_OK) cudaStreamSynchronize(ctx->copy);  // nothing of this call stays in flight behind an error
+    return rc;
+}
+
+int tetra_set_h2d_chunk(tetra_ctx* ctx, int64_t bytes) {
+    if (!ctx) return TETRA_E_INVALID;
+    ctx->h2d_chunk_bytes = bytes;
+    return TETRA_OK;
+}
+
 int tetra_process_batch_sync(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, int64_t pitch, const double* fo_hz,
                              uint8_t* dibits, int64_t cap, int32_t* n_dibits, float* symbols, int32_t* best_phase,
                              uint8_t* ts_match, int32_t* sync_pos, int32_t max_pos, int32_t* n_sync, int32_t async) {
+    const int rc = process_chunked(ctx, iq, false, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, sync_pos,
+                                   max_pos, n_sync, async);
+    if (rc != CHUNK_NOT_APPLICABLE) return rc;
     return process_impl(ctx, iq, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, sync_pos, max_pos,
                         n_sync, async, nullptr);
 }
@@ -636,8 +761,6 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         if (n_sync) { if (d_nsync) CK(cudaMemsetAsync(n_sync, 0, sizeof(int32_t) * C, st)); else memset(n_sync, 0, sizeof(int32_t) * C); }
         return TETRA_OK;
     }
-    if (sync_pos && cap > FIN_DIB_SMEM)                // checked before anything is enqueued
-        return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
     if (sync_pos && (int64_t)max_pos < (2 * cap) / 250 + 2)
         return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
     if (pl.sps > 1 && (pl.sps + pl.step - 1) / pl.step > FIN_MAXPH)
@@ -987,6 +1110,10 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
         ctx->launches++;
         CK(cudaGetLastError());
     }
+    if (sync_pos && !fused_sync) {                      // blocks too long for the fused front end's shared memory
+        rc = launch_sync_positions(ctx, st, k_dib, cap, k_nd, C, k_spos, max_pos, k_nsync);
+        if (rc) return rc;
+    }
     if (ctx->timing && use_fast && ctx->ph_ev[0]) { CK(cudaEventRecord(ctx->ph_ev[3], st)); ctx->ph_valid = true; }
     // ---- results to host buffers ----
     if (staged) {
@@ -1103,6 +1230,11 @@ int tetra_process_batch_u8(tetra_ctx* ctx, const uint8_t* iq_u8, int32_t C, int6
     if (C == 0 || N == 0)
         return tetra_process_batch_sync(ctx, nullptr, C, N, N, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match,
                                         sync_pos, max_pos, n_sync, 0);
+    {
+        const int rc = process_chunked(ctx, iq_u8, true, C, N, pitch, fo_hz, dibits, cap, n_dibits, symbols, best_phase, ts_match, sync_pos,
+                                       max_pos, n_sync, 0);
+        if (rc != CHUNK_NOT_APPLICABLE) return rc;
+    }
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const uint8_t* d_in = iq_u8;
@@ -1195,8 +1327,8 @@ int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, con
     if (C < 0 || cap < 0 || (C > 0 && (!dibits || !n_dibits || !sync_pos || !n_sync)) || max_pos <= 0)
         return fail(ctx, TETRA_E_INVALID, "tetra_sync_positions: bad arguments");
     if (C == 0) return TETRA_OK;
-    if (cap > FIN_DIB_SMEM) return fail(ctx, TETRA_E_UNSUPPORTED, "sync positions need blocks of at most %d dibits", FIN_DIB_SMEM);
     if ((int64_t)max_pos < (2 * cap) / 250 + 2) return fail(ctx, TETRA_E_INVALID, "max_positions too small: need at least %lld", (long long)((2 * cap) / 250 + 2));
+    if (cap > ((int64_t)1 << 29)) return fail(ctx, TETRA_E_INVALID, "tetra_sync_positions: streams too long");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const bool dev_in = is_device_ptr(dibits), dev_nd = is_device_ptr(n_dibits), dev_out = is_device_ptr(sync_pos);
@@ -1218,9 +1350,10 @@ int tetra_sync_positions(tetra_ctx* ctx, const uint8_t* dibits, int64_t cap, con
         a.sync_pos = (int32_t*)ctx->spos.p;
         a.n_sync = a.sync_pos + (size_t)C * max_pos;
     }
-    k_sync_positions<<<C, FIN_THREADS, 0, st>>>(a);
-    ctx->launches++;
-    CK(cudaGetLastError());
+    {
+        const int rc = launch_sync_positions(ctx, st, a.dibits, cap, a.n_dibits, C, a.sync_pos, max_pos, a.n_sync);
+        if (rc) return rc;
+    }
     if (!dev_out) {
         CK(cudaMemcpyAsync(sync_pos, a.sync_pos, (size_t)C * max_pos * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(n_sync, a.n_sync, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));

@@ -116,9 +116,42 @@ __device__ inline int sync_walk(const uint32_t* mask, int nw, int32_t* pos, int 
     return n;
 }
 
+// the same walk by the 32 lanes of one warp, for masks in global memory: empty stretches are scanned 32 words per load
+__device__ inline int sync_walk_warp(const uint32_t* mask, int nw, int32_t* pos, int max_pos) {
+    const int lane = threadIdx.x & 31;
+    const int n_words = (nw + 31) >> 5;
+    int n = 0, i = 0;
+    while (i < nw) {
+        int wd = i >> 5;
+        uint32_t m = mask[wd] & (0xFFFFFFFFu << (i & 31));
+        if (m == 0) {
+            int found = -1;
+            for (int base = wd + 1; base < n_words; base += 32) {
+                const int w = base + lane;
+                const uint32_t v = w < n_words ? mask[w] : 0u;
+                const unsigned b = __ballot_sync(0xffffffffu, v != 0u);
+                if (b) {
+                    const int l = __ffs(b) - 1;
+                    found = base + l;
+                    m = __shfl_sync(0xffffffffu, v, l);
+                    break;
+                }
+            }
+            if (found < 0) break;
+            wd = found;
+        }
+        const int p = (wd << 5) + __ffs(m) - 1;
+        if (p >= nw) break;
+        if (lane == 0 && n < max_pos) pos[n] = p;
+        ++n;
+        i = p + 250;
+    }
+    return n;
+}
+
 // find_sync(bits, threshold) -> number of positions (written to pos[], global or shared), *max_corr
 __device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double thr, int32_t* pos, int max_pos,
-                               SyncScratch& sc, double* max_corr) {
+                               SyncScratch& sc, double* max_corr, uint32_t* mask) {
     const int tid = threadIdx.x;
     const int n_words = (nw + 31) >> 5;
     const int cmin = sync_min_count(thr);
@@ -133,11 +166,14 @@ __device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double
                 if (c1 >= cmin || c2 >= cmin) m |= 1u << b;
             }
         }
-        sc.mask[wd] = m;
+        mask[wd] = m;
     }
     if (tid == 0) sc.max_cnt = 0;
     __syncthreads();
-    if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+    const bool global_mask = mask != sc.mask;
+    if (global_mask) {
+        if (tid < 32) { const int np = sync_walk_warp(mask, nw, pos, max_pos); if (tid == 0) sc.n_pos = np; }
+    } else if (tid == 0) sc.n_pos = sync_walk(mask, nw, pos, max_pos);
     __syncthreads();
     int n = sc.n_pos;
     // max_corr over the VISITED offsets: everything except the 249 offsets skipped after each hit. At a visited
@@ -175,11 +211,13 @@ __device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double
                         if (max(c1, c2) >= amin) m |= 1u << b;      // no offset was skipped: best_here = max of both
                     }
                 }
-                sc.mask[wd] = m;
+                mask[wd] = m;
             }
             __syncthreads();
             // accepted offsets block +-250 around them; scanning upwards that is the same jump-250 walk
-            if (tid == 0) sc.n_pos = sync_walk(sc.mask, nw, pos, max_pos);
+            if (global_mask) {
+                if (tid < 32) { const int np = sync_walk_warp(mask, nw, pos, max_pos); if (tid == 0) sc.n_pos = np; }
+            } else if (tid == 0) sc.n_pos = sync_walk(mask, nw, pos, max_pos);
             __syncthreads();
             n = sc.n_pos;
         }
@@ -189,14 +227,21 @@ __device__ int block_find_sync(const uint32_t* __restrict__ bits, int nw, double
 }
 
 // decode()'s cascade 0.90 -> 0.85 -> 0.80 -> adaptive (decoder.py:845-856)
-__device__ int block_sync_cascade(const uint32_t* __restrict__ bits, int nd, int32_t* pos, int max_pos, SyncScratch& sc) {
+// `mask`: one bit per window start -- the scratch's own array (blocks up to FIN_DIB_SMEM dibits) or global memory (longer ones)
+__device__ int block_sync_cascade(const uint32_t* __restrict__ bits, int nd, int32_t* pos, int max_pos, SyncScratch& sc,
+                                  uint32_t* mask = nullptr) {
+    if (!mask) mask = sc.mask;
     const int nw = 2 * nd - 22 + 1;
-    if (nw <= 0) return 0;                              // decoder.py:226-228: fewer than 22 bits
+    if (nw <= 0) {                                      // decoder.py:226-228: fewer than 22 bits
+        for (int i = threadIdx.x; i < max_pos; i += FIN_THREADS) pos[i] = 0;
+        return 0;
+    }
     double mx = 0.0;
-    int n = block_find_sync(bits, nw, 0.90, pos, max_pos, sc, &mx);
-    if (n == 0) n = block_find_sync(bits, nw, 0.85, pos, max_pos, sc, &mx);
-    if (n == 0) n = block_find_sync(bits, nw, 0.80, pos, max_pos, sc, &mx);
-    if (n == 0 && mx >= 0.75) n = block_find_sync(bits, nw, fmax(0.75, mx - 0.02), pos, max_pos, sc, &mx);
+    int n = block_find_sync(bits, nw, 0.90, pos, max_pos, sc, &mx, mask);
+    if (n == 0) n = block_find_sync(bits, nw, 0.85, pos, max_pos, sc, &mx, mask);
+    if (n == 0) n = block_find_sync(bits, nw, 0.80, pos, max_pos, sc, &mx, mask);
+    if (n == 0 && mx >= 0.75) n = block_find_sync(bits, nw, fmax(0.75, mx - 0.02), pos, max_pos, sc, &mx, mask);
+    for (int i = n + (int)threadIdx.x; i < max_pos; i += FIN_THREADS) pos[i] = 0;      // unused entries read 0, whatever the buffer held
     return n;
 }
 
@@ -436,6 +481,24 @@ __global__ void __launch_bounds__(FIN_THREADS) k_sync_positions(const SyncPosArg
     pack_dibits(s_dib, nd, s_bits);
     __syncthreads();
     const int n = block_sync_cascade(s_bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync);
+    if (threadIdx.x == 0) a.n_sync[car] = n;
+}
+
+// the same for blocks of more than FIN_DIB_SMEM dibits (a recording processed in one call): the packed bits and the hit
+// mask of a carrier live in global scratch ([C][words] each, words = cap / 16 + 2) instead of shared memory
+struct SyncPosLongArgs {
+    const uint8_t* dibits; int64_t cap; const int32_t* n_dibits;
+    int32_t* sync_pos; int32_t max_pos; int32_t* n_sync;
+    uint32_t* bits; uint32_t* mask; int64_t words;
+};
+__global__ void __launch_bounds__(FIN_THREADS) k_sync_positions_long(const SyncPosLongArgs a) {
+    __shared__ SyncScratch s_sync;
+    const int car = blockIdx.x;
+    const int nd = (int)min((int64_t)a.n_dibits[car], a.cap);
+    uint32_t* bits = a.bits + (int64_t)car * a.words;
+    pack_dibits(a.dibits + (int64_t)car * a.cap, nd, bits);
+    __syncthreads();                                     // the CTA's own global stores, visible to all of its threads
+    const int n = block_sync_cascade(bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync, a.mask + (int64_t)car * a.words);
     if (threadIdx.x == 0) a.n_sync[car] = n;
 }
 
