@@ -735,6 +735,7 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     // u8 != null: the input is [C][u8_pitch][2] unsigned bytes on the device (RTL-SDR format) and `iq` is unused
     if (!ctx) return TETRA_E_INVALID;
     static const int edge_mode = getenv("TETRA_EDGE_MODE") ? atoi(getenv("TETRA_EDGE_MODE")) : 0;   // debug switch, see DESIGN.md §5
+    static const bool fin_prefetch = getenv("TETRA_FIN_PREFETCH") ? atoi(getenv("TETRA_FIN_PREFETCH")) != 0 : true;   // A/B switch
     if ((sync_pos != nullptr) != (n_sync != nullptr) || (sync_pos && max_pos <= 0))
         return fail(ctx, TETRA_E_INVALID, "tetra_process_batch_sync: sync_pos, n_sync and max_positions go together");
     if (C < 0 || N < 0 || (C > 0 && N > 0 && (u8 ? u8_pitch < N : (!iq || pitch < N))) || !n_dibits || (cap > 0 && !dibits) || cap < 0)
@@ -1084,7 +1085,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
                 const int p_lo = (g - 1) * grp_car;
                 CK(cudaStreamWaitEvent(ctx->side, ctx->ev_grp[g - 1], 0));
                 fa.car0 = p_lo;
-                k_finalize<<<c_lo - p_lo, FIN_THREADS, 0, ctx->side>>>(fa);
+                if (fin_prefetch) k_finalize<true><<<c_lo - p_lo, FIN_THREADS, 0, ctx->side>>>(fa);
+                else k_finalize<false><<<c_lo - p_lo, FIN_THREADS, 0, ctx->side>>>(fa);
                 ctx->launches++;
                 CK(cudaGetLastError());
             }
@@ -1100,7 +1102,8 @@ static int process_impl(tetra_ctx* ctx, const float* iq, int32_t C, int64_t N, i
     }
     if (ctx->timing && use_fast && ctx->ph_ev[0]) CK(cudaEventRecord(ctx->ph_ev[2], st));
     fa.car0 = fin_c0;
-    k_finalize<<<C - fin_c0, FIN_THREADS, 0, st>>>(fa);
+    if (fin_prefetch) k_finalize<true><<<C - fin_c0, FIN_THREADS, 0, st>>>(fa);
+    else k_finalize<false><<<C - fin_c0, FIN_THREADS, 0, st>>>(fa);
     ctx->launches++;
     CK(cudaGetLastError());
     if (ts_match && cap > 0 && !fused_match) {

@@ -269,6 +269,7 @@ struct FinSmem {
 
 // everything k_finalize does for one carrier, by the FIN_THREADS threads of a CTA. y, partial and the corrections are read
 // once: L2 loads (ld.global.cg)
+template <bool PREFETCH>
 __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car, FinSmem& sm) {
     double* red = sm.red;
     int& s_best = sm.s_best;
@@ -368,22 +369,36 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
         }
         __syncthreads();
     }
-    auto sym_at = [&](int k) {
-        float2 v = __ldcg(ys + ks * k);
+    // symbol k as the slicer sees it: the loaded sample, or its corrected copy next to a block end
+    auto fixed = [&](int k, float2 v) {
         if (k < k_head) v = s_fix[k];
         else if (k >= k_tail) v = s_fix[k_head + (k - k_tail)];
         return v;
     };
-    // every warp runs the same number of batches (the previous symbol comes from the neighbouring lane by shuffle; only lane 0
-    // loads its own)
-    for (int base = 0; base < n_sym; base += FIN_B * FIN_THREADS) {
-        float2 s1[FIN_B], s0[FIN_B];
+    // a batch's loads: symbol k of every slot of this thread and, on lane 0, its predecessor (the other lanes get theirs from
+    // the neighbouring lane by shuffle). Every warp runs the same number of batches.
+    auto fetch = [&](int base, float2 (&d1)[FIN_B], float2 (&d0)[FIN_B]) {
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
             const int k = min(base + tid + j * FIN_THREADS, n_sym - 1);
-            s1[j] = sym_at(k);
-            if ((tid & 31) == 0) s0[j] = sym_at(max(k - 1, 0));
+            d1[j] = __ldcg(ys + ks * k);
+            if ((tid & 31) == 0) d0[j] = __ldcg(ys + ks * max(k - 1, 0));
         }
+    };
+    // PREFETCH: the loads of batch b + 1 are issued before batch b is sliced (a CTA has eight batches of dependent load ->
+    // slice -> store rounds per carrier; without the prefetch the load latency of every round is exposed)
+    float2 nx1[FIN_B], nx0[FIN_B];
+    if (PREFETCH && n_sym > 0) fetch(0, nx1, nx0);
+    for (int base = 0; base < n_sym; base += FIN_B * FIN_THREADS) {
+        float2 s1[FIN_B], s0[FIN_B];
+        if (!PREFETCH) fetch(base, nx1, nx0);
+#pragma unroll
+        for (int j = 0; j < FIN_B; ++j) {
+            const int k = min(base + tid + j * FIN_THREADS, n_sym - 1);
+            s1[j] = fixed(k, nx1[j]);
+            if ((tid & 31) == 0) s0[j] = fixed(max(k - 1, 0), nx0[j]);
+        }
+        if (PREFETCH && base + FIN_B * FIN_THREADS < n_sym) fetch(base + FIN_B * FIN_THREADS, nx1, nx0);
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
             const float px = __shfl_up_sync(0xffffffffu, s1[j].x, 1), py = __shfl_up_sync(0xffffffffu, s1[j].y, 1);
@@ -459,9 +474,11 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     }
 }
 
-__global__ void __launch_bounds__(FIN_THREADS, 5) k_finalize(const FinArgs a) {
+// PREFETCH: 64 registers / 4 CTAs per SM with the next batch's loads in flight; without: 48 registers / 5 CTAs per SM
+template <bool PREFETCH>
+__global__ void __launch_bounds__(FIN_THREADS, PREFETCH ? 4 : 5) k_finalize(const FinArgs a) {
     __shared__ FinSmem sm;
-    finalize_carrier(a, a.car0 + blockIdx.x, sm);
+    finalize_carrier<PREFETCH>(a, a.car0 + blockIdx.x, sm);
 }
 
 // standalone: sync positions from dibit streams (the same device code; used when the streams come from elsewhere)

@@ -455,7 +455,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     for (int i = tid; i < K1_VRING + K1_VPAD; i += K1_THREADS) s.v[i] = make_float2(0.f, 0.f);
     for (int i = tid; i < K1_NBUF * (K1_HDR + K1_TILE); i += K1_THREADS) (&s.in[0][0])[i] = make_float2(0.f, 0.f);
     if (tid == 0) {
-        s.s_item[0] = (int)atomicAdd(a.counter, 1u);      // the grid never exceeds the item count: every CTA gets a first item
+        s.s_item[0] = (int)atomicAdd(a.counter, 1u);      // the grid never exceeds the item count, but see the check below
         s.s_nmy = K1_NMY_UNKNOWN;
         for (int b = 0; b < K1_NBUF; ++b) mbar_init(&s.full[b], 1);
         if (U8) for (int b = 0; b < K1_RAWBUF; ++b) mbar_init(&rawfull[b], 1);
@@ -464,6 +464,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) k1_channelize_demod(const K1Arg
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeroed input buffers are refilled by bulk copies
     __syncthreads();                                      // slot 0's item is known to every thread
+    // A CTA that starts late -- its SM was still held by a block-end kernel of the side stream, say -- may find the counter
+    // already run out by the other CTAs' look-ahead claims (launches with about as many items as CTAs): nothing is left for it.
+    if (*reinterpret_cast<const volatile int*>(&s.s_item[0]) >= a.n_items) return;
     if (ROT) {
         const K1Slot s0 = k1_slot(a, s, 0);
         if (FO && tid < 2 * TB_REQ_K + 1) sf.rtap[0][tid] = k1_req_tap(tid, a.fo[s0.car]);
