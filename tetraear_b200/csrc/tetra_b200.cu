@@ -254,9 +254,15 @@ int launch_edge_correct(tetra_ctx* ctx, cudaStream_t st, const float2* x, const 
         ea.m = (const double*)ctx->emat[k0].p;
     }
     const int g1 = d_fo ? (C + KC_THREADS / 32 - 1) / (KC_THREADS / 32) : C;      // with freq_offsets: one warp per carrier
-    if (x8) k_edge_states<1><<<g1, KC_THREADS, 0, st>>>(ea);
-    else if (d_chan) k_edge_states<2><<<g1, KC_THREADS, 0, st>>>(ea);
-    else k_edge_states<0><<<g1, KC_THREADS, 0, st>>>(ea);
+    if (ea.fo) {
+        if (x8) k_edge_states<1, true><<<g1, KC_THREADS, 0, st>>>(ea);
+        else if (d_chan) k_edge_states<2, true><<<g1, KC_THREADS, 0, st>>>(ea);
+        else k_edge_states<0, true><<<g1, KC_THREADS, 0, st>>>(ea);
+    } else {
+        if (x8) k_edge_states<1, false><<<g1, KC_THREADS, 0, st>>>(ea);
+        else if (d_chan) k_edge_states<2, false><<<g1, KC_THREADS, 0, st>>>(ea);
+        else k_edge_states<0, false><<<g1, KC_THREADS, 0, st>>>(ea);
+    }
     if (d_fo) k_edge_recursions<<<dim3((C + KC2_THREADS - 1) / KC2_THREADS, 2), KC2_THREADS, 0, st>>>(ea);
     else k_edge_apply<<<dim3((C + KA_CPB - 1) / KA_CPB, 2), KA_THREADS, 0, st>>>(ea);
     ctx->launches++;

@@ -137,13 +137,15 @@ __device__ __forceinline__ void kc_warp_sum(dcx (&acc)[NA], double2* dst, int la
 // ----------------------------------------------------------------------------------------------
 // k_edge_states: the functionals. One warp per carrier; lane l takes samples l, l + 32, ... of each end.
 // ----------------------------------------------------------------------------------------------
-template <int IN>   // 0: complex64 rows, 1: uint8 rows, 2: channels of one shared complex64 capture
-__global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a) {
+// FO: the batch has freq_offsets (a.fo != null). A compile-time switch because the modal recursion of that case keeps 80
+// float64 registers alive; without it the common kernel fits more CTAs per SM.
+template <int IN, bool FO>   // IN 0: complex64 rows, 1: uint8 rows, 2: channels of one shared complex64 capture
+__global__ void __launch_bounds__(KC_THREADS, FO ? 3 : 5) k_edge_states(const EdgeCorrArgs a) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Without freq_offsets: one CTA per carrier, its four warps share the seven table passes (role = warp). With them the
     // Butterworth-state pass is a serial chain ~18 table passes long that no split of the others can balance: one warp per
     // carrier does everything (role -1), four carriers per CTA.
-    const bool wpc = a.fo != nullptr;
+    constexpr bool wpc = FO;
     const int car = wpc ? blockIdx.x * (KC_THREADS / 32) + warp : blockIdx.x;
     if (car >= a.n_carriers) return;                          // whole warps
     const int role = wpc ? -1 : warp;
@@ -152,7 +154,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
     const int L = a.L;
     const int k0 = (int)((n - 1) % 10);
     const double chan_hz = (IN == 2) ? a.chan[car] : 0.0;
-    const double fo = a.fo ? a.fo[car] : 0.0;
+    const double fo = FO ? a.fo[car] : 0.0;
     auto xr = [&](int d) { return kc_load<IN>(a, car, chan_hz, n - 1 - d); };      // d samples before the last one
     auto xl = [&](int i) { return kc_load<IN>(a, car, chan_hz, i); };
     double2* out = a.states + (int64_t)car * KC_NSTATE;
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
     // s(L) = e^{-jW(L-1)} sum_d x[n-1-d] Wv(d - k0),  Wv(u) = Bv g1[u] + e^{jW} A Wv(u - 10)  (tools/edge_model.py).
     // Without a freq_offset the weights are real and fixed: one more table pass.
     if (!has(0)) return;
-    if (fo == 0.0) {
+    if (!FO || fo == 0.0) {
         dcx a4[4] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
         const double* __restrict__ w0 = a.t.w0 + 9 - k0;      // w0[k * NW0 + d] = W0[k][d - k0 + 9]
         const int cnt = ET_NW0 - 9 + k0;
@@ -267,6 +269,7 @@ __global__ void __launch_bounds__(KC_THREADS) k_edge_states(const EdgeCorrArgs a
         kc_warp_sum(a4, out + KS_S2, lane);
         return;
     }
+    if (!FO) return;
     // With one: in modal coordinates (A = V diag(p) V^-1, lambda_r = p_r e^{jW}):
     //   s(L) = V sigma,  sigma_r = c_r e^{-jW(L-1)} sum_d x[n-1-d] Om_r(d - k0),  Om_r(u) = g1[u] + lambda_r Om_r(u - 10).
     // Ten chains (u mod 10) of NSTEP steps, each cut into three segments: a lane runs its segment from zero, then the

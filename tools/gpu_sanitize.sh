@@ -5,8 +5,8 @@ set -u
 TAG=${1:-sanitize}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-SEL='tiny or rate_ or gui or unaligned or one_symbol or mixed or outside_fused or u8_ingest or u8_with or survey or spectrum or shapes or peer_memory or allgather or transport or edge or crafted or bursts'
-timeout 2400 compute-sanitizer --tool memcheck --print-limit 20 python -m pytest tests -m gpu -q -x -k "$SEL" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/status.txt
+SEL='tiny or rate_ or gui or unaligned or one_symbol or mixed or outside_fused or u8_ingest or u8_with or survey or spectrum or shapes or peer_memory or allgather or transport or edge or crafted or bursts or chunked or longer_than or as_many_items'
+timeout 2400 compute-sanitizer --tool memcheck --padding 4096 --print-limit 20 python -m pytest tests -m gpu -q -x -k "$SEL" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/status.txt
 tail -6 $OUT/memcheck.log
 timeout 1800 compute-sanitizer --tool racecheck --print-limit 20 python __graft_entry__.py smoke > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/status.txt
 tail -6 $OUT/racecheck.log
