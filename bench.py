@@ -382,7 +382,8 @@ def run_ours(a):
     e2e = {"value": world * ce * N_SAMPLES / dt / 1e6, "unit": "MS/s",
            "h2d_bytes_per_step": int(ce * N_SAMPLES * 8), "d2h_bytes_per_step": int(ce * (cap + 8 + 8 * (cap + 1))),
            "carriers_per_rank": ce, "timed": "host wall clock around SignalProcessor.process_batch, max over ranks",
-           "note": "pinned host IQ -> tetra_process_batch -> host dibits + soft symbols + timing phase; PCIe-bound"}
+           "note": "pinned host IQ -> tetra_process_batch (32 MiB chunks of carriers, the H2D copy of the chunks ahead beside the kernels "
+                   "and result copies of the current one) -> host dibits + soft symbols + timing phase; PCIe-bound"}
 
     # ---- the same through the RTL-SDR byte format: 2 bytes per sample cross PCIe ----
     scale = float(x[:ce].abs().max().item())

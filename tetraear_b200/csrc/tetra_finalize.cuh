@@ -245,17 +245,37 @@ __device__ int block_sync_cascade(const uint32_t* __restrict__ bits, int nd, int
     return n;
 }
 
-// dibits in shared memory -> MSB-first packed bits (decoder.py:140-169), one zero word behind
+// dibits -> MSB-first packed bits (decoder.py:140-169), one zero word behind. Four dibits in the four bytes of a 32-bit word
+// (lowest address first) become one byte, first dibit highest.
+__device__ __forceinline__ uint32_t pack4_msb(uint32_t x) {
+    const uint32_t t = x & 0x03030303u;
+    return ((t << 6) | (t >> 4) | (t >> 14) | (t >> 24)) & 0xFFu;
+}
+// s_dib: 16-byte aligned shared memory (entries behind nd may hold anything)
 __device__ __forceinline__ void pack_dibits(const uint8_t* s_dib, int nd, uint32_t* s_bits) {
+    const int n_words = (nd + 15) / 16 + 1;
+    for (int j = threadIdx.x; j < n_words; j += blockDim.x) {
+        const int valid = nd - 16 * j;                      // dibits of this word that belong to the stream
+        uint32_t w = 0;
+        if (valid > 0) {
+            const uint4 v = *reinterpret_cast<const uint4*>(s_dib + 16 * j);
+            w = (pack4_msb(v.x) << 24) | (pack4_msb(v.y) << 16) | (pack4_msb(v.z) << 8) | pack4_msb(v.w);
+            if (valid < 16) w &= ~((1u << (2 * (16 - valid))) - 1u);
+        }
+        s_bits[j] = w;
+    }
+}
+// the same from global memory with any alignment (k_sync_positions_long)
+__device__ __forceinline__ void pack_dibits_bytes(const uint8_t* dib, int nd, uint32_t* bits) {
     const int n_words = (nd + 15) / 16 + 1;
     for (int j = threadIdx.x; j < n_words; j += blockDim.x) {
         uint32_t w = 0;
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int idx = 16 * j + m;
-            w = (w << 2) | (idx < nd ? (uint32_t)(s_dib[idx] & 3u) : 0u);
+            w = (w << 2) | (idx < nd ? (uint32_t)(dib[idx] & 3u) : 0u);
         }
-        s_bits[j] = w;
+        bits[j] = w;
     }
 }
 
@@ -392,11 +412,20 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     for (int base = 0; base < n_sym; base += FIN_B * FIN_THREADS) {
         float2 s1[FIN_B], s0[FIN_B];
         if (!PREFETCH) fetch(base, nx1, nx0);
+        // only the first and the last batches hold symbols next to a block end (CTA-uniform)
+        const bool end_batch = base <= k_head || base + FIN_B * FIN_THREADS >= k_tail;
 #pragma unroll
         for (int j = 0; j < FIN_B; ++j) {
-            const int k = min(base + tid + j * FIN_THREADS, n_sym - 1);
-            s1[j] = fixed(k, nx1[j]);
-            if ((tid & 31) == 0) s0[j] = fixed(max(k - 1, 0), nx0[j]);
+            s1[j] = nx1[j];
+            if ((tid & 31) == 0) s0[j] = nx0[j];
+        }
+        if (end_batch) {
+#pragma unroll
+            for (int j = 0; j < FIN_B; ++j) {
+                const int k = min(base + tid + j * FIN_THREADS, n_sym - 1);
+                s1[j] = fixed(k, s1[j]);
+                if ((tid & 31) == 0) s0[j] = fixed(max(k - 1, 0), s0[j]);
+            }
         }
         if (PREFETCH && base + FIN_B * FIN_THREADS < n_sym) fetch(base + FIN_B * FIN_THREADS, nx1, nx0);
 #pragma unroll
@@ -425,19 +454,25 @@ __device__ __forceinline__ void finalize_carrier(const FinArgs& a, const int car
     const int nw = 2 * nd - 22 + 1;                     // window starts (decoder.py:232)
     if (a.match) {
         uint8_t* out = a.match + (int64_t)car * a.cap * 4;
-        for (int p = tid; 2 * p < nw; p += FIN_THREADS) {   // windows 2p and 2p+1 share their words
-            const int i = 2 * p;
+        for (int p = tid; 4 * p < nw; p += FIN_THREADS) {   // windows 4p .. 4p+3 share their words
+            const int i = 4 * p;
             const uint64_t two = ((uint64_t)s_bits[i >> 5] << 32) | s_bits[(i >> 5) + 1];
-            const int sh = i & 31;                          // even, <= 30: 23 bits starting at sh fit in 64
-            const uint32_t w0 = (uint32_t)(two >> (64 - 22 - sh)) & 0x3FFFFFu;
-            const uint32_t w1 = (uint32_t)(two >> (64 - 23 - sh)) & 0x3FFFFFu;
-            uchar4 o;
-            o.x = (uint8_t)(22 - __popc(w0 ^ TS1_BITS));
-            o.y = (uint8_t)(22 - __popc(w0 ^ TS2_BITS));
-            o.z = (uint8_t)(22 - __popc(w1 ^ TS1_BITS));
-            o.w = (uint8_t)(22 - __popc(w1 ^ TS2_BITS));
-            if (i + 1 < nw) *reinterpret_cast<uchar4*>(out + 2 * (int64_t)i) = o;
-            else { out[2 * (int64_t)i] = o.x; out[2 * (int64_t)i + 1] = o.y; }
+            const int sh = i & 31;                          // a multiple of 4, <= 28: 25 bits starting at sh fit in 64
+            uint32_t c[4];                                  // c[m]: TS1 count | TS2 count << 8 of window i + m
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const uint32_t w = (uint32_t)(two >> (64 - 22 - m - sh)) & 0x3FFFFFu;
+                c[m] = (uint32_t)(22 - __popc(w ^ TS1_BITS)) | ((uint32_t)(22 - __popc(w ^ TS2_BITS)) << 8);
+            }
+            uint8_t* o = out + 2 * (int64_t)i;              // 4-byte aligned: rows are multiples of 4 bytes, i of 4
+            if (i + 3 < nw) {
+                *reinterpret_cast<uint32_t*>(o) = c[0] | (c[1] << 16);
+                *reinterpret_cast<uint32_t*>(o + 4) = c[2] | (c[3] << 16);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (i + m < nw) *reinterpret_cast<uint16_t*>(o + 2 * m) = (uint16_t)c[m];
+            }
         }
     }
     if (a.sync_pos) {
@@ -513,7 +548,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_sync_positions_long(const SyncP
     const int car = blockIdx.x;
     const int nd = (int)min((int64_t)a.n_dibits[car], a.cap);
     uint32_t* bits = a.bits + (int64_t)car * a.words;
-    pack_dibits(a.dibits + (int64_t)car * a.cap, nd, bits);
+    pack_dibits_bytes(a.dibits + (int64_t)car * a.cap, nd, bits);
     __syncthreads();                                     // the CTA's own global stores, visible to all of its threads
     const int n = block_sync_cascade(bits, nd, a.sync_pos + (int64_t)car * a.max_pos, a.max_pos, s_sync, a.mask + (int64_t)car * a.words);
     if (threadIdx.x == 0) a.n_sync[car] = n;
