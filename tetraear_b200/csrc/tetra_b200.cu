@@ -203,6 +203,8 @@ int upload_tables(tetra_ctx* ctx) {
                       sizeof ET_RING == sizeof(double) * 8 * ET_NRING && sizeof ET_U == sizeof(double) * 64, "edge tables changed shape");
         size_t total = 0;
         for (size_t c : cnt) total += (c + 3) & ~(size_t)3;             // every table starts on a 32-byte boundary
+        const size_t g1p_off = total, g1p_cnt = (size_t)(2 * ET_G + 1 + 2 * ET_G1_PAD);
+        total += (g1p_cnt + 3) & ~(size_t)3;                            // g1 once more, between two runs of zeros
         CK(ctx->etab.ensure(total * sizeof(double)));
         const double* dev[NT];
         size_t off = 0;
@@ -211,8 +213,14 @@ int upload_tables(tetra_ctx* ctx) {
             CK(cudaMemcpy((double*)ctx->etab.p + off, src[k], cnt[k] * sizeof(double), cudaMemcpyHostToDevice));
             off += (cnt[k] + 3) & ~(size_t)3;
         }
-        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9], dev[10]};
+        CK(cudaMemset((double*)ctx->etab.p + g1p_off, 0, g1p_cnt * sizeof(double)));
+        CK(cudaMemcpy((double*)ctx->etab.p + g1p_off + ET_G1_PAD, ET_G1, sizeof ET_G1, cudaMemcpyHostToDevice));
+        ctx->etab_ptrs = EdgeTables{dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6], dev[7], dev[8], dev[9], dev[10],
+                                    (const double*)ctx->etab.p + g1p_off + ET_G1_PAD};
     }
+    // the copies above ran on the legacy default stream and may return with their last DMA in flight; the kernels use
+    // non-blocking streams. Only that stream is waited for: another context's kernels may be spinning on this context's push.
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     ctx->tables_uploaded = true;
     return 0;
 }

@@ -54,7 +54,12 @@ struct EdgeTables {          // device copies of edge_tables_generated.h
     const double* bp;        // [4][2]      poles of the Butterworth stage
     const double* bc;        // [4][2]      its input vector in modal coordinates
     const double* bv;        // [4][4][2]   modal coordinates -> lfilter state
+    const double* g1p;       // g1 between two runs of ET_G1_PAD zeros: g1p[i] = g1[i] for 0 <= i <= 2 G, 0 for -PAD <= i < 0 and
+                             // 2 G < i <= 2 G + PAD (the pointwise windows index it without a range check)
 };
+constexpr int ET_G1_PAD = 96;
+static_assert(ET_G1_PAD >= 10 * 7 + 1 && ET_G - 9 - 80 * (ET_NPTS / 8 - 1) - 70 >= -ET_G1_PAD && ET_G + 80 * (ET_NPTS / 8 - 1) + 70 <= 2 * ET_G + ET_G1_PAD,
+              "pointwise window indices leave the padded table");
 
 struct EdgeCorrArgs {
     const float2* x;         // [C][pitch] complex64 ...
@@ -159,6 +164,7 @@ __global__ void __launch_bounds__(KC_THREADS, FO ? 3 : 5) k_edge_states(const Ed
     auto xl = [&](int i) { return kc_load<IN>(a, car, chan_hz, i); };
     double2* out = a.states + (int64_t)car * KC_NSTATE;
     const double* __restrict__ g1 = a.t.g1;
+    const double* __restrict__ g1p = a.t.g1p;
     constexpr int UN = 4;                                      // samples in flight per lane
 
     dcx acc[8];
@@ -220,10 +226,12 @@ __global__ void __launch_bounds__(KC_THREADS, FO ? 3 : 5) k_edge_states(const Ed
             for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < cnt_r ? xr(d0 + 32 * q) : dcx{0.0, 0.0};
 #pragma unroll
             for (int q = 0; q < UN; ++q) {
+                // lanes beyond the window hold v = 0: any finite weight will do, the index only has to stay inside the table;
+                // inside the window off_r - 70 <= idx <= 2 G + 70, where the padded table reads g1 or 0
+                const double* __restrict__ gp = g1p + (min(d0 + 32 * q, cnt_r - 1) + off_r);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int idx = d0 + 32 * q + off_r - 10 * k;
-                    const double w = (idx >= 0 && idx <= 2 * ET_G) ? g1[idx] : 0.0;
+                    const double w = gp[-10 * k];
                     acc[k].x += w * v[q].x; acc[k].y += w * v[q].y;
                 }
             }
@@ -237,10 +245,10 @@ __global__ void __launch_bounds__(KC_THREADS, FO ? 3 : 5) k_edge_states(const Ed
             for (int q = 0; q < UN; ++q) v[q] = d0 + 32 * q < cnt_l ? xl(d0 + 32 * q) : dcx{0.0, 0.0};
 #pragma unroll
             for (int q = 0; q < UN; ++q) {
+                const double* __restrict__ gp = g1p + (off_l - min(d0 + 32 * q, cnt_l - 1));     // -70 <= idx <= G + 150
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int idx = off_l + 10 * k - (d0 + 32 * q);
-                    const double w = (idx >= 0 && idx <= 2 * ET_G) ? g1[idx] : 0.0;
+                    const double w = gp[10 * k];
                     acc[k].x += w * v[q].x; acc[k].y += w * v[q].y;
                 }
             }
