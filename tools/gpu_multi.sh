@@ -5,7 +5,7 @@ N=${1:-2}; TAG=${2:-r02_n$N}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 nvidia-smi topo -m > $OUT/topo.txt 2>&1
-for G in p2p p2p-fused nccl; do
+for G in ${GATHERS:-p2p p2p-fused nccl}; do
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 3 --gather $G > $OUT/bench_$G.json 2> $OUT/bench_$G.err; echo "bench $G rc=$?" | tee -a $OUT/status.txt
 tail -3 $OUT/bench_$G.err
 python - <<PY
