@@ -79,3 +79,40 @@ def test_batch_shapes_against_the_oracle(gpu_processor, bases, seed):
     refs = {}
     for _ in range(6):
         _trial(sp, bases, rng, refs)
+
+
+# the RTL-SDR rates of signal/capture.py:83-87 (and two low rates): sample_rate, samples per symbol of the generator so that
+# the decimated stream has a whole number of samples per symbol (the reference samples every int(rate / 18000)-th)
+RATES = [(1.8e6, 98), (1.92e6, 104), (2.048e6, 112), (2.56e6, 140), (2.88e6, 156), (3.2e6, 169), (1.0e6, 52), (240e3, 13)]
+RATE_LENGTHS = [4097, 5000, 12345, 16384, 40000, 65536, 100003, 131072, 200000, 262144, 300001]
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_other_sample_rates_against_the_oracle(gpu_processor, seed):
+    """The exact path (k_exact_block / k_exact_chain) over the valid RTL-SDR rates, block lengths, batch sizes, freq_offsets."""
+    sp = gpu_processor
+    rng = np.random.default_rng(8800 + seed)
+    try:
+        for _ in range(4):
+            fs, sps = RATES[int(rng.integers(0, len(RATES)))]
+            n = int(rng.choice(RATE_LENGTHS))
+            n_car = int(rng.choice([1, 2, 3, 5]))
+            with_fo = bool(rng.integers(0, 2))
+            x = np.stack([synth.carrier_iq(n, seed=3000 + 10 * seed + c, alphabet="centred" if c % 2 else "pi4", snr_db=30.0, sps=sps)
+                          for c in range(n_car)]).astype(np.complex64)
+            fo = np.array([777.7 * (1 + c) for c in range(n_car)]) if with_fo else None
+            sp.sample_rate = fs
+            res = sp.process_batch(x, fo, want_symbols=True, want_match=True)
+            tag = dict(fs=fs, n=n, n_car=n_car, with_fo=with_fo)
+            for c in range(n_car):
+                r = ref_dsp.process(x[c].astype(np.complex128), float(fo[c]) if with_fo else 0.0, fs)
+                nd = int(res["n_dibits"][c])
+                assert nd == len(r["dibits"]) and np.array_equal(res["dibits"][c, :nd], r["dibits"]), (tag, c)
+                assert int(res["best_phase"][c]) == int(r["best_phase"]), (tag, c)
+                if len(r["symbols"]):
+                    s = res["symbols"][c, : len(r["symbols"])].astype(np.complex128)
+                    assert np.abs(s - r["symbols"]).max() / np.abs(r["symbols"]).max() <= SOFT_TOL, (tag, c)
+                if nd >= 11:
+                    assert np.array_equal(res["ts_match"][c, : 2 * nd - 21], ref_dsp.match_counts(ref_dsp.symbols_to_bits(r["dibits"]))), (tag, c)
+    finally:
+        sp.sample_rate = 2.4e6
