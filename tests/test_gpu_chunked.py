@@ -40,14 +40,14 @@ def test_chunked_host_batch_equals_one_piece(gpu_processor, with_fo):
     x = _batch(n_car, n)
     fo = np.linspace(-4000.0, 4000.0, n_car) if with_fo else None
     try:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, -1), "set_h2d_chunk")
+        sp.set_h2d_chunk(-1)
         whole = sp.process_batch(x, fo, want_symbols=True, want_match=True, want_sync=True)
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 1 << 20), "set_h2d_chunk")
+        sp.set_h2d_chunk(1 << 20)
         l0 = sp._lib.tetra_launch_count(sp._ctx)
         chunked = sp.process_batch(x, fo, want_symbols=True, want_match=True, want_sync=True)
         assert sp._lib.tetra_launch_count(sp._ctx) - l0 >= 6 * 3, "the batch did not go through in six chunks"
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)
     _same(whole, chunked)
     for c in (0, 5, 10):
         ref = ref_dsp.process(x[c].astype(np.complex128), float(fo[c]) if with_fo else 0.0, 2.4e6)
@@ -67,12 +67,12 @@ def test_chunked_host_bytes_equal_one_piece(gpu_processor):
     raw = np.clip(np.round((np.stack([x.real, x.imag], axis=-1) / scale * 0.9 + 1.0) * 127.5), 0, 255).astype(np.uint8)
     fo = np.linspace(-3000.0, 3000.0, n_car)
     try:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, -1), "set_h2d_chunk")
+        sp.set_h2d_chunk(-1)
         whole = sp.process_batch_u8(raw, fo, want_symbols=True, want_match=True)
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 1 << 18), "set_h2d_chunk")     # two carriers of bytes per chunk
+        sp.set_h2d_chunk(1 << 18)     # two carriers of bytes per chunk
         chunked = sp.process_batch_u8(raw, fo, want_symbols=True, want_match=True)
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)
     _same(whole, chunked)
     c = 4
     xs = (raw[c].astype(np.float64) / 127.5 - 1.0)
@@ -92,7 +92,7 @@ def test_chunked_padded_rows_through_the_c_abi(gpu_processor):
     out = {}
     try:
         for tag, chunk in (("whole", -1), ("chunked", 2 * pitch * 8)):
-            sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, chunk), "set_h2d_chunk")
+            sp.set_h2d_chunk(chunk)
             dib = np.zeros((n_car, cap), dtype=np.uint8)
             nd = np.zeros(n_car, dtype=np.int32)
             ph = np.zeros(n_car, dtype=np.int32)
@@ -100,7 +100,7 @@ def test_chunked_padded_rows_through_the_c_abi(gpu_processor):
                                                   None, ph.ctypes.data, None, 0), "process_batch")
             out[tag] = (dib, nd, ph)
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)
     for a, b in zip(out["whole"], out["chunked"]):
         assert np.array_equal(a, b)
     ref = ref_dsp.process(x[3, :n].astype(np.complex128), 0.0, 2.4e6)
@@ -119,10 +119,10 @@ def test_more_carriers_than_one_launch_takes(gpu_processor, chunk):
     x = np.ascontiguousarray(base[np.arange(n_car) % 8])
     x[33000] = base[3] * np.complex64(0.5)                 # one carrier beyond the first chunk that differs from its neighbours
     try:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, chunk), "set_h2d_chunk")
+        sp.set_h2d_chunk(chunk)
         res = sp.process_batch(x, None, want_symbols=True, want_match=False)
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)
     for c in (0, 7, 4193, 4194, 32767, 32768, 33000, 39999):
         ref = ref_dsp.process(x[c].astype(np.complex128), 0.0, 2.4e6)
         nd = int(res["n_dibits"][c])
@@ -163,7 +163,7 @@ def test_launches_with_as_many_items_as_ctas(gpu_processor):
     x16 = torch.from_numpy(np.ascontiguousarray(base[np.arange(16) % 2])).pin_memory()
     refs64 = [ref_dsp.process(base[c].astype(np.complex128), 0.0, 2.4e6) for c in range(2)]
     try:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, -1), "set_h2d_chunk")
+        sp.set_h2d_chunk(-1)
         for rep in range(3):
             res = sp.process_batch(x16.numpy(), None, want_symbols=False, want_match=False)
             for c in range(16):
@@ -171,4 +171,4 @@ def test_launches_with_as_many_items_as_ctas(gpu_processor):
                 nd = int(res["n_dibits"][c])
                 assert nd == len(r["dibits"]) and np.array_equal(res["dibits"][c, :nd], r["dibits"]), (rep, c)
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)

@@ -42,11 +42,11 @@ def _trial(sp, bases, rng, refs):
         batch = keep.numpy()
     tag = dict(n_car=n_car, n=n, u8=u8, with_fo=with_fo, pinned=pinned, chunk=chunk)
     try:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, chunk), "set_h2d_chunk")
+        sp.set_h2d_chunk(chunk)
         call = sp.process_batch_u8 if u8 else sp.process_batch
         res = call(batch, fo, want_symbols=True, want_match=True, want_sync=bool(rng.integers(0, 2)))
     finally:
-        sp._check(sp._lib.tetra_set_h2d_chunk(sp._ctx, 0), "set_h2d_chunk")
+        sp.set_h2d_chunk(0)
     for c in range(n_car):
         f = float(fo[c]) if with_fo else 0.0
         key = (int(which[c]), n, u8, f)

@@ -677,15 +677,7 @@ static int process_chunked(tetra_ctx* ctx, const void* in, bool is_u8, int32_t C
                             sync_pos ? sync_pos + c0 * max_pos : nullptr, max_pos, n_sync ? n_sync + c0 : nullptr, async, nullptr,
                             is_u8 ? (const uint8_t*)chunk_in : nullptr, chunk_pitch);
     };
-    if (!host_in) {
-        for (int g = 0; g < n_chunks; ++g) {
-            const int64_t c0 = (int64_t)g * Cc;
-            const int rc = call(c0, (int32_t)std::min<int64_t>(Cc, C - c0), (const uint8_t*)in + c0 * pitch * bps, pitch);
-            if (rc) return rc;
-        }
-        return TETRA_OK;
-    }
-    if (!pipelined) {                                       // host input, copy beside the kernels switched off: chunk by chunk
+    if (!pipelined) {              // device input, or host input with the copy-ahead switched off: chunk by chunk, buffers as they are
         for (int g = 0; g < n_chunks; ++g) {
             const int64_t c0 = (int64_t)g * Cc;
             const int rc = call(c0, (int32_t)std::min<int64_t>(Cc, C - c0), (const uint8_t*)in + c0 * pitch * bps, pitch);

@@ -270,6 +270,12 @@ class SignalProcessor:
             stream = 1                                    # cudaStreamLegacy
         self._check(self._lib.tetra_set_stream(self._ctx, stream), "set_stream")
 
+    def set_h2d_chunk(self, n_bytes: int = 0):
+        """Host batches larger than two chunks go through in chunks of carriers, the host-to-device copy of the chunks ahead
+        beside the kernels of the current one (``tetra_set_h2d_chunk``): chunk size in bytes, 0 = the default (32 MiB),
+        negative = host batches go through in one piece."""
+        self._check(self._lib.tetra_set_h2d_chunk(self._ctx, int(n_bytes)), "set_h2d_chunk")
+
     def process_batch_device(self, iq_ptr: int, n_carriers: int, n_samples: int, pitch: int, dibits_ptr: int,
                              cap: int, n_dibits_ptr: int, symbols_ptr: int = 0, best_phase_ptr: int = 0,
                              ts_match_ptr: int = 0, stream=None, freq_offsets=None):
